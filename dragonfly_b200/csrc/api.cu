@@ -1,0 +1,560 @@
+// C-ABI of libdfb200.so (include/dfb200.h): handle, workspace carve-up and the call sequences.
+// No CPU fallback anywhere: every entry point drives CUDA kernels on the handle's stream.
+#include <stdarg.h>
+#include <new>
+#include "kernels.cuh"
+
+namespace dfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int64_t default_chunk(int64_t npad) {
+  int64_t c = ((int64_t)32 << 20) / npad;   // ~256 MB of K_* rows per chunk
+  c = c / TILE * TILE;
+  if (c < TILE) c = TILE;
+  if (c > 65536) c = 65536;
+  return c;
+}
+
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(char* b) : base(b), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) / 256 * 256;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// One definition of the layout, used both to size the workspace and to carve it.
+static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
+  const int64_t npad = round_up(n_max < 1 ? 1 : n_max, TILE);
+  if (chunk <= 0) chunk = default_chunk(npad);
+  chunk = round_up(chunk, TILE);
+  const int64_t nb = npad / TILE;
+  Carver c(base);
+  double* T = c.take<double>((size_t)(2 * npad + TILE) * npad);
+  double* W = c.take<double>((size_t)npad * npad);
+  double* Dinv = c.take<double>((size_t)TILE * TILE);
+  double* X = c.take<double>((size_t)npad * DFB_MAX_SLOTS);
+  double* yc = c.take<double>((size_t)npad);
+  double* alpha = c.take<double>((size_t)npad);
+  double* tr_xs = c.take<double>((size_t)npad * DFB_MAX_SLOTS);
+  double* tr_nrm = c.take<double>((size_t)npad * DFB_MAX_FACTORS);
+  double* te_xs = c.take<double>((size_t)npad * DFB_MAX_SLOTS);
+  double* te_nrm = c.take<double>((size_t)npad * DFB_MAX_FACTORS);
+  double* Ks = c.take<double>((size_t)chunk * npad);
+  double* partial = c.take<double>((size_t)nb * chunk);
+  double* mu = c.take<double>((size_t)chunk);
+  double* sd = c.take<double>((size_t)chunk);
+  double* score = c.take<double>((size_t)chunk);
+  double* kssv = c.take<double>((size_t)chunk);
+  double* stage = c.take<double>((size_t)chunk * DFB_MAX_SLOTS);
+  double* blk_score = c.take<double>((size_t)chunk / 128 + 16);
+  int64_t* blk_index = c.take<int64_t>((size_t)chunk / 128 + 16);
+  double* best_score = c.take<double>(1);
+  int64_t* best_index = c.take<int64_t>(1);
+  double* red = c.take<double>(8);
+  int* info = c.take<int>(4);
+  dfb_kernel_desc* d0 = c.take<dfb_kernel_desc>(1);
+  dfb_kernel_desc* d1 = c.take<dfb_kernel_desc>(1);
+  dfb_kernel_desc* d2 = c.take<dfb_kernel_desc>(1);
+  if (h != nullptr && base != nullptr) {
+    h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
+    h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
+    h->Ks = Ks; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
+    h->blk_score = blk_score; h->blk_index = blk_index; h->best_score = best_score;
+    h->best_index = best_index; h->red = red; h->info = info;
+    h->d_desc_tr = d0; h->d_desc_te = d1; h->d_desc_tmp = d2;
+    h->n_max = n_max; h->npad_max = npad; h->chunk = chunk;
+  }
+  return c.off + 256;
+}
+
+static int check_desc(const dfb_kernel_desc* d) {
+  if (d == nullptr) { set_error("kernel descriptor is NULL"); return -1; }
+  if (d->n_terms < 1 || d->n_terms > DFB_MAX_TERMS || d->n_factors < 1 ||
+      d->n_factors > DFB_MAX_FACTORS || d->n_slots < 1 || d->n_slots > DFB_MAX_SLOTS) {
+    set_error("kernel descriptor out of range (terms %d, factors %d, slots %d)", d->n_terms,
+              d->n_factors, d->n_slots);
+    return -1;
+  }
+  if (d->term_first_factor[0] != 0 || d->term_first_factor[d->n_terms] != d->n_factors) {
+    set_error("kernel descriptor: term_first_factor does not cover the factors");
+    return -1;
+  }
+  for (int f = 0; f < d->n_factors; f++) {
+    const dfb_factor_desc& fd = d->factors[f];
+    if ((fd.kind != DFB_BASE_SE && fd.kind != DFB_BASE_MATERN) || fd.n_dims < 1 ||
+        fd.slot_off < 0 || fd.slot_off + fd.n_dims > d->n_slots || fd.p < 0 ||
+        fd.p > DFB_MAX_MATERN_P) {
+      set_error("kernel descriptor: bad factor %d", f);
+      return -1;
+    }
+  }
+  for (int s = 0; s < d->n_slots; s++) {
+    if (d->slot_train_coord[s] < 0 || d->slot_train_coord[s] >= d->train_dim ||
+        d->slot_cand_coord[s] < 0 || d->slot_cand_coord[s] >= d->cand_dim ||
+        !(d->slot_bandwidth[s] > 0.0)) {
+      set_error("kernel descriptor: bad slot %d", s);
+      return -1;
+    }
+  }
+  return 0;
+}
+
+#define DFB_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+static int need(dfb_handle* h, bool ws, bool kern, bool train, bool post, bool w) {
+  if (h == nullptr) { set_error("handle is NULL"); return -1; }
+  if (ws && h->ws == nullptr) { set_error("no workspace: call dfb_set_workspace first"); return -1; }
+  if (kern && !h->have_kernel) { set_error("no kernel: call dfb_set_kernel first"); return -1; }
+  if (train && !h->have_train) { set_error("no training data: call dfb_set_train first"); return -1; }
+  if (post && !h->have_post) { set_error("no posterior: call dfb_build_posterior first"); return -1; }
+  if (w && !h->have_w) { set_error("posterior was built LML-only: W = L^-1 is not available"); return -1; }
+  return 0;
+}
+
+static int ensure_train_scaled(dfb_handle* h) {
+  if (!h->tr_prepped) {
+    DFB_TRY(launch_prep_scaled(h, h->d_desc_tr, 1, h->X, h->n, h->d, h->tr.xs, h->tr.nrm, h->npad));
+    h->tr_prepped = true;
+  }
+  return 0;
+}
+
+static int ensure_test_scaled(dfb_handle* h) {
+  if (h->have_test_kernel && !h->te_prepped) {
+    DFB_TRY(launch_prep_scaled(h, h->d_desc_te, 1, h->X, h->n, h->d, h->te.xs, h->te.nrm, h->npad));
+    h->te_prepped = true;
+  }
+  return 0;
+}
+
+// The blocked right-looking factorisation of the tall matrix [A ; I ; y^T] (see gemm.cuh):
+// top -> L, bottom -> L^-T, y row -> (L^-1 y)^T.
+static int factorise_tall(dfb_handle* h, double* T, int64_t npad, double* Dinv, int* info,
+                          bool with_bottom) {
+  const int nb = (int)(npad / TILE);
+  for (int step = 0; step < nb; step++) {
+    DFB_TRY(launch_chol_diag(h, T, npad, step, Dinv, info));
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = T; g.lda = npad; g.B = Dinv; g.ldb = TILE; g.D = T; g.ldd = npad;
+    g.alpha = 1.0; g.mode = MODE_PANEL; g.K = TILE; g.step = step; g.nb = nb; g.info = info;
+    g.skip_bottom = with_bottom ? 0 : 1;
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, 2 * nb + 1 - (step + 1)));
+    const int ncols = nb - step - 1;
+    if (ncols > 0) {
+      g.mode = MODE_TRAIL; g.alpha = -1.0; g.B = nullptr; g.ldb = npad;
+      DFB_TRY(launch_gemm(h, g, EPI_STORE, (2 * nb + 1 - (step + 1)) * ncols));
+    }
+  }
+  return 0;
+}
+
+// ---- optional per-class event timing -------------------------------------------------------------
+static int prof_flush(dfb_handle* h, int cls) {
+  ProfClass& pc = h->prof[cls];
+  if (pc.n == 0) return 0;
+  DFB_CUDA_OK(cudaEventSynchronize(pc.stop[pc.n - 1]));
+  for (int i = 0; i < pc.n; i++) {
+    float ms = 0.f;
+    DFB_CUDA_OK(cudaEventElapsedTime(&ms, pc.start[i], pc.stop[i]));
+    pc.acc_ms += ms;
+    pc.acc_units += pc.units[i];
+    pc.acc_launches += 1;
+  }
+  pc.n = 0;
+  return 0;
+}
+static int prof_begin(dfb_handle* h, int cls) {
+  if (!h->prof_on) return 0;
+  ProfClass& pc = h->prof[cls];
+  if (!pc.created) {
+    for (int i = 0; i < PROF_RING; i++) {
+      DFB_CUDA_OK(cudaEventCreate(&pc.start[i]));
+      DFB_CUDA_OK(cudaEventCreate(&pc.stop[i]));
+    }
+    pc.created = true;
+  }
+  if (pc.n == PROF_RING) DFB_TRY(prof_flush(h, cls));
+  DFB_CUDA_OK(cudaEventRecord(pc.start[pc.n], h->stream));
+  return 0;
+}
+static int prof_end(dfb_handle* h, int cls, double units) {
+  if (!h->prof_on) return 0;
+  ProfClass& pc = h->prof[cls];
+  DFB_CUDA_OK(cudaEventRecord(pc.stop[pc.n], h->stream));
+  pc.units[pc.n] = units;
+  pc.n++;
+  return 0;
+}
+
+struct ChunkOut {
+  double* mu; double* sd; double* score;   // user pointers (space given), may be NULL
+};
+
+// Scores m candidates chunk by chunk: K_* rows + mu -> |L^-1 k_*|^2 -> sd / acquisition / arg-max.
+static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, int64_t m, int32_t dc,
+                      int32_t space, double mean_const, ChunkOut out, bool want_std, bool do_argmax) {
+  const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
+  const dfb_kernel_desc* d_desc = h->have_test_kernel ? h->d_desc_te : h->d_desc_tr;
+  const ScaledSet& ss = h->have_test_kernel ? h->te : h->tr;
+  if (dc != desc.cand_dim) {
+    set_error("candidates have %d columns, the kernel descriptor expects %d", dc, desc.cand_dim);
+    return -1;
+  }
+  if (space == DFB_HOST && dc > DFB_MAX_SLOTS) { set_error("host candidates: dc > %d", DFB_MAX_SLOTS); return -1; }
+  DFB_TRY(ensure_train_scaled(h));
+  DFB_TRY(ensure_test_scaled(h));
+  const int64_t npad = h->npad, Mc = h->chunk;
+  const int nb = (int)(npad / TILE);
+  if (do_argmax) DFB_TRY(launch_reset_best(h));
+  for (int64_t c0 = 0; c0 < m; c0 += Mc) {
+    const int64_t mc = (m - c0 < Mc) ? (m - c0) : Mc;
+    const int64_t m_rows = round_up(mc, TILE);
+    const double* xc_dev;
+    if (space == DFB_HOST) {
+      DFB_CUDA_OK(cudaMemcpyAsync(h->stage, Xc + c0 * dc, sizeof(double) * mc * dc,
+                                  cudaMemcpyHostToDevice, h->stream));
+      xc_dev = h->stage;
+    } else {
+      xc_dev = Xc + c0 * dc;
+    }
+    double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : h->mu;
+    double* sd_dev = (space == DFB_DEVICE && out.sd) ? out.sd + c0 : h->sd;
+    double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0 : (out.score ? h->score : nullptr);
+    DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
+    DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
+                         h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
+    DFB_TRY(prof_end(h, DFB_PROF_KSTAR, (double)mc));
+    if (want_std) {
+      GemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.A = h->W; g.lda = npad; g.B = h->Ks; g.ldb = npad; g.mode = MODE_SCORE;
+      g.n_rb = nb; g.n_cb = (int)(m_rows / TILE); g.K = (int)npad;
+      g.partial = h->partial; g.ld_partial = Mc;
+      DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
+      DFB_TRY(launch_gemm(h, g, EPI_SUMSQ, g.n_rb * g.n_cb));
+      DFB_TRY(prof_end(h, DFB_PROF_GEMM, (double)mc));
+    }
+    if (want_std || do_argmax || sc_dev != nullptr) {
+      DFB_TRY(prof_begin(h, DFB_PROF_ACQ));
+      DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, Mc, nb, h->kssv, mc, c0, want_std ? 1 : 0,
+                         want_std ? sd_dev : nullptr, sc_dev, do_argmax));
+      DFB_TRY(prof_end(h, DFB_PROF_ACQ, (double)mc));
+    }
+    if (space == DFB_HOST) {
+      if (out.mu)
+        DFB_CUDA_OK(cudaMemcpyAsync(out.mu + c0, mu_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+      if (out.sd && want_std)
+        DFB_CUDA_OK(cudaMemcpyAsync(out.sd + c0, sd_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+      if (out.score)
+        DFB_CUDA_OK(cudaMemcpyAsync(out.score + c0, sc_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  return 0;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_version(void) { return DFB_VERSION; }
+
+const char* dfb_last_error(void) { return g_err; }
+
+int dfb_create(dfb_handle** out, int device) {
+  if (out == nullptr) { set_error("out is NULL"); return -1; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no CUDA device visible (%s): libdfb200 has no CPU fallback", cudaGetErrorString(e));
+    return -2;
+  }
+  if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DFB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; libdfb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return -2;
+  }
+  dfb_handle* h = new (std::nothrow) dfb_handle();
+  if (h == nullptr) { set_error("out of host memory"); return -2; }
+  h->device = device;
+  *out = h;
+  return 0;
+}
+
+void dfb_destroy(dfb_handle* h) {
+  if (h == nullptr) return;
+  if (h->prof != nullptr) {
+    for (int c = 0; c < PROF_CLASSES; c++)
+      if (h->prof[c].created)
+        for (int i = 0; i < PROF_RING; i++) { cudaEventDestroy(h->prof[c].start[i]); cudaEventDestroy(h->prof[c].stop[i]); }
+    delete[] h->prof;
+  }
+  delete h;
+}
+
+int dfb_set_stream(dfb_handle* h, void* cuda_stream) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+
+size_t dfb_workspace_bytes(int64_t n_max, int32_t n_slots, int64_t chunk) {
+  (void)n_slots;
+  return carve(nullptr, nullptr, n_max, chunk);
+}
+
+int dfb_set_workspace(dfb_handle* h, void* workspace_dev, size_t bytes, int64_t n_max, int64_t chunk) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (workspace_dev == nullptr || n_max < 1) { set_error("bad workspace arguments"); return -1; }
+  const size_t want = carve(nullptr, nullptr, n_max, chunk);
+  if (bytes < want) { set_error("workspace too small: %zu bytes given, %zu needed", bytes, want); return -1; }
+  if ((reinterpret_cast<uintptr_t>(workspace_dev) & 255) != 0) { set_error("workspace must be 256-byte aligned"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  h->ws = static_cast<char*>(workspace_dev);
+  h->ws_bytes = bytes;
+  carve(h, h->ws, n_max, chunk);
+  h->have_train = h->have_post = h->have_w = false;
+  h->tr_prepped = h->te_prepped = false;
+  if (h->have_kernel)
+    DFB_CUDA_OK(cudaMemcpyAsync(h->d_desc_tr, &h->desc_tr, sizeof(dfb_kernel_desc), cudaMemcpyHostToDevice, h->stream));
+  if (h->have_test_kernel)
+    DFB_CUDA_OK(cudaMemcpyAsync(h->d_desc_te, &h->desc_te, sizeof(dfb_kernel_desc), cudaMemcpyHostToDevice, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dfb_set_kernel(dfb_handle* h, const dfb_kernel_desc* desc) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  DFB_TRY(check_desc(desc));
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));   // the pageable host copy below must not race
+  h->desc_tr = *desc;
+  DFB_CUDA_OK(cudaMemcpyAsync(h->d_desc_tr, &h->desc_tr, sizeof(dfb_kernel_desc), cudaMemcpyHostToDevice, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->have_kernel = true;
+  h->tr_prepped = false;
+  h->have_post = h->have_w = false;
+  return 0;
+}
+
+int dfb_set_test_kernel(dfb_handle* h, const dfb_kernel_desc* desc) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  if (desc == nullptr) { h->have_test_kernel = false; h->te_prepped = false; return 0; }
+  DFB_TRY(check_desc(desc));
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->desc_te = *desc;
+  DFB_CUDA_OK(cudaMemcpyAsync(h->d_desc_te, &h->desc_te, sizeof(dfb_kernel_desc), cudaMemcpyHostToDevice, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->have_test_kernel = true;
+  h->te_prepped = false;
+  return 0;
+}
+
+int dfb_set_train(dfb_handle* h, const double* X_dev, int64_t n, int32_t d, const double* y_centred_dev) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  if (n < 1 || n > h->n_max) { set_error("n = %lld outside [1, n_max = %lld]", (long long)n, (long long)h->n_max); return -1; }
+  if (d < 1 || d > DFB_MAX_SLOTS) { set_error("d = %d outside [1, %d]", d, DFB_MAX_SLOTS); return -1; }
+  if (X_dev == nullptr || y_centred_dev == nullptr) { set_error("X / y pointer is NULL"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  h->n = n; h->d = d; h->npad = round_up(n, TILE);
+  DFB_CUDA_OK(cudaMemcpyAsync(h->X, X_dev, sizeof(double) * n * d, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_TRY(launch_copy_pad(h, y_centred_dev, n, h->yc, h->npad));
+  DFB_TRY(launch_fill(h, h->alpha, h->npad, 0.0));
+  h->have_train = true;
+  h->tr_prepped = h->te_prepped = false;
+  h->have_post = h->have_w = false;
+  return 0;
+}
+
+int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t flags, double* lml_out_host) {
+  DFB_TRY(need(h, true, true, true, false, false));
+  if (h->desc_tr.train_dim != h->d) { set_error("kernel train_dim %d != data dim %d", h->desc_tr.train_dim, h->d); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  const int64_t n = h->n, npad = h->npad;
+  const bool with_bottom = (flags != DFB_BUILD_LML_ONLY);
+  h->have_post = h->have_w = false;
+  DFB_TRY(prof_begin(h, DFB_PROF_BUILD));
+  DFB_CUDA_OK(cudaMemsetAsync(h->info, 0, sizeof(int) * 4, h->stream));
+  DFB_CUDA_OK(cudaMemsetAsync(h->T, 0, sizeof(double) * (size_t)(2 * npad + TILE) * npad, h->stream));
+  DFB_TRY(ensure_train_scaled(h));
+  // K(X, X): GP._get_training_kernel_matrix (gp_core.py:149-153)
+  DFB_TRY(launch_kstar(h, h->d_desc_tr, h->desc_tr, 1, h->tr.xs, h->tr.nrm, npad, nullptr, h->X, n, h->d,
+                       n, h->T, npad, n, npad, 0.0, nullptr, nullptr));
+  DFB_TRY(launch_init_tall(h, h->T, n, npad, noise_var + jitter, h->yc, with_bottom ? 1 : 0));
+  DFB_TRY(factorise_tall(h, h->T, npad, h->Dinv, h->info, with_bottom));
+  const double* Wt = h->T + (size_t)npad * npad;
+  const double* v = h->T + (size_t)2 * npad * npad;
+  if (with_bottom) DFB_TRY(launch_transpose(h, Wt, h->W, npad));
+  if (flags == DFB_BUILD_FULL) DFB_TRY(launch_alpha(h, Wt, v, h->alpha, n, npad));
+  DFB_TRY(launch_lml_reduce(h, h->T, h->yc, flags == DFB_BUILD_FULL ? h->alpha : nullptr, v, n, npad, h->red));
+  DFB_TRY(prof_end(h, DFB_PROF_BUILD, 1.0));
+  double red[3];
+  int info = 0;
+  DFB_CUDA_OK(cudaMemcpyAsync(red, h->red, sizeof(red), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(&info, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->max_diag = h->desc_tr.kss + noise_var;
+  if (info != 0) {
+    set_error("matrix is not positive definite: non-positive pivot at index %d", info - 1);
+    return info;
+  }
+  h->noise_plus_jitter = noise_var + jitter;
+  h->have_post = true;
+  h->have_w = with_bottom;
+  if (lml_out_host != nullptr) {
+    const double quad = (flags == DFB_BUILD_FULL) ? red[1] : red[2];
+    *lml_out_host = -0.5 * quad - red[0] - 0.5 * (double)n * log(2.0 * M_PI);
+  }
+  return 0;
+}
+
+int dfb_get_max_diag(dfb_handle* h, double* out_host) {
+  DFB_TRY(need(h, true, true, true, false, false));
+  if (out_host == nullptr) { set_error("out is NULL"); return -1; }
+  *out_host = h->max_diag;
+  return 0;
+}
+
+int dfb_get_state(dfb_handle* h, double* L_dev, double* alpha_dev, double* K_dev) {
+  DFB_TRY(need(h, true, true, true, true, false));
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  if (L_dev) DFB_TRY(launch_extract_lower(h, h->T, h->npad, L_dev, h->n));
+  if (alpha_dev) DFB_TRY(launch_copy_pad(h, h->alpha, h->n, alpha_dev, h->n));
+  if (K_dev)
+    DFB_TRY(launch_kstar(h, h->d_desc_tr, h->desc_tr, 1, h->tr.xs, h->tr.nrm, h->npad, nullptr, h->X, h->n,
+                         h->d, h->n, K_dev, h->n, h->n, h->n, 0.0, nullptr, nullptr));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dfb_set_alpha(dfb_handle* h, const double* alpha_dev, int64_t n) {
+  DFB_TRY(need(h, true, true, true, false, false));
+  if (alpha_dev == nullptr || n < 0 || n > h->n) { set_error("bad alpha arguments"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_TRY(launch_copy_pad(h, alpha_dev, n, h->alpha, h->npad));
+  return 0;
+}
+
+int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t space, double mean_const,
+             double* mu, double* sd) {
+  DFB_TRY(need(h, true, true, true, true, sd != nullptr));
+  if (m < 0 || (m > 0 && (Xc == nullptr || mu == nullptr))) { set_error("bad eval arguments"); return -1; }
+  if (m == 0) return 0;
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  dfb_acq_desc acq;
+  memset(&acq, 0, sizeof(acq));
+  acq.kind = DFB_ACQ_MEAN;
+  ChunkOut out = {mu, sd, nullptr};
+  DFB_TRY(run_chunks(h, acq, Xc, m, dc, space, mean_const, out, sd != nullptr, false));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, int64_t m, int32_t dc,
+                     int32_t space, double mean_const, double* scores, double* best_score_host,
+                     int64_t* best_index_host) {
+  if (acq == nullptr) { set_error("acq is NULL"); return -1; }
+  const bool want_std = (acq->kind != DFB_ACQ_MEAN);
+  DFB_TRY(need(h, true, true, true, true, want_std));
+  if (m < 1 || Xc == nullptr) { set_error("bad score arguments (m = %lld)", (long long)m); return -1; }
+  if (acq->kind < DFB_ACQ_MEAN || acq->kind > DFB_ACQ_TTEI) { set_error("unknown acquisition kind %d", acq->kind); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  ChunkOut out = {nullptr, nullptr, scores};
+  DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, want_std, true));
+  double bs = 0.0;
+  int64_t bi = -1;
+  DFB_CUDA_OK(cudaMemcpyAsync(&bs, h->best_score, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(&bi, h->best_index, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (best_score_host) *best_score_host = bs;
+  if (best_index_host) *best_index_host = bi;
+  return 0;
+}
+
+int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,
+                      int32_t d1, const double* X2_dev, int64_t n2, int32_t d2, double* K_dev) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  DFB_TRY(check_desc(desc));
+  if (n1 < 1 || n2 < 1 || X1_dev == nullptr || X2_dev == nullptr || K_dev == nullptr) { set_error("bad kernel_matrix arguments"); return -1; }
+  if (d1 != d2 || d1 != desc->train_dim) { set_error("kernel_matrix: dims %d, %d vs kernel train_dim %d", d1, d2, desc->train_dim); return -1; }
+  const int64_t np2 = round_up(n2, TILE);
+  if (np2 > h->npad_max) { set_error("kernel_matrix: n2 = %lld exceeds the workspace (n_max = %lld)", (long long)n2, (long long)h->n_max); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->desc_tmp = *desc;
+  DFB_CUDA_OK(cudaMemcpyAsync(h->d_desc_tmp, &h->desc_tmp, sizeof(dfb_kernel_desc), cudaMemcpyHostToDevice, h->stream));
+  h->te_prepped = false;   // the test-kernel scaled set is used as scratch
+  DFB_TRY(launch_prep_scaled(h, h->d_desc_tmp, 1, X2_dev, n2, d2, h->te.xs, h->te.nrm, np2));
+  DFB_TRY(launch_kstar(h, h->d_desc_tmp, h->desc_tmp, 1, h->te.xs, h->te.nrm, np2, nullptr, X1_dev, n1, d1,
+                       n1, K_dev, n2, n2, n2, 0.0, nullptr, nullptr));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
+                   double* mu_dev, double* covar_dev) {
+  (void)h; (void)Xc_dev; (void)m; (void)dc; (void)mean_const; (void)mu_dev; (void)covar_dev;
+  set_error("dfb_eval_covar: not implemented in this build");
+  return -3;
+}
+
+int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
+                 const double* U_dev, int32_t S, double jitter, double* samples_dev, double* max_diag_host) {
+  (void)h; (void)Xc_dev; (void)m; (void)dc; (void)mean_const; (void)U_dev; (void)S; (void)jitter;
+  (void)samples_dev; (void)max_diag_host;
+  set_error("dfb_ts_draws: not implemented in this build");
+  return -3;
+}
+
+int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }
+
+int dfb_profile_enable(dfb_handle* h, int on) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  if (on && h->prof == nullptr) {
+    h->prof = new (std::nothrow) ProfClass[PROF_CLASSES];
+    if (h->prof == nullptr) { set_error("out of host memory"); return -2; }
+  }
+  h->prof_on = (on != 0);
+  return 0;
+}
+
+int dfb_profile_read(dfb_handle* h, int cls, double* ms_total, int64_t* launches, double* units) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (cls < 0 || cls >= PROF_CLASSES || h->prof == nullptr) { set_error("profiling not enabled / bad class"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_TRY(prof_flush(h, cls));
+  ProfClass& pc = h->prof[cls];
+  if (ms_total) *ms_total = pc.acc_ms;
+  if (launches) *launches = pc.acc_launches;
+  if (units) *units = pc.acc_units;
+  pc.acc_ms = 0.0; pc.acc_units = 0.0; pc.acc_launches = 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Shared declarations for libdfb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/dfb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdfb200 is written for sm_100a (B200) only"
+#endif
+
+namespace dfb {
+
+constexpr int TILE = 128;            // block size of every blocked algorithm (rows/cols)
+constexpr int GEMM_BK = 16;          // k-extent of one pipeline stage (16 doubles = 128 B per row)
+
+void set_error(const char* fmt, ...);
+
+#define DFB_CUDA_OK(expr)                                                               \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      dfb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side view of the posterior state and the workspace carve-up.
+// ------------------------------------------------------------------------------------------------
+struct ScaledSet {        // scaled training coordinates for one kernel descriptor (SoA, j contiguous)
+  double* xs;             // [n_slots][npad]    x~ = x[coord] / bw
+  double* nrm;            // [n_factors][npad]  |x~|^2 per factor
+};
+
+}  // namespace dfb
+
+namespace dfb {
+constexpr int PROF_CLASSES = 4;
+constexpr int PROF_RING = 1024;
+struct ProfClass {
+  cudaEvent_t start[PROF_RING];
+  cudaEvent_t stop[PROF_RING];
+  double units[PROF_RING];
+  int n = 0;
+  bool created = false;
+  double acc_ms = 0.0, acc_units = 0.0;
+  int64_t acc_launches = 0;
+};
+}  // namespace dfb
+
+// The opaque handle of the C-ABI.
+struct dfb_handle {
+  bool prof_on = false;
+  dfb::ProfClass* prof = nullptr;   // [PROF_CLASSES], allocated on first enable
+
+  int device = 0;
+  cudaStream_t stream = 0;
+  int64_t launches = 0;
+
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t n_max = 0, npad_max = 0, chunk = 0;
+
+  // carved pointers (see api.cu: carve())
+  double* T = nullptr;        // tall factorisation matrix: (2*npad + TILE) x npad
+  double* W = nullptr;        // L^-1, npad x npad, lower triangular, row-major
+  double* Dinv = nullptr;     // TILE x TILE inverse of the current diagonal block
+  double* X = nullptr;        // n x d training inputs (copy)
+  double* yc = nullptr;       // npad centred targets (zero padded)
+  double* alpha = nullptr;    // npad (zero padded)
+  dfb::ScaledSet tr;          // scaled set for the GP kernel
+  dfb::ScaledSet te;          // scaled set for the test kernel (Add-UCB)
+  double* Ks = nullptr;       // chunk x npad  K_* rows of the current candidate chunk
+  double* partial = nullptr;  // (npad/TILE) x chunk  per-row-block |v|^2 partial sums
+  double* mu = nullptr;       // chunk
+  double* sd = nullptr;       // chunk
+  double* score = nullptr;    // chunk
+  double* kssv = nullptr;     // chunk  k(x*, x*) per candidate
+  double* stage = nullptr;    // chunk x DFB_MAX_SLOTS host-candidate staging
+  double* blk_score = nullptr;  // per-block arg-max scratch
+  int64_t* blk_index = nullptr;
+  double* best_score = nullptr;  // running best (device)
+  int64_t* best_index = nullptr;
+  double* red = nullptr;      // small reduction scratch (4 doubles)
+  int* info = nullptr;        // factorisation status
+  dfb_kernel_desc* d_desc_tr = nullptr;
+  dfb_kernel_desc* d_desc_te = nullptr;
+  dfb_kernel_desc* d_desc_tmp = nullptr;
+
+  // model state
+  dfb_kernel_desc desc_tr;
+  dfb_kernel_desc desc_te;
+  dfb_kernel_desc desc_tmp;
+  bool tr_prepped = false, te_prepped = false;
+  bool have_kernel = false, have_test_kernel = false, have_train = false, have_post = false;
+  bool have_w = false;
+  int64_t n = 0, npad = 0;
+  int32_t d = 0;
+  double noise_plus_jitter = 0.0;
+  double max_diag = 0.0;
+};

@@ -1,0 +1,719 @@
+// CUDA kernels of libdfb200.so other than the DMMA GEMM core (gemm.cuh): kernel-matrix builds,
+// the diagonal-block Cholesky/inverse, small vector kernels and the acquisition + arg-max.
+// sm_100a only.  Reference paths are relative to the reference tree (dragonfly-opt 0.1.7).
+#include "kernels.cuh"
+
+namespace dfb {
+
+// ================================================================================================
+// Kernel evaluation in the reference's operation order (include/dfb200.h, "kernel descriptor").
+// ================================================================================================
+__device__ __forceinline__ double base_kernel_value(const dfb_factor_desc& f, double d2) {
+  if (f.kind == DFB_BASE_SE) {
+    // scale * np.exp(-dist_sq / 2)                                        kernel.py:176
+    return __dmul_rn(f.scale, exp(__dmul_rn(d2, -0.5)));
+  }
+  // Matern: dist = sqrt(D2); kernel.py:259-270, 292-299
+  const double dist = sqrt(d2);
+  const double mm = __dmul_rn(f.s8, dist);
+  double u = 0.0;
+  const int p = f.p;
+  for (int i = 0; i <= p; i++) {
+    const int e = p - i;
+    double pw;
+    if (e == 0) pw = 1.0;
+    else if (e == 1) pw = mm;
+    else if (e == 2) pw = __dmul_rn(mm, mm);
+    else pw = pow(mm, (double)e);
+    u = __dadd_rn(u, __dmul_rn(f.coeffs[i], pw));
+  }
+  const double w = __dmul_rn(f.gamma_ratio, exp(__dmul_rn(-f.s2, dist)));
+  u = __dmul_rn(u, w);
+  return __dmul_rn(f.scale, u);
+}
+
+// (X**2).sum(axis=1) in NumPy's own association order (general_utils.py:66-67): add.reduce seeds the
+// output with the first element and adds pairwise_sum(rest): sequential from 0 for fewer than 8
+// remaining elements, else eight interleaved accumulators combined as ((r0+r1)+(r2+r3)) +
+// ((r4+r5)+(r6+r7)) plus a sequential tail (n <= 128: no recursive split).  Matching it keeps the
+// rounding noise of D2(x, x) = (|x|^2 + |x|^2) - 2 x.x -- which sqrt() amplifies to ~1e-8 for
+// Matern-1/2 -- identical to the reference's.
+template <typename F>
+__device__ __forceinline__ double numpy_sumsq(int n, F get) {
+  if (n <= 0) return 0.0;
+  const double x0 = get(0);
+  const double first = __dmul_rn(x0, x0);
+  const int m = n - 1;
+  if (m == 0) return first;
+  double res;
+  if (m < 8) {
+    res = 0.0;
+    for (int i = 0; i < m; i++) { const double v = get(1 + i); res = __dadd_rn(res, __dmul_rn(v, v)); }
+  } else {
+    double r[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const double v = get(1 + q); r[q] = __dmul_rn(v, v); }
+    int i = 8;
+    for (; i < m - (m % 8); i += 8) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) { const double v = get(1 + i + q); r[q] = __dadd_rn(r[q], __dmul_rn(v, v)); }
+    }
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < m; i++) { const double v = get(1 + i); res = __dadd_rn(res, __dmul_rn(v, v)); }
+  }
+  return __dadd_rn(first, res);
+}
+
+// ---- scaled training set: x~ = x / bw (SoA, j contiguous) and per-factor squared norms ----------
+// SEKernel.get_scaled_repr (kernel.py:179-181) + the (X2**2).sum(axis=1) of dist_squared
+// (general_utils.py:66).
+__global__ void prep_scaled_kernel(const dfb_kernel_desc* __restrict__ desc, int use_train_coords,
+                                   const double* __restrict__ X, int64_t n, int d, double* xs,
+                                   double* nrm, int64_t npad) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  const int nf = desc->n_factors;
+  for (int f = 0; f < nf; f++) {
+    const dfb_factor_desc& fd = desc->factors[f];
+    for (int q = 0; q < fd.n_dims; q++) {
+      const int slot = fd.slot_off + q;
+      double v = 0.0;
+      if (j < n) {
+        const int coord = use_train_coords ? desc->slot_train_coord[slot] : desc->slot_cand_coord[slot];
+        v = X[j * d + coord] / desc->slot_bandwidth[slot];
+      }
+      xs[(int64_t)slot * npad + j] = v;
+    }
+    nrm[(int64_t)f * npad + j] = numpy_sumsq(fd.n_dims, [&](int q) {
+      return xs[(int64_t)(fd.slot_off + q) * npad + j];
+    });
+  }
+}
+
+// ---- K_* rows for a block of candidates, fused with mu = mean + K_* alpha -----------------------
+// Kernel.__call__(X_test, X) (kernel.py:72-83) + K_tetr.dot(alpha) (gp_core.py:173-174).
+// One warp owns KSTAR_R candidate rows; its lanes stride over the training points so that the
+// stores of each K_* row are 256 B coalesced and the training coordinates are read once per
+// KSTAR_R rows.  The alpha-weighted row sum is reduced with warp shuffles.
+constexpr int KSTAR_R = 2;
+constexpr int KSTAR_WARPS = 8;
+constexpr int KSTAR_CANDS = KSTAR_R * KSTAR_WARPS;
+
+__global__ void __launch_bounds__(KSTAR_WARPS * 32)
+kstar_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coords,
+             const double* __restrict__ xsT, const double* __restrict__ nrmT, int64_t npad_tr,
+             const double* __restrict__ alpha, const double* __restrict__ Xc, int64_t m, int dc,
+             int64_t m_rows, double* __restrict__ Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
+             double mean_const, double* __restrict__ mu, double* __restrict__ kss_out) {
+  extern __shared__ __align__(16) unsigned char kraw[];
+  dfb_kernel_desc* desc = reinterpret_cast<dfb_kernel_desc*>(kraw);
+  {
+    const int nwords = sizeof(dfb_kernel_desc) / 4;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(desc_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(kraw);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int ns = desc->n_slots, nf = desc->n_factors, nt = desc->n_terms;
+  double* xc = reinterpret_cast<double*>(kraw + ((sizeof(dfb_kernel_desc) + 15) / 16) * 16);
+  double* nc = xc + KSTAR_CANDS * ns;
+  const int64_t base = (int64_t)blockIdx.x * KSTAR_CANDS;
+
+  for (int idx = threadIdx.x; idx < KSTAR_CANDS * ns; idx += blockDim.x) {
+    const int r = idx / ns, s = idx - r * ns;
+    const int64_t cand = base + r;
+    double v = 0.0;
+    if (cand < m) {
+      const int coord = cand_uses_train_coords ? desc->slot_train_coord[s] : desc->slot_cand_coord[s];
+      v = Xc[cand * dc + coord] / desc->slot_bandwidth[s];
+    }
+    xc[idx] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < KSTAR_CANDS * nf; idx += blockDim.x) {
+    const int r = idx / nf, f = idx - r * nf;
+    const dfb_factor_desc& fd = desc->factors[f];
+    nc[idx] = numpy_sumsq(fd.n_dims, [&](int q) { return xc[r * ns + fd.slot_off + q]; });
+  }
+  __syncthreads();
+  // k(x*, x*) the way the reference gets it: the diagonal of kernel(X_test, X_test)
+  // (gp_core.py:179), i.e. through D2(x, x) = (|x|^2 + |x|^2) - 2 x.x with its rounding noise.
+  if (kss_out != nullptr && threadIdx.x < KSTAR_CANDS) {
+    const int r = threadIdx.x;
+    const int64_t cand = base + r;
+    if (cand < m) {
+      double sum = 0.0;
+      for (int t = 0; t < nt; t++) {
+        double prod = desc->term_pre_scale[t];
+        for (int f = desc->term_first_factor[t]; f < desc->term_first_factor[t + 1]; f++) {
+          const dfb_factor_desc& fd = desc->factors[f];
+          double dot = 0.0;
+          for (int q = 0; q < fd.n_dims; q++) {
+            const double v = xc[r * ns + fd.slot_off + q];
+            dot = fma(v, v, dot);
+          }
+          const double nn = nc[r * nf + f];
+          double d2 = __dadd_rn(__dadd_rn(nn, nn), -2.0 * dot);
+          d2 = fmax(d2, 0.0);
+          prod = __dmul_rn(prod, base_kernel_value(fd, d2));
+        }
+        sum = __dadd_rn(sum, prod);
+      }
+      kss_out[cand] = __dmul_rn(desc->post_scale, sum);
+    }
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = warp * KSTAR_R;
+  const int64_t cand0 = base + r0;
+  if (cand0 >= m_rows) return;
+  double mu_acc[KSTAR_R];
+#pragma unroll
+  for (int r = 0; r < KSTAR_R; r++) mu_acc[r] = 0.0;
+  const double post = desc->post_scale;
+
+  for (int64_t j = lane; j < n_write; j += 32) {
+    double kv[KSTAR_R];
+#pragma unroll
+    for (int r = 0; r < KSTAR_R; r++) kv[r] = 0.0;
+    if (j < n_valid) {
+      double sum[KSTAR_R];
+#pragma unroll
+      for (int r = 0; r < KSTAR_R; r++) sum[r] = 0.0;
+      for (int t = 0; t < nt; t++) {
+        double prod[KSTAR_R];
+#pragma unroll
+        for (int r = 0; r < KSTAR_R; r++) prod[r] = desc->term_pre_scale[t];
+        for (int f = desc->term_first_factor[t]; f < desc->term_first_factor[t + 1]; f++) {
+          const dfb_factor_desc& fd = desc->factors[f];
+          double dot[KSTAR_R];
+#pragma unroll
+          for (int r = 0; r < KSTAR_R; r++) dot[r] = 0.0;
+          for (int q = 0; q < fd.n_dims; q++) {
+            const int s = fd.slot_off + q;
+            const double xt = xsT[(int64_t)s * npad_tr + j];
+#pragma unroll
+            for (int r = 0; r < KSTAR_R; r++) dot[r] = fma(xc[(r0 + r) * ns + s], xt, dot[r]);
+          }
+          const double nt2 = nrmT[(int64_t)f * npad_tr + j];
+#pragma unroll
+          for (int r = 0; r < KSTAR_R; r++) {
+            // (|y|^2 + |x|^2) - 2 x.y, clipped at 0                      general_utils.py:66-69
+            double d2 = __dadd_rn(__dadd_rn(nt2, nc[(r0 + r) * nf + f]), -2.0 * dot[r]);
+            d2 = fmax(d2, 0.0);
+            prod[r] = __dmul_rn(prod[r], base_kernel_value(fd, d2));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < KSTAR_R; r++) sum[r] = __dadd_rn(sum[r], prod[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < KSTAR_R; r++) kv[r] = __dmul_rn(post, sum[r]);
+    }
+    const double aj = (alpha != nullptr && j < n_valid) ? alpha[j] : 0.0;
+#pragma unroll
+    for (int r = 0; r < KSTAR_R; r++) {
+      const int64_t cand = cand0 + r;
+      if (cand < m_rows) {
+        const double v = (cand < m) ? kv[r] : 0.0;
+        Ks[cand * ldk + j] = v;
+        mu_acc[r] = fma(v, aj, mu_acc[r]);
+      }
+    }
+  }
+  if (mu != nullptr) {
+#pragma unroll
+    for (int r = 0; r < KSTAR_R; r++) {
+      double s = mu_acc[r];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int64_t cand = cand0 + r;
+      if (lane == 0 && cand < m) mu[cand] = mean_const + s;
+    }
+  }
+}
+
+// ---- tall factorisation matrix set-up -------------------------------------------------------------
+// T = [ K + (noise + jitter) I (padded with identity) ; I ; y_c^T (row 0 of the last block) ].
+__global__ void init_tall_kernel(double* T, int64_t n, int64_t npad, double diag_add,
+                                 const double* __restrict__ yc, int with_bottom) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  if (i < n) T[i * npad + i] += diag_add;       // K_trtr_wo_noise + noise_var * np.eye (gp_core.py:843)
+  else T[i * npad + i] = 1.0;
+  if (with_bottom) T[(npad + i) * npad + i] = 1.0;
+  T[2 * npad * npad + i] = (i < n) ? yc[i] : 0.0;
+}
+
+// ---- diagonal block: Cholesky factor AND its inverse in one pass ---------------------------------------
+// Factorises the 128 x 128 block T[step] in place (lower) and writes W_kk = L_kk^-1 (lower) to
+// Dinv.  The inverse costs no extra storage: the same right-looking elimination is applied to the
+// virtual tall block [A_kk ; I]; the strictly-upper triangle of the shared array holds the evolving
+// L_kk^-T while the lower triangle holds L_kk.  A non-positive (or NaN) pivot reports
+// info = global index + 1, the LAPACK dpotrf convention behind np.linalg.LinAlgError
+// (general_utils.py:176-180).
+constexpr int DIAG_LD = TILE + 1;
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* T, int64_t ld, int step,
+                                                         double* Dinv, int* info) {
+  extern __shared__ __align__(16) double S[];   // [128][129] + dL[128] + dW[128]
+  if (*info != 0) return;
+  double* dL = S + TILE * DIAG_LD;
+  double* dW = dL + TILE;
+  double* blk = T + (int64_t)step * TILE * ld + (int64_t)step * TILE;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    const int i = idx >> 7, c = idx & 127;
+    S[i * DIAG_LD + c] = (c <= i) ? blk[(int64_t)i * ld + c] : 0.0;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int j = 0; j < TILE; j++) {
+    const double piv = S[j * DIAG_LD + j];
+    if (!(piv > 0.0)) {                 // uniform across the block
+      if (tid == 0) atomicCAS(info, 0, step * TILE + j + 1);
+      return;
+    }
+    const double dj = sqrt(piv);
+    const double rj = 1.0 / dj;
+    __syncthreads();                    // everyone has read the pivot before column j changes
+    if (tid < TILE) {
+      if (tid == j) { dL[j] = dj; dW[j] = rj; S[j * DIAG_LD + j] = rj; }
+      else S[tid * DIAG_LD + j] = S[tid * DIAG_LD + j] / dj;
+    }
+    __syncthreads();
+    // S[i][c] -= m_i * S[c][j] for c > j and (i <= j  [inverse rows]  or  c <= i  [Cholesky rows]);
+    // m_i = S[i][j] (for i == j this slot temporarily holds 1/d_j).
+    for (int i = ty; i < TILE; i += 16) {
+      const double mi = S[i * DIAG_LD + j];
+      const int c_hi = (i <= j) ? (TILE - 1) : i;
+      for (int c = j + 1 + tx; c <= c_hi; c += 16)
+        S[i * DIAG_LD + c] = fma(-mi, S[c * DIAG_LD + j], S[i * DIAG_LD + c]);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    const int i = idx >> 7, c = idx & 127;
+    double lv, wv;
+    if (c < i) { lv = S[i * DIAG_LD + c]; wv = S[c * DIAG_LD + i]; }
+    else if (c == i) { lv = dL[i]; wv = dW[i]; }
+    else { lv = 0.0; wv = 0.0; }
+    blk[(int64_t)i * ld + c] = lv;
+    Dinv[i * TILE + c] = wv;
+  }
+}
+
+// ---- W = (L^-T)^T : 32 x 32 tile transpose ----------------------------------------------------------
+__global__ void transpose_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  __shared__ double tile[32][33];
+  const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    tile[r][threadIdx.x] = src[(by + r) * n + bx + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    dst[(bx + r) * n + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// ---- alpha = L^-T (L^-1 y) = rows of L^-T dotted with v = L^-1 y  (gp_core.py:162-163) ---------
+__global__ void alpha_kernel(const double* __restrict__ Wt, const double* __restrict__ v,
+                             double* alpha, int64_t n, int64_t npad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= npad) return;
+  double s = 0.0;
+  if (j < n) {
+    const double* row = Wt + j * npad;
+    for (int64_t i = (j & ~(int64_t)31) + lane; i < npad; i += 32) s = fma(row[i], v[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if (lane == 0) alpha[j] = s;
+}
+
+// ---- LML pieces: sum log L_ii, y_c . alpha, |L^-1 y_c|^2  (gp_core.py:222-227) --------------------
+__global__ void lml_reduce_kernel(const double* __restrict__ T, const double* __restrict__ yc,
+                                  const double* __restrict__ alpha, const double* __restrict__ v,
+                                  int64_t n, int64_t npad, double* out) {
+  __shared__ double sh[3][32];
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    a += log(T[i * npad + i]);
+    if (alpha != nullptr) b = fma(yc[i], alpha[i], b);
+    c = fma(v[i], v[i], c);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    a = lane < nw ? sh[0][lane] : 0.0;
+    b = lane < nw ? sh[1][lane] : 0.0;
+    c = lane < nw ? sh[2][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { out[0] = a; out[1] = b; out[2] = c; }
+  }
+}
+
+// ---- copy-outs for gp.L / generic strided copies ----------------------------------------------------
+__global__ void extract_lower_kernel(const double* __restrict__ T, int64_t npad, double* L, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int64_t i = idx / n, c = idx - i * n;
+  L[idx] = (c <= i) ? T[i * npad + c] : 0.0;
+}
+
+__global__ void copy_pad_kernel(const double* __restrict__ src, int64_t n_src, double* dst, int64_t n_dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_dst) dst[i] = (i < n_src) ? src[i] : 0.0;
+}
+
+__global__ void copy_rows_kernel(const double* __restrict__ src, int64_t ld_src, double* dst,
+                                 int64_t ld_dst, int64_t rows, int64_t cols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t r = idx / cols, c = idx - r * cols;
+  dst[r * ld_dst + c] = src[r * ld_src + c];
+}
+
+// ================================================================================================
+// Acquisition + arg-max                                       dragonfly/opt/gpb_acquisitions.py
+// ================================================================================================
+// scipy.stats.norm.cdf == scipy.special.ndtr (cephes): 0.5 erfc(-z / sqrt 2) split at |x| < sqrt(1/2).
+__device__ __forceinline__ double norm_cdf_ref(double z) {
+  if (isnan(z)) return z;
+  const double x = z * 0.70710678118654752440;
+  const double ax = fabs(x);
+  double y;
+  if (ax < 0.70710678118654752440) {
+    y = 0.5 + 0.5 * erf(x);
+  } else {
+    y = 0.5 * erfc(ax);
+    if (x > 0) y = 1.0 - y;
+  }
+  return y;
+}
+// scipy.stats.norm.pdf: exp(-x**2 / 2) / sqrt(2 pi)
+__device__ __forceinline__ double norm_pdf_ref(double z) {
+  return exp(__dmul_rn(__dmul_rn(z, z), -0.5)) / 2.50662827463100050242;
+}
+__device__ __forceinline__ double ei_for_norm_diff(double z) {     // gpb_acquisitions.py:247-249
+  return __dadd_rn(__dmul_rn(z, norm_cdf_ref(z)), norm_pdf_ref(z));
+}
+
+// np.argmax order: NaN beats everything, ties go to the lower index (oper_utils.py:73).
+__device__ __forceinline__ bool better(double sa, int64_t ia, double sb, int64_t ib) {
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  const bool na = isnan(sa), nb = isnan(sb);
+  if (na || nb) {
+    if (na && nb) return ia < ib;
+    return na;
+  }
+  if (sa > sb) return true;
+  if (sa < sb) return false;
+  return ia < ib;
+}
+
+__global__ void __launch_bounds__(256)
+acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* __restrict__ partial,
+           int64_t ld_partial, int nrb, const double* __restrict__ kss, int64_t m, int64_t idx_base,
+           int want_std,
+           double* __restrict__ sd_out, double* __restrict__ score_out, double* blk_score,
+           int64_t* blk_index) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double score = 0.0;
+  int64_t index = -1;
+  if (i < m) {
+    const double mean = mu[i];
+    double sd = 0.0;
+    if (want_std) {
+      double vn = 0.0;
+      for (int rb = 0; rb < nrb; rb++) vn += partial[(int64_t)rb * ld_partial + i];
+      sd = sqrt(__dadd_rn(kss[i], -vn));    // np.sqrt(np.diag(K_tete - V.T.dot(V))): no clamp
+      if (sd_out != nullptr) sd_out[i] = sd;
+    }
+    switch (acq.kind) {
+      case DFB_ACQ_UCB:                       // mu + beta_th * sigma            :219-222
+        score = __dadd_rn(mean, __dmul_rn(acq.beta, sd));
+        break;
+      case DFB_ACQ_EI: {                      // sigma * EI((mu - best) / sigma)  :255-260
+        const double z = __dadd_rn(mean, -acq.best) / sd;
+        score = __dmul_rn(sd, ei_for_norm_diff(z));
+        break;
+      }
+      case DFB_ACQ_PI:                        // Phi((mu - best) / sigma)         :235-238
+        score = norm_cdf_ref(__dadd_rn(mean, -acq.best) / sd);
+        break;
+      case DFB_ACQ_TTEI: {                    // :274-279
+        const double comb = sqrt(__dadd_rn(__dmul_rn(acq.ref_std, acq.ref_std), __dmul_rn(sd, sd)));
+        const double z = __dadd_rn(mean, -acq.ref_mean) / comb;
+        score = __dmul_rn(comb, ei_for_norm_diff(z));
+        break;
+      }
+      default:
+        score = mean;
+    }
+    if (score_out != nullptr) score_out[i] = score;
+    index = idx_base + i;
+  }
+  if (blk_score == nullptr) return;
+  // block arg-max
+  for (int o = 16; o > 0; o >>= 1) {
+    const double so = __shfl_xor_sync(0xffffffffu, score, o);
+    const int64_t io = __shfl_xor_sync(0xffffffffu, index, o);
+    if (better(so, io, score, index)) { score = so; index = io; }
+  }
+  __shared__ double ss[8];
+  __shared__ int64_t si[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ss[warp] = score; si[warp] = index; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(ss[w], si[w], score, index)) { score = ss[w]; index = si[w]; }
+    blk_score[blockIdx.x] = score;
+    blk_index[blockIdx.x] = index;
+  }
+}
+
+// Folds the per-block winners of one chunk into the running (score, index) of the whole call.
+__global__ void __launch_bounds__(256)
+argmax_merge_kernel(const double* __restrict__ blk_score, const int64_t* __restrict__ blk_index,
+                    int nblk, double* best_score, int64_t* best_index) {
+  double score = 0.0;
+  int64_t index = -1;
+  if (threadIdx.x == 0) { score = *best_score; index = *best_index; }
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+    if (better(blk_score[b], blk_index[b], score, index)) { score = blk_score[b]; index = blk_index[b]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double so = __shfl_xor_sync(0xffffffffu, score, o);
+    const int64_t io = __shfl_xor_sync(0xffffffffu, index, o);
+    if (better(so, io, score, index)) { score = so; index = io; }
+  }
+  __shared__ double ss[8];
+  __shared__ int64_t si[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ss[warp] = score; si[warp] = index; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(ss[w], si[w], score, index)) { score = ss[w]; index = si[w]; }
+    *best_score = score;
+    *best_index = index;
+  }
+}
+
+__global__ void reset_best_kernel(double* best_score, int64_t* best_index) {
+  *best_score = 0.0;
+  *best_index = -1;
+}
+
+// samples[s][a] += mu[a]   (draw_gaussian_samples: L.dot(U).T + mu, general_utils.py:231)
+__global__ void add_row_vector_kernel(double* M, int64_t ld, int64_t rows, int64_t cols,
+                                      const double* __restrict__ v) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t r = idx / cols, c = idx - r * cols;
+  M[r * ld + c] += v[c];
+}
+
+// covar[a][b] = kss_or_K**[a][b] handled by the caller; this zero-fills a padded matrix
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void set_diag_kernel(double* M, int64_t ld, int64_t from, int64_t to, double v, int add) {
+  const int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < to) M[i * ld + i] = add ? (M[i * ld + i] + v) : v;
+}
+
+// ================================================================================================
+// Host launchers
+// ================================================================================================
+static bool g_attr_done[2] = {false, false};
+
+int launch_gemm(dfb_handle* h, const GemmArgs& g, int epi, int n_blocks) {
+  if (n_blocks <= 0) return 0;
+  if (epi == EPI_SUMSQ) {
+    if (!g_attr_done[1]) {
+      DFB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<EPI_SUMSQ>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM_BYTES));
+      g_attr_done[1] = true;
+    }
+    gemm_tn_kernel<EPI_SUMSQ><<<n_blocks, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
+  } else {
+    if (!g_attr_done[0]) {
+      DFB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<EPI_STORE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM_BYTES));
+      g_attr_done[0] = true;
+    }
+    gemm_tn_kernel<EPI_STORE><<<n_blocks, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
+  }
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_prep_scaled(dfb_handle* h, const dfb_kernel_desc* d_desc, int use_train_coords,
+                       const double* X, int64_t n, int d, double* xs, double* nrm, int64_t npad) {
+  const int threads = 128;
+  prep_scaled_kernel<<<(unsigned)((npad + threads - 1) / threads), threads, 0, h->stream>>>(
+      d_desc, use_train_coords, X, n, d, xs, nrm, npad);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
+                 int cand_uses_train_coords, const double* xsT, const double* nrmT, int64_t npad_tr,
+                 const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows, double* Ks,
+                 int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const, double* mu,
+                 double* kss_out) {
+  if (m_rows <= 0) return 0;
+  const size_t smem = ((sizeof(dfb_kernel_desc) + 15) / 16) * 16 +
+                      sizeof(double) * KSTAR_CANDS * (size_t)(desc.n_slots + desc.n_factors);
+  const unsigned blocks = (unsigned)((m_rows + KSTAR_CANDS - 1) / KSTAR_CANDS);
+  kstar_kernel<<<blocks, KSTAR_WARPS * 32, smem, h->stream>>>(
+      d_desc, cand_uses_train_coords, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid,
+      n_write, mean_const, mu, kss_out);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double diag_add,
+                     const double* yc, int with_bottom) {
+  init_tall_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, h->stream>>>(T, n, npad, diag_add, yc,
+                                                                         with_bottom);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static bool g_diag_attr = false;
+int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info) {
+  const size_t smem = sizeof(double) * (TILE * DIAG_LD + 2 * TILE);
+  if (!g_diag_attr) {
+    DFB_CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    g_diag_attr = true;
+  }
+  chol_diag_kernel<<<1, 256, smem, h->stream>>>(T, ld, step, Dinv, info);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_transpose(dfb_handle* h, const double* src, double* dst, int64_t n) {
+  dim3 grid((unsigned)(n / 32), (unsigned)(n / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, h->stream>>>(src, dst, n);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_alpha(dfb_handle* h, const double* Wt, const double* v, double* alpha, int64_t n,
+                 int64_t npad) {
+  alpha_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, h->stream>>>(Wt, v, alpha, n, npad);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_lml_reduce(dfb_handle* h, const double* T, const double* yc, const double* alpha,
+                      const double* v, int64_t n, int64_t npad, double* out) {
+  lml_reduce_kernel<<<1, 1024, 0, h->stream>>>(T, yc, alpha, v, n, npad, out);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_extract_lower(dfb_handle* h, const double* T, int64_t npad, double* L, int64_t n) {
+  extract_lower_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, h->stream>>>(T, npad, L, n);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_copy_pad(dfb_handle* h, const double* src, int64_t n_src, double* dst, int64_t n_dst) {
+  copy_pad_kernel<<<(unsigned)((n_dst + 255) / 256), 256, 0, h->stream>>>(src, n_src, dst, n_dst);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
+                     int64_t rows, int64_t cols) {
+  if (rows * cols <= 0) return 0;
+  copy_rows_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, h->stream>>>(src, ld_src, dst,
+                                                                               ld_dst, rows, cols);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
+               int64_t ld_partial, int nrb, const double* __restrict__ kss, int64_t m, int64_t idx_base,
+           int want_std,
+               double* sd_out, double* score_out, bool do_argmax) {
+  if (m <= 0) return 0;
+  const unsigned blocks = (unsigned)((m + 255) / 256);
+  acq_kernel<<<blocks, 256, 0, h->stream>>>(acq, mu, partial, ld_partial, nrb, kss, m, idx_base,
+                                            want_std, sd_out, score_out,
+                                            do_argmax ? h->blk_score : nullptr,
+                                            do_argmax ? h->blk_index : nullptr);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  if (do_argmax) {
+    argmax_merge_kernel<<<1, 256, 0, h->stream>>>(h->blk_score, h->blk_index, (int)blocks,
+                                                  h->best_score, h->best_index);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_reset_best(dfb_handle* h) {
+  reset_best_kernel<<<1, 1, 0, h->stream>>>(h->best_score, h->best_index);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, int64_t cols,
+                          const double* v) {
+  if (rows * cols <= 0) return 0;
+  add_row_vector_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, h->stream>>>(M, ld, rows,
+                                                                                    cols, v);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fill(dfb_handle* h, double* p, int64_t n, double v) {
+  if (n <= 0) return 0;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(p, n, v);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_set_diag(dfb_handle* h, double* M, int64_t ld, int64_t from, int64_t to, double v, int add) {
+  if (to <= from) return 0;
+  set_diag_kernel<<<(unsigned)((to - from + 255) / 256), 256, 0, h->stream>>>(M, ld, from, to, v, add);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dfb

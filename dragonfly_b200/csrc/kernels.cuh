@@ -1,0 +1,36 @@
+// Host-side launchers of the CUDA kernels in kernels.cu (one stream: h->stream).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace dfb {
+
+int launch_prep_scaled(dfb_handle* h, const dfb_kernel_desc* d_desc, int use_train_coords,
+                       const double* X, int64_t n, int d, double* xs, double* nrm, int64_t npad);
+int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
+                 int cand_uses_train_coords, const double* xsT, const double* nrmT, int64_t npad_tr,
+                 const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows, double* Ks,
+                 int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const, double* mu,
+                 double* kss_out);
+int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double diag_add,
+                     const double* yc, int with_bottom);
+int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info);
+int launch_transpose(dfb_handle* h, const double* src, double* dst, int64_t n);
+int launch_alpha(dfb_handle* h, const double* Wt, const double* v, double* alpha, int64_t n,
+                 int64_t npad);
+int launch_lml_reduce(dfb_handle* h, const double* T, const double* yc, const double* alpha,
+                      const double* v, int64_t n, int64_t npad, double* out);
+int launch_extract_lower(dfb_handle* h, const double* T, int64_t npad, double* L, int64_t n);
+int launch_copy_pad(dfb_handle* h, const double* src, int64_t n_src, double* dst, int64_t n_dst);
+int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
+                     int64_t rows, int64_t cols);
+int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
+               int64_t ld_partial, int nrb, const double* kss, int64_t m, int64_t idx_base,
+               int want_std, double* sd_out, double* score_out, bool do_argmax);
+int launch_reset_best(dfb_handle* h);
+int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, int64_t cols,
+                          const double* v);
+int launch_fill(dfb_handle* h, double* p, int64_t n, double v);
+int launch_set_diag(dfb_handle* h, double* M, int64_t ld, int64_t from, int64_t to, double v, int add);
+
+}  // namespace dfb

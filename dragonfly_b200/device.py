@@ -1,0 +1,194 @@
+"""
+Device-side objects behind the Python host: a `DevicePosterior` wraps one libdfb200 handle plus the
+torch-owned workspace it computes in.  PyTorch appears here only as the allocator of device buffers
+and the owner of CUDA streams; every numeric result comes from libdfb200's CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .kernel import build_descriptor
+
+
+def _require_cuda(device=None):
+  if not torch.cuda.is_available():
+    raise RuntimeError('dragonfly_b200 needs a CUDA device (B200, sm_100a); none is visible and '
+                       'there is no CPU fallback.')
+  if device is None:
+    device = torch.cuda.current_device()
+  return torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+
+
+def _dev_f64(arr, device):
+  """ Host array-like or torch tensor -> contiguous fp64 CUDA tensor on `device`. """
+  if isinstance(arr, torch.Tensor):
+    return arr.to(device=device, dtype=torch.float64).contiguous()
+  return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=np.float64))).to(device)
+
+
+class DevicePosterior(object):
+  """ One handle + workspace.  Immutable once built (GP objects replace, never mutate, it), so
+      shallow / deep copies of a GP may share it (gpb_acquisitions.py:104, unittest_mf_gp.py:109). """
+
+  def __init__(self, n_max, device=None, chunk=0):
+    self.lib = _lib.load()
+    self.device = _require_cuda(device)
+    self.n_max = int(n_max)
+    hp = C.c_void_p()
+    _lib.check(self.lib.dfb_create(C.byref(hp), self.device.index), 'dfb_create')
+    self.h = hp
+    nbytes = self.lib.dfb_workspace_bytes(self.n_max, 0, int(chunk))
+    self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+    ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+    with torch.cuda.device(self.device):
+      stream = torch.cuda.current_stream(self.device).cuda_stream
+      _lib.check(self.lib.dfb_set_stream(self.h, C.c_void_p(stream)), 'dfb_set_stream')
+      _lib.check(self.lib.dfb_set_workspace(self.h, C.c_void_p(ptr), C.c_size_t(nbytes), self.n_max,
+                                            int(chunk)), 'dfb_set_workspace')
+    self.n = 0
+    self.dim = 0
+    self.lml = None
+    self._keep = []      # tensors that must outlive asynchronous use
+
+  def __del__(self):
+    try:
+      if getattr(self, 'h', None) is not None and self.h.value:
+        torch.cuda.synchronize(self.device)
+        self.lib.dfb_destroy(self.h)
+        self.h = None
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  # -- model ------------------------------------------------------------------------------------
+  def set_kernel(self, desc):
+    _lib.check(self.lib.dfb_set_kernel(self.h, C.byref(desc)), 'dfb_set_kernel')
+
+  def set_test_kernel(self, desc):
+    if desc is None:
+      _lib.check(self.lib.dfb_set_test_kernel(self.h, None), 'dfb_set_test_kernel')
+    else:
+      _lib.check(self.lib.dfb_set_test_kernel(self.h, C.byref(desc)), 'dfb_set_test_kernel')
+
+  def set_train(self, X, y_centred):
+    Xd = _dev_f64(X, self.device)
+    yd = _dev_f64(y_centred, self.device)
+    self.n, self.dim = int(Xd.shape[0]), int(Xd.shape[1])
+    _lib.check(self.lib.dfb_set_train(self.h, C.c_void_p(Xd.data_ptr()), self.n, self.dim,
+                                      C.c_void_p(yd.data_ptr())), 'dfb_set_train')
+    torch.cuda.synchronize(self.device)
+
+  def build(self, noise_var, jitter=0.0, flags=_lib.DFB_BUILD_FULL):
+    """ Returns (info, lml): info > 0 means 'not positive definite' (np.linalg.LinAlgError). """
+    lml = C.c_double(0.0)
+    info = _lib.check(self.lib.dfb_build_posterior(self.h, float(noise_var), float(jitter), int(flags),
+                                                   C.byref(lml)), 'dfb_build_posterior')
+    self.lml = lml.value if info == 0 else None
+    return info, self.lml
+
+  def max_diag(self):
+    out = C.c_double(0.0)
+    _lib.check(self.lib.dfb_get_max_diag(self.h, C.byref(out)), 'dfb_get_max_diag')
+    return out.value
+
+  def get_state(self, want_L=False, want_alpha=False, want_K=False):
+    L = torch.empty((self.n, self.n), dtype=torch.float64, device=self.device) if want_L else None
+    a = torch.empty((self.n,), dtype=torch.float64, device=self.device) if want_alpha else None
+    K = torch.empty((self.n, self.n), dtype=torch.float64, device=self.device) if want_K else None
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(self.lib.dfb_get_state(self.h, ptr(L), ptr(a), ptr(K)), 'dfb_get_state')
+    return L, a, K
+
+  def set_alpha(self, alpha):
+    ad = _dev_f64(alpha, self.device)
+    _lib.check(self.lib.dfb_set_alpha(self.h, C.c_void_p(ad.data_ptr()), int(ad.shape[0])),
+               'dfb_set_alpha')
+    torch.cuda.synchronize(self.device)
+
+  # -- prediction ---------------------------------------------------------------------------------
+  def eval(self, Xc, mean_const=0.0, want_std=True):
+    """ Xc: host ndarray (results are host ndarrays, copies inside the C call) or CUDA tensor
+        (results are CUDA tensors).  Returns (mu, sd or None). """
+    if isinstance(Xc, torch.Tensor):
+      Xd = _dev_f64(Xc, self.device)
+      m, dc = int(Xd.shape[0]), int(Xd.shape[1])
+      mu = torch.empty((m,), dtype=torch.float64, device=self.device)
+      sd = torch.empty((m,), dtype=torch.float64, device=self.device) if want_std else None
+      _lib.check(self.lib.dfb_eval(self.h, C.c_void_p(Xd.data_ptr()), m, dc, _lib.DFB_DEVICE,
+                                   float(mean_const), C.c_void_p(mu.data_ptr()),
+                                   C.c_void_p(sd.data_ptr()) if want_std else None), 'dfb_eval')
+      return mu, sd
+    Xh = np.ascontiguousarray(np.asarray(Xc, dtype=np.float64))
+    m, dc = Xh.shape
+    mu = np.empty((m,), dtype=np.float64)
+    sd = np.empty((m,), dtype=np.float64) if want_std else None
+    _lib.check(self.lib.dfb_eval(self.h, Xh.ctypes.data_as(C.c_void_p), m, dc, _lib.DFB_HOST,
+                                 float(mean_const), mu.ctypes.data_as(C.c_void_p),
+                                 sd.ctypes.data_as(C.c_void_p) if want_std else None), 'dfb_eval')
+    return mu, sd
+
+  def score_argmax(self, acq_desc, Xc, mean_const=0.0, want_scores=False):
+    """ Fused scoring + arg-max.  Returns (best_score, best_index, scores or None). """
+    bs, bi = C.c_double(0.0), C.c_int64(-1)
+    if isinstance(Xc, torch.Tensor):
+      Xd = _dev_f64(Xc, self.device)
+      m, dc = int(Xd.shape[0]), int(Xd.shape[1])
+      sc = torch.empty((m,), dtype=torch.float64, device=self.device) if want_scores else None
+      _lib.check(self.lib.dfb_score_argmax(
+          self.h, C.byref(acq_desc), C.c_void_p(Xd.data_ptr()), m, dc, _lib.DFB_DEVICE,
+          float(mean_const), C.c_void_p(sc.data_ptr()) if want_scores else None, C.byref(bs),
+          C.byref(bi)), 'dfb_score_argmax')
+      return bs.value, bi.value, sc
+    Xh = np.ascontiguousarray(np.asarray(Xc, dtype=np.float64))
+    m, dc = Xh.shape
+    sc = np.empty((m,), dtype=np.float64) if want_scores else None
+    _lib.check(self.lib.dfb_score_argmax(
+        self.h, C.byref(acq_desc), Xh.ctypes.data_as(C.c_void_p), m, dc, _lib.DFB_HOST,
+        float(mean_const), sc.ctypes.data_as(C.c_void_p) if want_scores else None, C.byref(bs),
+        C.byref(bi)), 'dfb_score_argmax')
+    return bs.value, bi.value, sc
+
+  def launch_count(self):
+    return int(self.lib.dfb_launch_count(self.h))
+
+  def profile_enable(self, on=True):
+    _lib.check(self.lib.dfb_profile_enable(self.h, 1 if on else 0), 'dfb_profile_enable')
+
+  def profile_read(self, cls):
+    """ (milliseconds, launches, work units) accumulated for a kernel class; resets it. """
+    ms, n, u = C.c_double(0.0), C.c_int64(0), C.c_double(0.0)
+    _lib.check(self.lib.dfb_profile_read(self.h, int(cls), C.byref(ms), C.byref(n), C.byref(u)),
+               'dfb_profile_read')
+    return ms.value, n.value, u.value
+
+
+_KM_CACHE = {}
+
+
+def kernel_matrix(kern, X1, X2, device=None):
+  """ Kernel.__call__(X1, X2) on the GPU (dfb_kernel_matrix).  Returns a host ndarray (n1, n2). """
+  dev = _require_cuda(device)
+  X1d = _dev_f64(np.asarray(X1, dtype=np.float64), dev)
+  X2d = _dev_f64(np.asarray(X2, dtype=np.float64), dev)
+  n1, d1 = int(X1d.shape[0]), int(X1d.shape[1])
+  n2, d2 = int(X2d.shape[0]), int(X2d.shape[1])
+  key = (dev.index,)
+  post = _KM_CACHE.get(key)
+  if post is None or post.n_max < n2:
+    post = DevicePosterior(max(n2, 1024), device=dev, chunk=128)
+    _KM_CACHE[key] = post
+  desc = build_descriptor(kern, train_dim=d1, cand_dim=d1)
+  K = torch.empty((n1, n2), dtype=torch.float64, device=dev)
+  _lib.check(post.lib.dfb_kernel_matrix(post.h, C.byref(desc), C.c_void_p(X1d.data_ptr()), n1, d1,
+                                        C.c_void_p(X2d.data_ptr()), n2, d2,
+                                        C.c_void_p(K.data_ptr())), 'dfb_kernel_matrix')
+  return K.cpu().numpy()
+
+
+def make_acq_desc(kind, beta=0.0, best=0.0, ref_mean=0.0, ref_std=0.0):
+  a = _lib.AcqDesc()
+  a.kind = {'mean': _lib.DFB_ACQ_MEAN, 'ucb': _lib.DFB_ACQ_UCB, 'ei': _lib.DFB_ACQ_EI,
+            'pi': _lib.DFB_ACQ_PI, 'ttei': _lib.DFB_ACQ_TTEI}[kind]
+  a.beta, a.best, a.ref_mean, a.ref_std = float(beta), float(best), float(ref_mean), float(ref_std)
+  return a

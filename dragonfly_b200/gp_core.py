@@ -1,0 +1,343 @@
+"""
+Drop-in for dragonfly.gp.gp_core.GP (gp_core.py:86-304) whose numeric bodies run on a B200 through
+libdfb200: same constructor, methods, option meaning, public attributes (X, Y lists, num_tr_data,
+kernel, noise_var, mean_func, L, alpha, K_trtr_wo_noise) and error behaviour.
+
+What stays on the host, as in the reference: the Python `mean_func` callable (evaluated on the
+training inputs for centring; constant means -- what GPFitter.build_gp always produces,
+gp_core.py:527-530 -- are folded into the device call, anything else is added on the host), and the
+jitter ladder of stable_cholesky (general_utils.py:166-204), which re-submits the factorisation with
+10^p * max(diag) added until the device reports success.
+"""
+import sys
+from warnings import warn
+
+import numpy as np
+
+from . import _lib
+from .kernel import build_descriptor
+
+
+def _check_feature_label_lengths_and_format(X, Y):
+  """ gp_core.py:71-75.  (The reference concatenates str + int here, so a length mismatch
+      surfaces as TypeError there; we raise the ValueError it meant to.) """
+  if len(X) != len(Y):
+    raise ValueError('Length of X (%d) and Y (%d) do not match.' % (len(X), len(Y)))
+
+
+def _as_2d(X):
+  arr = np.asarray(X, dtype=np.float64)
+  if arr.ndim == 1:
+    arr = arr.reshape(1, -1)
+  return np.ascontiguousarray(arr)
+
+
+def _constant_mean_value(mean_func, dim):
+  """ Returns c if mean_func is constant on a few probe points (the only kind GPFitter produces),
+      else None.  Objects may also advertise it via a `const_value` attribute. """
+  if hasattr(mean_func, 'const_value'):
+    return float(mean_func.const_value)
+  try:
+    probe = np.array([[0.0] * dim, [0.5] * dim, [0.123456789] * dim, [1.0] * dim])
+    vals = np.asarray(mean_func(probe), dtype=np.float64).reshape(-1)
+  except Exception:  # pylint: disable=broad-except
+    return None
+  if vals.shape[0] == 4 and np.all(vals == vals[0]):
+    return float(vals[0])
+  return None
+
+
+class ConstantMean(object):
+  """ lambda x: np.array([c] * len(x)) with the constant advertised (gp_core.py:527-530). """
+
+  def __init__(self, value):
+    self.const_value = float(value)
+
+  def __call__(self, x):
+    return np.array([self.const_value] * len(x))
+
+
+def stable_cholesky_on_device(post, noise_var, add_to_diag_till_psd=True, flags=_lib.DFB_BUILD_FULL):
+  """ general_utils.py:166-204 with np.linalg.cholesky replaced by the device factorisation:
+      try jitter 0, then 10^p * max(diag M) for p = -11, -10, ...; ValueError once p reaches 5.
+      Returns (lml, jitter_power or None). """
+  info, lml = post.build(noise_var, 0.0, flags)
+  if info == 0:
+    return lml, None
+  if not add_to_diag_till_psd:
+    raise np.linalg.LinAlgError('Matrix is not positive definite (pivot %d).' % (info - 1))
+  max_M = post.max_diag()
+  diag_noise_power = -11
+  printed_warning = False
+  while True:
+    diag_noise = (10 ** diag_noise_power) * max_M
+    info, lml = post.build(noise_var, diag_noise, flags)
+    if info == 0:
+      return lml, diag_noise_power
+    if diag_noise_power > -9 and not printed_warning:
+      warn(('Could not compute Cholesky decomposition despite adding %0.4f to the diagonal. '
+            'This is likely because the M is not positive semi-definite.') % (diag_noise))
+      printed_warning = True
+    diag_noise_power += 1
+    if diag_noise_power >= 5:
+      raise ValueError(('Could not compute Cholesky decomposition despite adding %0.4f to the '
+                        'diagonal. This is likely because the M is not positive semi-definite or '
+                        'has infinities/nans.') % (diag_noise))
+
+
+class GP(object):
+  """ Base class for Gaussian processes -- device-backed mirror of gp_core.py:86-304. """
+  # pylint: disable=attribute-defined-outside-init
+
+  def __init__(self, X, Y, kernel, mean_func, noise_var, build_posterior=True,
+               reporter=None, handle_non_psd_kernels='guaranteed_psd', device=None):
+    super(GP, self).__init__()
+    _check_feature_label_lengths_and_format(X, Y)
+    self._device = device
+    self._post = None
+    self._cache = {}
+    self.set_data(X, Y, build_posterior=False)
+    self.kernel = kernel
+    self.mean_func = mean_func
+    self.noise_var = noise_var
+    self.reporter = reporter
+    self.handle_non_psd_kernels = handle_non_psd_kernels
+    self.num_tr_data = len(self.Y)
+    self.jitter_power = None
+    self._set_up()
+    if build_posterior:
+      self.build_posterior()
+
+  def _set_up(self):
+    """ gp_core.py:113-118 """
+    if not self.kernel.is_guaranteed_psd():
+      assert self.handle_non_psd_kernels in ['project_first', 'try_before_project']
+
+  def _write_message(self, msg):
+    if self.reporter is not None and hasattr(self.reporter, 'write'):
+      self.reporter.write(msg)
+    else:
+      sys.stdout.write(msg)
+
+  # -- data ---------------------------------------------------------------------------------------
+  def set_data(self, X, Y, build_posterior=True):
+    """ gp_core.py:127-133 """
+    self.X = list(X)
+    self.Y = list(Y)
+    self.num_tr_data = len(self.Y)
+    if build_posterior:
+      self.build_posterior()
+
+  def add_data_single(self, x_new, y_new, *args, **kwargs):
+    self.add_data_multiple([x_new], [y_new], *args, **kwargs)
+
+  def add_data_multiple(self, X_new, Y_new, build_posterior=True):
+    """ gp_core.py:139-146 (full rebuild on every new observation, like the reference). """
+    _check_feature_label_lengths_and_format(X_new, Y_new)
+    self.X.extend(X_new)
+    self.Y.extend(Y_new)
+    self.num_tr_data = len(self.Y)
+    if build_posterior:
+      self.build_posterior()
+
+  # -- posterior ------------------------------------------------------------------------------------
+  def _train_matrix(self):
+    """ The training inputs as the (n, d) matrix the kernel sees.  Child classes with structured
+        inputs (multi-fidelity [z || x] rows) override this. """
+    return _as_2d(self.X)
+
+  def _new_device_posterior(self, n_max):
+    from .device import DevicePosterior
+    return DevicePosterior(n_max, device=self._device)
+
+  def _build_on_device(self, X_mat, y_centred, flags):
+    if self.handle_non_psd_kernels not in ('guaranteed_psd', 'try_before_project', 'project_first'):
+      raise ValueError('Unknown option for handle_non_psd_kernels: %s' % (
+          self.handle_non_psd_kernels))
+    if self.handle_non_psd_kernels == 'project_first':
+      raise NotImplementedError('project_first needs an eigen-decomposition; every kernel on the '
+                                'B200 hot path is guaranteed PSD (no CPU fallback).')
+    post = self._new_device_posterior(len(X_mat))
+    post.set_kernel(build_descriptor(self.kernel, train_dim=X_mat.shape[1], cand_dim=X_mat.shape[1]))
+    post.set_train(X_mat, y_centred)
+    ladder = (self.handle_non_psd_kernels == 'guaranteed_psd')
+    try:
+      lml, power = stable_cholesky_on_device(post, self.noise_var, add_to_diag_till_psd=ladder,
+                                             flags=flags)
+    except np.linalg.LinAlgError:
+      raise NotImplementedError('try_before_project fell through to project_first, which needs '
+                                'an eigen-decomposition (out of the B200 hot-path scope).')
+    return post, lml, power
+
+  def build_posterior(self):
+    """ gp_core.py:155-163: K, L = chol(K + noise I), alpha -- all on the device. """
+    self._cache = {}
+    if self.num_tr_data == 0:
+      self._post = None
+      self._cache = {'L': np.zeros((0, 0)), 'alpha': np.zeros((0,)), 'K': np.zeros((0, 0))}
+      self._lml = -0.0
+      return
+    X_mat = self._train_matrix()
+    y_centred = np.asarray(self.Y, dtype=np.float64) - np.asarray(self.mean_func(self.X))
+    self._y_centred = y_centred
+    self._post, self._lml, self.jitter_power = self._build_on_device(X_mat, y_centred,
+                                                                     _lib.DFB_BUILD_FULL)
+    self._mean_const = _constant_mean_value(self.mean_func, X_mat.shape[1])
+
+  def _state(self, name):
+    if name not in self._cache:
+      if self._post is None:
+        raise RuntimeError('Posterior has not been built.')
+      L, a, K = self._post.get_state(want_L=(name == 'L'), want_alpha=(name == 'alpha'),
+                                     want_K=(name == 'K'))
+      t = {'L': L, 'alpha': a, 'K': K}[name]
+      self._cache[name] = t.cpu().numpy()
+    return self._cache[name]
+
+  # gp.L / gp.alpha are read directly by _add_ucb (gpb_acquisitions.py:169-171) and
+  # gp.K_trtr_wo_noise by gp_core.py:203: lazily copied back as NumPy arrays.
+  @property
+  def L(self):
+    return None if (self._post is None and 'L' not in self._cache) else self._state('L')
+
+  @L.setter
+  def L(self, value):
+    if value is not None:
+      self._cache['L'] = value
+
+  @property
+  def alpha(self):
+    return None if (self._post is None and 'alpha' not in self._cache) else self._state('alpha')
+
+  @alpha.setter
+  def alpha(self, value):
+    if value is not None:
+      self._cache['alpha'] = value
+
+  @property
+  def K_trtr_wo_noise(self):
+    return None if (self._post is None and 'K' not in self._cache) else self._state('K')
+
+  @K_trtr_wo_noise.setter
+  def K_trtr_wo_noise(self, value):
+    if value is not None:
+      self._cache['K'] = value
+
+  def compute_log_marginal_likelihood(self):
+    """ gp_core.py:222-227 (evaluated on the device during build_posterior). """
+    if self._post is None and self.num_tr_data > 0:
+      raise RuntimeError('Posterior has not been built.')
+    return self._lml
+
+  # -- prediction --------------------------------------------------------------------------------------
+  def _test_matrix(self, X_test):
+    import torch
+    if isinstance(X_test, torch.Tensor):
+      return X_test
+    return _as_2d(X_test)
+
+  def _eval_on(self, post, X_test, want_std):
+    import torch
+    Xm = self._test_matrix(X_test)
+    if self._mean_const is not None:
+      return post.eval(Xm, mean_const=self._mean_const, want_std=want_std)
+    if isinstance(Xm, torch.Tensor):
+      raise NotImplementedError('A non-constant mean_func needs host candidates (it is a Python '
+                                'callable, gp_core.py:172).')
+    mu, sd = post.eval(Xm, mean_const=0.0, want_std=want_std)
+    return np.asarray(self.mean_func(X_test)) + mu, sd
+
+  def eval(self, X_test, uncert_form='none'):
+    """ gp_core.py:165-190.  'std' never forms the M x M covariance. """
+    if uncert_form not in ('none', 'std', 'covar'):
+      raise ValueError('uncert_form should be none, covar or std.')
+    if len(X_test) == 0:
+      return np.zeros((0,)), (None if uncert_form == 'none' else np.zeros((0,)))
+    if self.num_tr_data == 0:
+      raise NotImplementedError('eval with no training data is outside the device path.')
+    if uncert_form == 'covar':
+      raise NotImplementedError('uncert_form="covar" is served by draw_samples / dfb_ts_draws.')
+    return self._eval_on(self._post, X_test, uncert_form == 'std')
+
+  def _augmented_posterior(self, X_halluc):
+    """ gp_core.py:200-206: the GP with the pending points appended, variance only.  alpha is the
+        un-augmented alpha zero-extended, so mu = K_*aug alpha_aug == K_* alpha exactly. """
+    X_aug = list(self.X) + list(X_halluc)
+    saved_X = self.X
+    try:
+      self.X = X_aug
+      X_mat = self._train_matrix()
+    finally:
+      self.X = saved_X
+    y_aug = np.concatenate((self._y_centred, np.zeros(len(X_halluc))))
+    post, _, _ = self._build_on_device(X_mat, y_aug, _lib.DFB_BUILD_NO_ALPHA)
+    post.set_alpha(self.alpha)
+    return post
+
+  def eval_with_hallucinated_observations(self, X_test, X_halluc, uncert_form='none'):
+    """ gp_core.py:192-220 """
+    if uncert_form not in ('none', 'std', 'covar'):
+      raise ValueError('uncert_form should be none, covar or std.')
+    if uncert_form == 'none' or len(X_halluc) == 0:
+      return self.eval(X_test, uncert_form)
+    if uncert_form == 'covar':
+      raise NotImplementedError('uncert_form="covar" is served by draw_samples / dfb_ts_draws.')
+    post = self._augmented_posterior(X_halluc)
+    return self._eval_on(post, X_test, True)
+
+  # -- fused acquisition scoring (the body of gpb_acquisitions' objectives + np.argmax) -----------
+  def _device_posterior(self, halluc=None):
+    if halluc is None or len(halluc) == 0:
+      return self._post
+    return self._augmented_posterior(halluc)
+
+  def _fused_score(self, acq, pts, halluc=None, test_desc=None, mean_const=None,
+                   want_scores=False):
+    """ One dfb_score_argmax call: returns (best_score, best_index, scores or None). """
+    post = self._device_posterior(halluc)
+    mc = self._mean_const if mean_const is None else mean_const
+    if mc is None:
+      raise NotImplementedError('Fused acquisition scoring needs a constant mean function '
+                                '(what GPFitter.build_gp produces, gp_core.py:527-530).')
+    if test_desc is not None:
+      post.set_test_kernel(test_desc)
+    try:
+      return post.score_argmax(acq, self._test_matrix(pts), mean_const=mc, want_scores=want_scores)
+    finally:
+      if test_desc is not None:
+        post.set_test_kernel(None)
+
+  def _group_test_descriptor(self, add_kernel, kernel_j, group_j, train_dim):
+    """ K_*j = scale * k_j(X*_j, X[:, g_j]) (gpb_acquisitions.py:166-170): candidates have d_j
+        columns, the training matrix keeps all of its columns. """
+    from .kernel import AdditiveKernel
+    d_j = len(group_j)
+    single = AdditiveKernel(add_kernel.hyperparams['scale'], [kernel_j], [list(range(d_j))])
+    return build_descriptor(single, train_dim=train_dim, cand_dim=d_j,
+                            train_coords=[int(g) for g in group_j], cand_coords=list(range(d_j)))
+
+  # -- sampling (gp_core.py:250-261) --------------------------------------------------------------------
+  def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None):
+    raise NotImplementedError('draw_samples: the Thompson-sampling block path is not built yet.')
+
+  def draw_samples_with_hallucinated_observations(self, num_samples, X_test, X_halluc):
+    raise NotImplementedError('draw_samples: the Thompson-sampling block path is not built yet.')
+
+  def __str__(self):
+    return '%s, noise-var=%0.3f (n=%d)' % (self._child_str(), self.noise_var, len(self.Y))
+
+  def _child_str(self):
+    return 'B200-GP %s' % (str(self.kernel))
+
+  # copies share the (immutable) device posterior
+  def __deepcopy__(self, memo):
+    import copy as _copy
+    cls = self.__class__
+    new = cls.__new__(cls)
+    memo[id(self)] = new
+    for k, v in self.__dict__.items():
+      if k == '_post':
+        new.__dict__[k] = v
+      else:
+        new.__dict__[k] = _copy.deepcopy(v, memo)
+    return new

@@ -1,0 +1,355 @@
+"""
+Drop-in for the acquisition operator table of dragonfly/opt/gpb_acquisitions.py (:443-471): the
+`asy` / `syn` / `seq` Namespaces of fn(gp, anc_data) -> point, with the same anc_data fields
+(gp_bandit.py:462-484), the same use of NumPy's global RNG for candidates and coin flips, and the
+same return values -- but the objective evaluation AND the arg-max of `random_maximise`
+(oper_utils.py:59-80) run as one fused device call (dfb_score_argmax) instead of
+gp.eval(.., 'std') + scipy.stats + np.argmax on M x N / M x M host temporaries.
+
+Scope: acq_opt_method == 'rand' on Euclidean domains, which is the vectorised branch of
+maximise_acquisition (gpb_acquisitions.py:29-31).  The sequential one-point maximisers
+(DIRECT / PDOO, :32-37) are host tree searches outside the hot path; when a Dragonfly install is
+importable they are delegated to its own maximise_with_method with the device-backed gp.eval as
+the objective, otherwise they raise.
+"""
+from argparse import Namespace
+from copy import copy
+
+import numpy as np
+
+from .device import make_acq_desc
+from .kernel import build_descriptor
+from .domains import EuclideanDomain
+
+
+# ---------------------------------------------------------------------------------------------
+# Candidate generation: random_sample (oper_utils.py:59-67) + map_to_bounds (general_utils.py:25-27)
+# ---------------------------------------------------------------------------------------------
+def map_to_bounds(pts, bounds):
+  bounds = np.asarray(bounds, dtype=np.float64)
+  return pts * (bounds[:, 1] - bounds[:, 0]) + bounds[:, 0]
+
+
+def draw_candidates(bounds, max_evals):
+  """ rand_pts = map_to_bounds(np.random.random((int(max_evals), dim)), bounds) -- consumes the
+      global MT19937 stream exactly like the reference, so seeded runs pick identical candidates. """
+  dim = len(bounds)
+  return map_to_bounds(np.random.random((int(max_evals), dim)), bounds)
+
+
+def _check_rand_euclidean(anc_data):
+  if anc_data.domain.get_type() != 'euclidean':
+    raise NotImplementedError('Only Euclidean domains are on the B200 hot path.')
+  return anc_data.acq_opt_method in ['rand']
+
+
+def _fused_maximise(scorer, anc_data, bounds=None):
+  """ maximise_acquisition (:23-40) for the `rand` method: draw candidates, one device call,
+      return the arg-max point. """
+  bounds = anc_data.domain.bounds if bounds is None else bounds
+  rand_pts = draw_candidates(bounds, anc_data.max_evals)
+  _, idx, _ = scorer(rand_pts)
+  return rand_pts[idx]
+
+
+def _delegate_to_reference_maximiser(acq_fn, anc_data):
+  """ Non-vectorised maximisers are the reference's own host code (oper_utils.py / doo.py). """
+  try:
+    from dragonfly.exd.exd_utils import maximise_with_method  # pylint: disable=import-error
+  except ImportError:
+    raise NotImplementedError(
+        "acq_opt_method '%s' is a sequential host maximiser outside the B200 hot path; only 'rand' "
+        'is served without a Dragonfly install.' % (anc_data.acq_opt_method))
+  acquisition = lambda x: acq_fn(np.asarray(x).reshape((1, -1)))
+  _, opt_pt = maximise_with_method(anc_data.acq_opt_method, acquisition, anc_data.domain,
+                                   anc_data.max_evals)
+  return opt_pt
+
+
+# ---------------------------------------------------------------------------------------------
+# Parallel strategy: hallucinated observations (:43-64)
+# ---------------------------------------------------------------------------------------------
+def _halluc_points(anc_data):
+  if anc_data.handle_parallel == 'halluc' and len(anc_data.eval_points_in_progress) > 0:
+    if getattr(anc_data, 'is_mf', False):
+      return list(anc_data.eval_fidel_points_in_progress)
+    return list(anc_data.eval_points_in_progress)
+  return []
+
+
+def _posterior_for(gp, anc_data):
+  """ The device posterior the acquisition scores against: the GP's own, or the one augmented with
+      the evaluations in progress (variance only; means from the un-augmented GP). """
+  halluc = _halluc_points(anc_data)
+  if len(halluc) == 0:
+    return gp._device_posterior()
+  return gp._device_posterior(halluc)
+
+
+def _get_gp_eval_for_parallel_strategy(gp, anc_data, uncert_form='std'):
+  """ :43-64 -- host-callable eval closure (used by TTEI's reference point and the delegated
+      sequential maximisers). """
+  halluc = _halluc_points(anc_data)
+  if len(halluc) > 0:
+    return lambda x: gp.eval_with_hallucinated_observations(x, halluc, uncert_form=uncert_form)
+  return lambda x: gp.eval(x, uncert_form=uncert_form)
+
+
+def _get_syn_recommendations_from_asy(asy_acq, num_workers, list_of_gps, anc_datas):
+  """ :90-115 -- worker k sees the previous k-1 picks as hallucinations. """
+  def _next(objs):
+    ret = objs.pop(0)
+    return ret, objs + [ret]
+  if not hasattr(list_of_gps, '__iter__'):
+    list_of_gps = [list_of_gps] * num_workers
+  if not hasattr(anc_datas, '__iter__'):
+    anc_datas = [anc_datas] * num_workers
+  list_of_gps = [copy(gp) for gp in list_of_gps]
+  anc_datas = [copy(ad) for ad in anc_datas]
+  next_gp, list_of_gps = _next(list_of_gps)
+  next_anc_data, anc_datas = _next(anc_datas)
+  recommendations = [asy_acq(next_gp, next_anc_data)]
+  for _ in range(1, num_workers):
+    next_gp, list_of_gps = _next(list_of_gps)
+    next_anc_data, anc_datas = _next(anc_datas)
+    next_anc_data.eval_points_in_progress = recommendations
+    recommendations.append(asy_acq(next_gp, next_anc_data))
+  return recommendations
+
+
+# ---------------------------------------------------------------------------------------------
+# UCB (:202-227)
+# ---------------------------------------------------------------------------------------------
+def _get_gp_ucb_dim(gp):
+  if hasattr(gp, 'ucb_dim') and gp.ucb_dim is not None:
+    return gp.ucb_dim
+  elif hasattr(gp.kernel, 'dim'):
+    return gp.kernel.dim
+  return 3.0
+
+
+def _get_ucb_beta_th(dim, time_step):
+  return np.sqrt(0.5 * dim * np.log(2 * dim * time_step + 1))
+
+
+def asy_ucb(gp, anc_data):
+  beta_th = _get_ucb_beta_th(_get_gp_ucb_dim(gp), anc_data.t)
+  if _check_rand_euclidean(anc_data):
+    acq = make_acq_desc('ucb', beta=beta_th)
+    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+  gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
+  def _ucb_acq(x):
+    mu, sigma = gp_eval(x)
+    return mu + beta_th * sigma
+  return _delegate_to_reference_maximiser(_ucb_acq, anc_data)
+
+
+def syn_ucb(num_workers, list_of_gps, anc_datas):
+  return _get_syn_recommendations_from_asy(asy_ucb, num_workers, list_of_gps, anc_datas)
+
+
+# ---------------------------------------------------------------------------------------------
+# PI (:230-243), EI (:246-265), TTEI (:268-298)
+# ---------------------------------------------------------------------------------------------
+def asy_pi(gp, anc_data):
+  curr_best = anc_data.curr_max_val
+  if _check_rand_euclidean(anc_data):
+    acq = make_acq_desc('pi', best=curr_best)
+    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+  from scipy.stats import norm as normal_distro
+  gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
+  def _pi_acq(x):
+    mu, sigma = gp_eval(x)
+    return normal_distro.cdf((mu - curr_best) / sigma)
+  return _delegate_to_reference_maximiser(_pi_acq, anc_data)
+
+
+def syn_pi(num_workers, list_of_gps, anc_datas):
+  return _get_syn_recommendations_from_asy(asy_pi, num_workers, list_of_gps, anc_datas)
+
+
+def asy_ei(gp, anc_data):
+  curr_best = anc_data.curr_max_val
+  if _check_rand_euclidean(anc_data):
+    acq = make_acq_desc('ei', best=curr_best)
+    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+  from scipy.stats import norm as normal_distro
+  gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
+  def _ei_acq(x):
+    mu, sigma = gp_eval(x)
+    z = (mu - curr_best) / sigma
+    return sigma * (z * normal_distro.cdf(z) + normal_distro.pdf(z))
+  return _delegate_to_reference_maximiser(_ei_acq, anc_data)
+
+
+def syn_ei(num_workers, list_of_gps, anc_datas):
+  return _get_syn_recommendations_from_asy(asy_ei, num_workers, list_of_gps, anc_datas)
+
+
+def _ttei(gp, anc_data, ref_point):
+  """ :269-280 -- expected improvement over the reference arm. """
+  gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
+  ref_mean, ref_std = gp_eval([ref_point])
+  ref_mean = float(ref_mean[0])
+  ref_std = float(ref_std[0])
+  if _check_rand_euclidean(anc_data):
+    acq = make_acq_desc('ttei', ref_mean=ref_mean, ref_std=ref_std)
+    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+  from scipy.stats import norm as normal_distro
+  def _tt_ei_acq(x):
+    mu, sigma = gp_eval(x)
+    comb_std = np.sqrt(ref_std ** 2 + sigma ** 2)
+    z = (mu - ref_mean) / comb_std
+    return comb_std * (z * normal_distro.cdf(z) + normal_distro.pdf(z))
+  return _delegate_to_reference_maximiser(_tt_ei_acq, anc_data)
+
+
+def asy_ttei(gp, anc_data):
+  """ :282-294 -- coin flip between the EI point and the best challenger of the EI point. """
+  if np.random.random() < 0.5:
+    return asy_ei(gp, anc_data)
+  max_acq_opt_evals = anc_data.max_evals
+  anc_data = copy(anc_data)
+  anc_data.max_evals = max_acq_opt_evals // 2
+  ei_argmax = asy_ei(gp, anc_data)
+  return _ttei(gp, anc_data, ei_argmax)
+
+
+def syn_ttei(num_workers, list_of_gps, anc_data):
+  return _get_syn_recommendations_from_asy(asy_ttei, num_workers, list_of_gps, anc_data)
+
+
+# ---------------------------------------------------------------------------------------------
+# Add-UCB (:134-199)
+# ---------------------------------------------------------------------------------------------
+def _get_add_ucb_beta_th(dim, time_step):
+  return np.sqrt(0.2 * dim * np.log(2 * dim * time_step + 1))
+
+
+def _add_ucb(gp, add_kernel, mean_funcs, anc_data):
+  """ :139-189.  Per group j the candidates live in the d_j-dimensional sub-box; K_*j =
+      scale * k_j(X*_j, X[:, g_j]) is scored against the FULL additive GP's L and alpha. """
+  if mean_funcs is not None:
+    raise NotImplementedError('Add-UCB with per-group mean functions is not used by GPBandit '
+                              '(asy_add_ucb passes None).')
+  if not _check_rand_euclidean(anc_data):
+    raise NotImplementedError("Add-UCB on device needs acq_opt_method == 'rand'.")
+  kernel_list = add_kernel.kernel_list
+  groupings = add_kernel.groupings
+  total_max_evals = anc_data.max_evals
+  domain_bounds = np.asarray(anc_data.domain_bounds)
+  num_groups = len(kernel_list)
+  group_points = []
+  num_coordinates = 0
+  anc_data.max_evals = total_max_evals // num_groups
+  train_dim = gp._train_matrix().shape[1]
+  for group_j, kernel_j in zip(groupings, kernel_list):
+    betath_j = _get_add_ucb_beta_th(len(group_j), anc_data.t)
+    desc_j = gp._group_test_descriptor(add_kernel, kernel_j, group_j, train_dim)
+    acq = make_acq_desc('ucb', beta=betath_j)
+    anc_data_j = copy(anc_data)
+    anc_data_j.domain = EuclideanDomain(domain_bounds[group_j])
+    scorer = lambda pts, _d=desc_j, _a=acq: gp._fused_score(_a, pts, [], test_desc=_d,
+                                                            mean_const=0.0)
+    point_j = _fused_maximise(scorer, anc_data_j)
+    group_points.append(point_j)
+    num_coordinates += len(point_j)
+  anc_data.max_evals = total_max_evals
+  ret = np.zeros((num_coordinates,))
+  for point_j, group_j in zip(group_points, groupings):
+    ret[group_j] = point_j
+  return ret
+
+
+def asy_add_ucb(gp, anc_data):
+  return _add_ucb(gp, gp.kernel, None, anc_data)
+
+
+def syn_add_ucb(num_workers, list_of_gps, anc_datas):
+  return _get_syn_recommendations_from_asy(asy_add_ucb, num_workers, list_of_gps, anc_datas)
+
+
+# ---------------------------------------------------------------------------------------------
+# Thompson sampling (:118-131)
+# ---------------------------------------------------------------------------------------------
+def asy_ts(gp, anc_data):
+  """ :119-127 -- always the random maximiser with 4x the evaluations; the objective is one joint
+      posterior draw over all candidates (gp.draw_samples(1, x)). """
+  anc_data = copy(anc_data)
+  if anc_data.acq_opt_method != 'rand':
+    anc_data.acq_opt_method = 'rand'
+    anc_data.max_evals = 4 * anc_data.max_evals
+  halluc = _halluc_points(anc_data)
+  rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
+  if len(halluc) > 0:
+    sample = gp.draw_samples_with_hallucinated_observations(1, rand_pts, halluc).ravel()
+  else:
+    sample = gp.draw_samples(1, rand_pts).ravel()
+  return rand_pts[sample.argmax()]
+
+
+def syn_ts(num_workers, list_of_gps, anc_datas):
+  return _get_syn_recommendations_from_asy(asy_ts, num_workers, list_of_gps, anc_datas)
+
+
+# ---------------------------------------------------------------------------------------------
+# Random (:300-311)
+# ---------------------------------------------------------------------------------------------
+def asy_rand(_, anc_data):
+  """ :301-307 -- the vectorised objective returns ONE uniform, so arg-max is candidate 0. """
+  rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
+  np.random.random((1,))
+  return rand_pts[0]
+
+
+def syn_rand(num_workers, list_of_gps, anc_data):
+  return _get_syn_recommendations_from_asy(asy_rand, num_workers, list_of_gps, anc_data)
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-fidelity: the fidel_to_opt slice used by BOCA step 1 (:314-332)
+# ---------------------------------------------------------------------------------------------
+class _FidelToOptGP(object):
+  """ Every candidate row gets the same fidelity prefix z = fidel_to_opt before it reaches the
+      MF-GP (mfgp.eval_at_fidel([fidel_to_opt] * len(x), x)). """
+
+  def __init__(self, mfgp, fidel_to_opt):
+    self.mfgp = mfgp
+    self.fidel_to_opt = np.asarray(fidel_to_opt, dtype=np.float64).reshape(-1)
+    self.kernel = mfgp.get_domain_kernel()
+
+  def _zx(self, x):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+      x = x.reshape(1, -1)
+    return self.mfgp.get_ZX_matrix(np.repeat(self.fidel_to_opt.reshape(1, -1), len(x), axis=0), x)
+
+  def eval(self, x, *args, **kwargs):
+    return self.mfgp.eval(self._zx(x), *args, **kwargs)
+
+  def eval_with_hallucinated_observations(self, x, halluc_fidel_pts, *args, **kwargs):
+    return self.mfgp.eval_with_hallucinated_observations(self._zx(x), halluc_fidel_pts, *args,
+                                                         **kwargs)
+
+  def draw_samples(self, n, x, *args, **kwargs):
+    return self.mfgp.draw_samples(n, self._zx(x), *args, **kwargs)
+
+  def draw_samples_with_hallucinated_observations(self, n, x, halluc_fidel_pts, *args, **kwargs):
+    return self.mfgp.draw_samples_with_hallucinated_observations(n, self._zx(x), halluc_fidel_pts,
+                                                                 *args, **kwargs)
+
+  def _fused_score(self, acq, pts, halluc, **kwargs):
+    return self.mfgp._fused_score(acq, self._zx(pts), halluc, **kwargs)
+
+
+def _get_fidel_to_opt_gp(mfgp, fidel_to_opt):
+  return _FidelToOptGP(mfgp, fidel_to_opt)
+
+
+# The operator tables looked up by name at gp_bandit.py:490,510,651,681 ---------------------------
+syn = Namespace(ucb=syn_ucb, add_ucb=syn_add_ucb, ei=syn_ei, pi=syn_pi, ttei=syn_ttei, ts=syn_ts,
+                rand=syn_rand)
+asy = Namespace(ucb=asy_ucb, add_ucb=asy_add_ucb, ei=asy_ei, pi=asy_pi, ttei=asy_ttei, ts=asy_ts,
+                rand=asy_rand)
+seq = Namespace(ucb=asy_ucb, add_ucb=asy_add_ucb, ei=asy_ei, pi=asy_pi, ttei=asy_ttei, ts=asy_ts,
+                rand=asy_rand)

@@ -1,0 +1,211 @@
+/*
+ * dfb200.h -- C-ABI of libdfb200.so: the B200 (sm_100a) GP-BO inner loop behind Dragonfly's
+ * Kernel / GP / gpb_acquisitions surfaces.
+ *
+ * The reference (dragonfly-opt 0.1.7) is pure Python + NumPy/SciPy and has NO C/FFI boundary on this
+ * path; the entry points below are what a ctypes binding placed at the reference's
+ * three Python-level extension points would call.  Each one cites the reference function whose
+ * numeric body it replaces (paths relative to the reference tree).  INTEGRATION.md shows the
+ * reference-side ctypes stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns int: 0 = ok; > 0 = LAPACK-style info (dfb_build_posterior: the 1-based
+ *     index of the first non-positive pivot, i.e. np.linalg.LinAlgError in the reference -- the
+ *     HOST then walks the reference's jitter ladder, general_utils.py:183-203); < 0 = argument or
+ *     CUDA error, message in dfb_last_error().
+ *   - all floating point data is IEEE fp64, row-major.
+ *   - pointers named *_dev are device pointers on the handle's device (e.g. torch.Tensor.data_ptr());
+ *     pointers with a `space` argument are host (DFB_HOST) or device (DFB_DEVICE) pointers; host
+ *     buffers are copied inside the call on the handle's stream (pinned memory recommended).
+ *   - the library allocates NO large device memory: the caller sizes a workspace with
+ *     dfb_workspace_bytes() and hands it over with dfb_set_workspace().
+ *   - a handle is not thread-safe; work is issued on the stream given to dfb_set_stream()
+ *     (default: the legacy default stream) and calls that return host scalars synchronise it.
+ *   - there is no CPU fallback: without a CUDA device dfb_create() fails.
+ */
+#ifndef DFB200_H_
+#define DFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_VERSION 100
+
+/* ---- memory spaces ------------------------------------------------------------------------- */
+#define DFB_DEVICE 0
+#define DFB_HOST   1
+
+/* ---- kernel descriptor ------------------------------------------------------------------------
+ * Canonical sum-of-products form of the kernels on the hot path (dragonfly/gp/kernel.py):
+ *
+ *     k(x, y) = post_scale * SUM_t ( ((pre_scale_t * b_{t,0}) * b_{t,1}) * ... )
+ *
+ * where every base factor b is an SE or half-integer Matern kernel on a subset of coordinates,
+ * evaluated exactly in the reference's operation order:
+ *     x~ = x[coords] / bandwidths                                   kernel.py:179-181, 255-257
+ *     D2 = max(0, (|y~|^2 + |x~|^2) - 2 x~.y~)                      general_utils.py:58-70
+ *     SE      b = scale * exp(-D2 / 2)                              kernel.py:171-177
+ *     Matern  r = sqrt(D2); m = s8 * r; u = SUM_i coeffs[i] * m^(p-i);
+ *             u *= gamma_ratio * exp(-s2 * r); b = scale * u        kernel.py:259-270, 292-299
+ *             (scale here = hyperparams['scale'] * norm_constant, formed on the host)
+ *   SEKernel / MaternKernel      : 1 term, 1 factor, pre_scale 1, post_scale 1
+ *   AdditiveKernel               : G terms of 1 factor, post_scale = outer scale   kernel.py:484-494
+ *   CoordinateProductKernel (MF) : 1 term of F factors, pre_scale = outer scale    kernel.py:573-584
+ * A slot is one (coordinate, bandwidth) pair of one factor; the train and candidate matrices may
+ * use different column indices for the same slot (Add-UCB scores d_j-column candidates against
+ * columns g_j of the training matrix, gpb_acquisitions.py:160-168).
+ */
+#define DFB_MAX_FACTORS   48
+#define DFB_MAX_TERMS     48
+#define DFB_MAX_SLOTS     128
+#define DFB_MAX_MATERN_P  3
+
+#define DFB_BASE_SE      0
+#define DFB_BASE_MATERN  1
+
+typedef struct dfb_factor_desc {
+  int32_t kind;          /* DFB_BASE_SE | DFB_BASE_MATERN */
+  int32_t p;             /* Matern: nu = p + 1/2 (0 <= p <= DFB_MAX_MATERN_P) */
+  int32_t n_dims;        /* number of slots of this factor */
+  int32_t slot_off;      /* first slot */
+  double  scale;         /* SE: scale;  Matern: scale * norm_constant */
+  double  s8;            /* sqrt(8 nu) */
+  double  s2;            /* sqrt(2 nu) */
+  double  gamma_ratio;   /* Gamma(p+1) / Gamma(2p+1) */
+  double  coeffs[DFB_MAX_MATERN_P + 1];  /* (p+i)! / (i! (p-i)!) */
+} dfb_factor_desc;
+
+typedef struct dfb_kernel_desc {
+  int32_t n_terms;
+  int32_t n_factors;
+  int32_t n_slots;
+  int32_t train_dim;     /* columns of the training matrix */
+  int32_t cand_dim;      /* columns of the candidate matrix */
+  int32_t reserved;
+  double  post_scale;
+  double  kss;           /* k(x, x) for any x (all supported kernels are stationary) */
+  int32_t term_first_factor[DFB_MAX_TERMS + 1];
+  double  term_pre_scale[DFB_MAX_TERMS];
+  dfb_factor_desc factors[DFB_MAX_FACTORS];
+  int32_t slot_train_coord[DFB_MAX_SLOTS];
+  int32_t slot_cand_coord[DFB_MAX_SLOTS];
+  double  slot_bandwidth[DFB_MAX_SLOTS];
+} dfb_kernel_desc;
+
+/* ---- acquisition descriptor --------------------------------- dragonfly/opt/gpb_acquisitions.py */
+#define DFB_ACQ_MEAN  0   /* score = mu                                   (uncert_form 'none')    */
+#define DFB_ACQ_UCB   1   /* mu + beta * sigma                            :215-222, add_ucb :176  */
+#define DFB_ACQ_EI    2   /* sigma (z Phi(z) + phi(z)), z=(mu-best)/sigma :247-260                */
+#define DFB_ACQ_PI    3   /* Phi((mu - best)/sigma)                       :230-238                */
+#define DFB_ACQ_TTEI  4   /* EI against a reference arm (ref_mean, ref_std) :269-279              */
+
+typedef struct dfb_acq_desc {
+  int32_t kind;
+  int32_t reserved;
+  double  beta;        /* UCB: beta_th */
+  double  best;        /* EI / PI: curr_max_val */
+  double  ref_mean;    /* TTEI */
+  double  ref_std;     /* TTEI */
+} dfb_acq_desc;
+
+/* ---- build flags ----------------------------------------------------------------------------- */
+#define DFB_BUILD_FULL      0   /* L, W = L^-1, alpha, LML  (GP.build_posterior, gp_core.py:155-163) */
+#define DFB_BUILD_LML_ONLY  1   /* L and LML only           (GPFitter._tuning_objective, :551-563)   */
+#define DFB_BUILD_NO_ALPHA  2   /* L, W only; alpha is supplied with dfb_set_alpha (hallucinations)  */
+
+typedef struct dfb_handle dfb_handle;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int         dfb_version(void);
+const char* dfb_last_error(void);
+int         dfb_create(dfb_handle** out, int device);
+void        dfb_destroy(dfb_handle* h);
+int         dfb_set_stream(dfb_handle* h, void* cuda_stream);
+/* Bytes of device workspace needed for n_max training points, a kernel with n_slots slots and
+ * scoring chunks of `chunk` candidates (chunk = 0: library default).  */
+size_t      dfb_workspace_bytes(int64_t n_max, int32_t n_slots, int64_t chunk);
+int         dfb_set_workspace(dfb_handle* h, void* workspace_dev, size_t bytes, int64_t n_max,
+                              int64_t chunk);
+
+/* ---- model ------------------------------------------------------------------------------------
+ * dfb_set_kernel       : the GP's kernel (Kernel protocol, kernel.py:59-129), used for K(X, X).
+ * dfb_set_test_kernel  : optional different descriptor for K(X*, X) and k(x*, x*) -- Add-UCB's
+ *                        per-group kernel (gpb_acquisitions.py:160-176); NULL resets to the GP's.
+ * dfb_set_train        : GP.set_data (gp_core.py:127-133): X (n x d) and y - mean_func(X).
+ */
+int dfb_set_kernel(dfb_handle* h, const dfb_kernel_desc* desc);
+int dfb_set_test_kernel(dfb_handle* h, const dfb_kernel_desc* desc);
+int dfb_set_train(dfb_handle* h, const double* X_dev, int64_t n, int32_t d,
+                  const double* y_centred_dev);
+
+/* GP.build_posterior (gp_core.py:155-163) + compute_log_marginal_likelihood (:222-227):
+ * K = k(X,X); L = chol(K + (noise_var + jitter) I); alpha = L^-T L^-1 y_c; W = L^-1;
+ * lml = -1/2 y_c^T alpha - sum log L_ii - n/2 log 2 pi.  Returns info > 0 when the matrix is not
+ * positive definite (np.linalg.LinAlgError in stable_cholesky, general_utils.py:176-192).  */
+int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t flags,
+                        double* lml_out_host);
+/* max(diag K) of the last build -- the jitter ladder's scale (general_utils.py:183-189). */
+int dfb_get_max_diag(dfb_handle* h, double* out_host);
+/* Copies of gp.L (n x n lower), gp.alpha (n), gp.K_trtr_wo_noise (n x n); any may be NULL.
+ * Read directly by _add_ucb (gpb_acquisitions.py:169-171) and gp_core.py:203.  */
+int dfb_get_state(dfb_handle* h, double* L_dev, double* alpha_dev, double* K_dev);
+/* Overrides alpha (n values; shorter vectors are zero-extended): eval_with_hallucinated_observations
+ * takes the mean from the un-augmented GP and the variance from the augmented one
+ * (gp_core.py:192-220).  */
+int dfb_set_alpha(dfb_handle* h, const double* alpha_dev, int64_t n);
+
+/* ---- prediction -------------------------------------------------------------------------------
+ * GP.eval(X_test, 'none' | 'std') (gp_core.py:165-190): mu = mean_const + K_* alpha;
+ * sd = sqrt(k(x*,x*) - |L^-1 k_*|^2) (no clamp: NaN for negative variances, like np.sqrt).
+ * Never materialises the M x M covariance.  sd may be NULL (uncert_form 'none').  */
+int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t space,
+             double mean_const, double* mu, double* sd);
+/* GP.eval(X_test, 'covar'): full M x M posterior covariance (device pointers only; M bounded by the
+ * workspace chunk).  Used by draw_samples (gp_core.py:250-254).  */
+int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
+                   double* mu_dev, double* covar_dev);
+
+/* The fused acquisition maximiser: the body of asy_ucb / asy_ei / asy_pi / _ttei / _add_ucb's
+ * per-group objective + random_maximise's arg-max (oper_utils.py:70-80).  Scores every candidate
+ * row and returns the FIRST index of the maximum with NaN counting as the maximum (np.argmax).
+ * scores (m values, same space as Xc) may be NULL.  */
+int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, int64_t m,
+                     int32_t dc, int32_t space, double mean_const, double* scores,
+                     double* best_score_host, int64_t* best_index_host);
+
+/* Kernel.__call__(X1, X2) (kernel.py:72-83): the n1 x n2 Gram matrix, device pointers. */
+int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,
+                      int32_t d1, const double* X2_dev, int64_t n2, int32_t d2, double* K_dev);
+
+/* Thompson sampling (asy_ts, gpb_acquisitions.py:119-127; GP.draw_samples, gp_core.py:250-254;
+ * draw_gaussian_samples, general_utils.py:224-232): samples = (L_post U)^T + mu with
+ * L_post = chol(K** - V^T V [+ jitter]) for ONE block of m candidates (m bounded by the workspace).
+ * U_dev is the m x S matrix of standard normals (host-drawn for parity).  samples_dev is S x m.
+ * Returns info > 0 if the posterior covariance is not PD at this jitter.  */
+int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
+                 const double* U_dev, int32_t S, double jitter, double* samples_dev,
+                 double* max_diag_host);
+
+/* Counters for bench.py: number of kernels this handle has launched. */
+int64_t dfb_launch_count(dfb_handle* h);
+
+/* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
+ * class 0 = K_* build (+mu), 1 = the DMMA contraction |L^-1 k_*|^2, 2 = acquisition + arg-max,
+ * 3 = posterior build (whole dfb_build_posterior).  dfb_profile_read synchronises, returns the
+ * accumulated milliseconds, launches and work units (candidates for 0-2, builds for 3) and resets. */
+#define DFB_PROF_KSTAR 0
+#define DFB_PROF_GEMM  1
+#define DFB_PROF_ACQ   2
+#define DFB_PROF_BUILD 3
+int dfb_profile_enable(dfb_handle* h, int on);
+int dfb_profile_read(dfb_handle* h, int cls, double* ms_total, int64_t* launches, double* units);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DFB200_H_ */

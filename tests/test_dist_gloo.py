@@ -1,0 +1,76 @@
+"""
+The N > 1 path on CPU: two gloo processes shard a candidate set, each finds its local winner (with a
+NumPy stand-in for the device scorer -- the collective logic is what is under test), and the
+16-byte all-gather + lexicographic reduce must return exactly np.argmax of the whole set, including
+ties across the shard boundary and NaNs.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case, out_dir):
+  sys.path.insert(0, ROOT)
+  import torch.distributed as dist
+  from dragonfly_b200 import dist as D
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  scores = np.load(os.path.join(out_dir, 'scores_%s.npy' % case))
+
+  def score_fn(lo, hi):
+    local = scores[lo:hi]
+    idx = int(np.argmax(local))
+    return local[idx], idx
+  s, i = D.sharded_score_argmax(score_fn, len(scores))
+  np.save(os.path.join(out_dir, 'res_%s_%d.npy' % (case, rank)), np.array([s, float(i)]))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+CASES = {
+  'plain': lambda rs: rs.standard_normal(1001),
+  'tie_across_shards': lambda rs: np.where(np.arange(1000) % 400 == 150, 7.0, rs.uniform(0, 1, 1000)),
+  'nan_in_second_shard': lambda rs: np.where(np.arange(1000) == 777, np.nan, rs.uniform(0, 1, 1000)),
+  'nan_in_both': lambda rs: np.where((np.arange(1000) == 777) | (np.arange(1000) == 30), np.nan,
+                                     rs.uniform(0, 1, 1000)),
+  'tiny': lambda rs: np.array([3.0]),
+}
+
+
+@pytest.mark.parametrize('case', sorted(CASES.keys()))
+def test_two_rank_argmax_equals_numpy(tmp_path, case):
+  scores = CASES[case](np.random.RandomState(0))
+  np.save(os.path.join(str(tmp_path), 'scores_%s.npy' % case), scores)
+  port = 29500 + (os.getpid() % 2000) + sorted(CASES.keys()).index(case)
+  mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+  want = int(np.argmax(scores))
+  for r in range(2):
+    s, i = np.load(os.path.join(str(tmp_path), 'res_%s_%d.npy' % (case, r)))
+    assert int(i) == want
+    assert (np.isnan(s) and np.isnan(scores[want])) or s == scores[want]
+
+
+def test_shard_bounds_cover_everything():
+  from dragonfly_b200 import dist as D
+  for m in [0, 1, 7, 1000, 4000001]:
+    for world in [1, 2, 3, 8]:
+      edges = [D.shard_bounds(m, r, world) for r in range(world)]
+      assert edges[0][0] == 0 and edges[-1][1] == m
+      assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+      sizes = [hi - lo for lo, hi in edges]
+      assert max(sizes) - min(sizes) <= 1
+
+
+def test_reduce_pairs_order():
+  from dragonfly_b200 import dist as D
+  assert D.reduce_pairs([1.0, 2.0, 2.0], [5, 9, 3]) == (2.0, 3)
+  s, i = D.reduce_pairs([1.0, np.nan, np.nan], [0, 8, 4])
+  assert np.isnan(s) and i == 4
+  assert D.reduce_pairs([0.0, 5.0], [-1, 2]) == (5.0, 2)
+  assert D.reduce_pairs([], []) == (0.0, -1)

@@ -1,0 +1,358 @@
+"""
+Parity tests proper (-m gpu): the CUDA path, called through the C-ABI (ctypes) behind the mirrored
+Kernel / GP / gpb_acquisitions surfaces, against
+  (1) the committed golden fixtures = outputs of the UNMODIFIED reference (tests/golden/*.npz),
+  (2) the NumPy oracle on the same seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full N.
+Tolerances (BASELINE.json north_star): |d mu| <= 1e-10, |d sigma^2| <= 1e-8, arg-max index exact.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+MU_TOL = 1e-10
+VAR_TOL = 1e-8
+
+
+@pytest.fixture(scope='module')
+def B():
+  import torch
+  assert torch.cuda.is_available(), 'these tests need the B200'
+  from dragonfly_b200 import kernel, gp_core, mf_gp, gpb_acquisitions, domains, device, _lib
+  _lib.load()
+  return Namespace(kernel=kernel, gp_core=gp_core, mf_gp=mf_gp, acq=gpb_acquisitions,
+                   domains=domains, device=device, lib=_lib, torch=torch)
+
+
+def const_mean(c):
+  return lambda x: np.array([c] * len(x))
+
+
+def anc(B, acq, max_evals, t, d, curr_max, in_progress=(), **kw):
+  dom = B.domains.EuclideanDomain([[0, 1]] * d)
+  return Namespace(curr_acq=acq, max_evals=max_evals, t=t, domain=dom, curr_max_val=curr_max,
+                   eval_points_in_progress=list(in_progress), acq_opt_method='rand',
+                   handle_parallel='halluc', mf_strategy=None, is_mf=False,
+                   domain_bounds=np.array(dom.bounds), **kw)
+
+
+def close(a, b, rtol=0, atol=0):
+  np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+# ---- the reference's own known-answer vectors, on the device -----------------------------------------
+def test_kernel_known_answers_on_device(B):
+  """ unittest_kernel.py:82-124 restated: closed forms to 1e-10 (Frobenius norm). """
+  g = load_golden('known_answers')
+  d1, d2 = g['data_1'], g['data_2']
+  se = B.kernel.SEKernel(2, 2, [0.1, 1])
+  t11 = 2 * np.array([[1, np.exp(-406.25 / 2)], [np.exp(-406.25 / 2), 1]])
+  t12 = 2 * np.array([[1, np.exp(-404 / 2)], [np.exp(-406.25 / 2), np.exp(-0.25 / 2)]])
+  assert np.linalg.norm(t11 - se(d1)) < 1e-10
+  assert np.linalg.norm(t12 - se(d1, d2)) < 1e-10
+  close(se(d1, d2), g['se_12'], atol=1e-13)
+  for nu in [0.5, 1.5, 2.5]:
+    tag = str(nu).replace('.', 'p')
+    mk = B.kernel.MaternKernel(2, nu, 2.1, [0.1, 1])
+    assert mk.norm_constant == float(g['matern_%s_norm_constant' % tag])
+    close(mk(d1), g['matern_%s_11' % tag], atol=1e-13)
+    close(mk(d1, d2), g['matern_%s_12' % tag], atol=1e-13)
+    close(mk(d2), g['matern_%s_22' % tag], atol=1e-13)
+
+
+def test_dist_squared_known_answer_through_se(B):
+  """ unittest_general_utils.py:26-35: D2 = [[1,4,6],[0,1,3],[2.25,2.25,0.25]] (exact in fp64);
+      seen through k = exp(-D2/2) with unit scale and bandwidths. """
+  X1 = np.array([[1, 2, 3], [1, 2, 4], [2, 3, 4.5]])
+  X2 = np.array([[1, 2, 4], [1, 2, 5], [2, 3, 5]])
+  true = np.array([[1, 4, 6], [0, 1, 3], [2.25, 2.25, 0.25]])
+  K = B.kernel.SEKernel(3, 1.0, [1.0, 1.0, 1.0])(X1, X2)
+  close(K, np.exp(-true / 2), rtol=4e-16)
+
+
+def test_empty_inputs(B):
+  se = B.kernel.SEKernel(2, 1.0, [1.0, 1.0])
+  assert se(np.zeros((0, 2)), np.zeros((3, 2))).shape == (0, 3)
+  assert se(np.zeros((3, 2)), np.zeros((0, 2))).shape == (3, 0)
+
+
+# ---- C1: Branin 2-D, SE, N = 50 --------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def c1(B):
+  g = load_golden('c1_se')
+  kern = B.kernel.SEKernel(2, float(g['scale']), g['bws'])
+  gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  return g, gp
+
+
+def test_c1_posterior_state(c1):
+  g, gp = c1
+  close(gp.K_trtr_wo_noise, g['K'], atol=1e-12)
+  close(gp.L, g['L'], rtol=1e-9, atol=1e-11)
+  close(gp.alpha, g['alpha'], rtol=1e-8, atol=1e-10)
+  close(gp.compute_log_marginal_likelihood(), g['lml'], rtol=1e-11)
+  assert gp.jitter_power is None
+
+
+def test_c1_eval(c1):
+  g, gp = c1
+  mu, sd = gp.eval(g['C'], 'std')
+  close(mu, g['mu'], atol=MU_TOL)
+  close(sd ** 2, g['sd'] ** 2, atol=VAR_TOL)
+  mu0, none = gp.eval(g['C'], 'none')
+  assert none is None
+  close(mu0, g['mu_none'], atol=MU_TOL)
+  with pytest.raises(ValueError):
+    gp.eval(g['C'][:4], 'bogus')
+  # a single row, a list of rows (gp.X style), and ragged chunk edges
+  mu1, sd1 = gp.eval([g['C'][7]], 'std')
+  close(mu1, g['mu'][7:8], atol=MU_TOL)
+  mu2, sd2 = gp.eval(list(g['C'][:129]), 'std')
+  close(mu2, g['mu'][:129], atol=MU_TOL); close(sd2 ** 2, g['sd'][:129] ** 2, atol=VAR_TOL)
+
+
+def test_c1_device_tensor_candidates(B, c1):
+  g, gp = c1
+  Cd = B.torch.from_numpy(g['C']).cuda()
+  mu, sd = gp.eval(Cd, 'std')
+  assert mu.is_cuda and sd.is_cuda
+  close(mu.cpu().numpy(), g['mu'], atol=MU_TOL)
+  close(sd.cpu().numpy() ** 2, g['sd'] ** 2, atol=VAR_TOL)
+
+
+@pytest.mark.parametrize('name', ['ucb', 'ei', 'pi', 'ttei'])
+def test_c1_acquisition_scores_and_argmax(B, c1, name):
+  g, gp = c1
+  if name == 'ucb':
+    acq = B.device.make_acq_desc('ucb', beta=float(g['beta']))
+  elif name == 'ttei':
+    ri = int(g['ttei_ref_idx'])
+    acq = B.device.make_acq_desc('ttei', ref_mean=float(g['mu'][ri]), ref_std=float(g['sd'][ri]))
+  else:
+    acq = B.device.make_acq_desc(name, best=float(g['curr_best']))
+  best, idx, scores = gp._fused_score(acq, g['C'], want_scores=True)
+  assert idx == int(g['argmax_' + name])              # bit-exact arg-max index
+  close(scores, g[name], rtol=1e-7, atol=1e-9)
+  assert best == scores[idx]
+  # device-resident candidates give the same answer
+  best_d, idx_d, _ = gp._fused_score(acq, B.torch.from_numpy(g['C']).cuda())
+  assert idx_d == idx and best_d == best
+
+
+@pytest.mark.parametrize('name', ['ei', 'ucb', 'pi'])
+def test_c1_end_to_end_acquisition(B, c1, name):
+  """ asy_<acq>(gp, anc_data) with the same global seed returns the reference's point exactly. """
+  g, gp = c1
+  np.random.seed(7)
+  pt = getattr(B.acq.asy, name)(gp, anc(B, name, 1500, int(g['t']), 2, float(g['curr_best'])))
+  assert (pt == g['e2e_%s_point' % name]).all()
+
+
+def test_c1_hallucinated(B, c1):
+  g, gp = c1
+  mu_h, sd_h = gp.eval_with_hallucinated_observations(g['C'][:800], list(g['Xh']), 'std')
+  close(mu_h, g['mu_h'], atol=MU_TOL)
+  close(sd_h ** 2, g['sd_h'] ** 2, atol=VAR_TOL)
+  np.random.seed(7)
+  pt = B.acq.asy.ucb(gp, anc(B, 'ucb', 1000, int(g['t']), 2, float(g['curr_best']),
+                            in_progress=list(g['Xh'])))
+  assert (pt == g['e2e_h_point']).all()
+
+
+def test_c1_copies_share_the_posterior(c1):
+  from copy import copy, deepcopy
+  g, gp = c1
+  for cp in (copy(gp), deepcopy(gp)):
+    mu, _ = cp.eval(g['C'][:32], 'std')
+    close(mu, g['mu'][:32], atol=MU_TOL)
+
+
+def test_c1_chunking_is_invisible(B, c1):
+  """ Ragged multi-chunk scoring (chunk = 128 rows) equals single-chunk scoring bit for bit. """
+  g, gp = c1
+  post = B.device.DevicePosterior(len(g['X']), chunk=128)
+  post.set_kernel(B.kernel.build_descriptor(gp.kernel))
+  y_c = np.asarray(g['Y']) - float(g['mean_const'])
+  post.set_train(g['X'], y_c)
+  info, lml = post.build(float(g['noise_var']))
+  assert info == 0
+  close(lml, g['lml'], rtol=1e-11)
+  C = g['C'][:1003]
+  mu, sd = post.eval(C, mean_const=float(g['mean_const']))
+  mu_ref, sd_ref = gp.eval(C, 'std')
+  assert (mu == mu_ref).all() and (sd == sd_ref).all()
+  acq = B.device.make_acq_desc('ei', best=float(g['curr_best']))
+  b1, i1, _ = post.score_argmax(acq, C, mean_const=float(g['mean_const']))
+  b2, i2, _ = gp._fused_score(acq, C)
+  assert i1 == i2 and b1 == b2
+
+
+# ---- Hartmann-6 Matern, N = 300 -------------------------------------------------------------------------------
+@pytest.mark.parametrize('nu', [0.5, 1.5, 2.5])
+def test_matern_h6(B, nu):
+  g = load_golden('matern_h6')
+  tag = str(nu).replace('.', 'p')
+  kern = B.kernel.MaternKernel(6, nu, float(g['scale']), g['bws'])
+  gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  close(gp.alpha, g['alpha_' + tag], rtol=1e-8, atol=1e-9)
+  close(np.diag(gp.L), g['Ldiag_' + tag], rtol=1e-10)
+  close(gp.L[::7, ::5], g['Lsub_' + tag], rtol=1e-8, atol=1e-11)
+  close(gp.K_trtr_wo_noise[::7, ::5], g['Ksub_' + tag], atol=1e-13)
+  close(gp.compute_log_marginal_likelihood(), g['lml_' + tag], rtol=1e-11)
+  close(kern(g['C'][:64], g['X']), g['Kstar_sub_' + tag], atol=1e-13)
+  mu, sd = gp.eval(g['C'], 'std')
+  close(mu, g['mu_' + tag], atol=MU_TOL)
+  close(sd ** 2, g['sd_' + tag] ** 2, atol=VAR_TOL)
+  beta = B.acq._get_ucb_beta_th(6, int(g['t']))
+  assert beta == float(g['beta'])
+  _, i_ucb, s_ucb = gp._fused_score(B.device.make_acq_desc('ucb', beta=beta), g['C'], want_scores=True)
+  _, i_ei, s_ei = gp._fused_score(B.device.make_acq_desc('ei', best=float(g['curr_best'])), g['C'],
+                                  want_scores=True)
+  assert i_ucb == int(g['argmax_ucb_' + tag])
+  assert i_ei == int(g['argmax_ei_' + tag])
+  close(s_ucb, g['ucb_' + tag], atol=1e-8)
+  close(s_ei, g['ei_' + tag], rtol=1e-6, atol=1e-10)
+
+
+# ---- additive GP + Add-UCB ---------------------------------------------------------------------------------------
+def test_additive_and_add_ucb(B):
+  g = load_golden('additive')
+  groups = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+  sub = [B.kernel.MaternKernel(4, 2.5, 1.0, [0.5] * 4), B.kernel.SEKernel(4, 1.0, [0.4, 0.5, 0.6, 0.7]),
+         B.kernel.MaternKernel(2, 1.5, 1.0, [0.3, 0.45])]
+  kern = B.kernel.AdditiveKernel(float(g['scale']), sub, groups)
+  gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  close(gp.alpha, g['alpha'], rtol=1e-8, atol=1e-9)
+  close(gp.K_trtr_wo_noise[::5, ::3], g['Ksub'], atol=1e-12)
+  close(gp.compute_log_marginal_likelihood(), g['lml'], rtol=1e-11)
+  mu, sd = gp.eval(g['C'], 'std')
+  close(mu, g['mu'], atol=MU_TOL); close(sd ** 2, g['sd'] ** 2, atol=VAR_TOL)
+  for j in range(3):
+    desc = gp._group_test_descriptor(kern, sub[j], groups[j], 10)
+    beta_j = B.acq._get_add_ucb_beta_th(len(groups[j]), int(g['t']))
+    _, idx, score = gp._fused_score(B.device.make_acq_desc('ucb', beta=beta_j), g['Cj_%d' % j],
+                                    test_desc=desc, mean_const=0.0, want_scores=True)
+    close(score, g['score_j_%d' % j], atol=1e-8)
+    assert idx == int(g['argmax_j_%d' % j])
+  # after the per-group calls the GP's own kernel is restored
+  mu2, _ = gp.eval(g['C'][:50], 'std')
+  close(mu2, g['mu'][:50], atol=MU_TOL)
+  np.random.seed(11)
+  pt = B.acq.asy.add_ucb(gp, anc(B, 'add_ucb', 900, int(g['t']), 10, float(g['Y'].max())))
+  assert (pt == g['e2e_point']).all()
+
+
+# ---- multi-fidelity product kernel + the fidel_to_opt slice -----------------------------------------------------------
+def test_mf_product_kernel_and_fidel_slice(B):
+  g = load_golden('mf')
+  kF = B.kernel.SEKernel(1, 1.0, [0.7]); kD = B.kernel.MaternKernel(4, 2.5, 1.0, [0.4] * 4)
+  mfgp = B.mf_gp.EuclideanMFGP(list(g['Z']), list(g['Xd']), list(g['Y']), None, float(g['scale']), kF, kD,
+                               const_mean(float(g['mean_const'])), float(g['noise_var']))
+  close(mfgp.alpha, g['alpha'], rtol=1e-8, atol=1e-9)
+  close(mfgp.compute_log_marginal_likelihood(), g['lml'], rtol=1e-11)
+  mu, sd = mfgp.eval_at_fidel(list(g['Cz']), list(g['Cx']), uncert_form='std')
+  close(mu, g['mu'], atol=MU_TOL); close(sd ** 2, g['sd'] ** 2, atol=VAR_TOL)
+  boca_gp = B.acq._get_fidel_to_opt_gp(mfgp, g['f2o'])
+  mu_f, sd_f = boca_gp.eval(g['Cx'], uncert_form='std')
+  close(mu_f, g['mu_f'], atol=MU_TOL); close(sd_f ** 2, g['sd_f'] ** 2, atol=VAR_TOL)
+  assert B.acq._get_gp_ucb_dim(boca_gp) == 4
+  acq = B.device.make_acq_desc('ucb', beta=float(g['beta']))
+  _, idx, score = boca_gp._fused_score(acq, g['Cx'], [], want_scores=True)
+  close(score, g['ucb_f'], atol=1e-8)
+  assert idx == int(g['argmax_ucb_f'])
+
+
+# ---- jitter ladder -------------------------------------------------------------------------------------------------------
+def test_jitter_ladder(B):
+  g = load_golden('jitter')
+  kern = B.kernel.SEKernel(3, float(g['scale']), g['bws'])
+  import warnings
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(0.0), 0.0)
+  assert gp.jitter_power == int(g['power'])
+  close(gp.L, g['L'], rtol=1e-6, atol=1e-9)
+
+
+def test_not_pd_reports_info(B):
+  """ A singular matrix with no ladder: the device reports the LAPACK-style pivot index. """
+  g = load_golden('jitter')
+  post = B.device.DevicePosterior(len(g['X']))
+  post.set_kernel(B.kernel.build_descriptor(B.kernel.SEKernel(3, float(g['scale']), g['bws'])))
+  post.set_train(g['X'], g['Y'])
+  info, lml = post.build(0.0)
+  assert info > 0 and lml is None
+  with pytest.raises(B.lib.DfbError):
+    post.eval(g['C'])
+
+
+# ---- the hyper-parameter grid objective -------------------------------------------------------------------------------------
+def test_lml_grid(B):
+  g = load_golden('lml_grid')
+  X, Y = g['X'], g['Y']
+  post = B.device.DevicePosterior(len(X))
+  post.set_train(X, np.asarray(Y) - float(g['mean_const']))
+  lmls = []
+  for hp in g['hps']:
+    kern = B.kernel.MaternKernel(6, 2.5, np.exp(hp[1]), np.exp(hp[2:]))
+    post.set_kernel(B.kernel.build_descriptor(kern))
+    info, lml = post.build(np.exp(hp[0]), 0.0, B.lib.DFB_BUILD_LML_ONLY)
+    assert info == 0
+    lmls.append(lml)
+  close(lmls, g['lmls'], rtol=1e-10)
+
+
+# ---- oracle comparison at larger N, and properties at the metric's N ---------------------------------------------------------
+def _oracle_gp(w):
+  from oracle import gp_oracle as O
+  k = w['kernel']
+  kern = O.OMaternKernel(k['dim'], k['nu'], k['scale'], k['dim_bandwidths'])
+  return O, O.OGP(w['X'], w['Y'], kern, const_mean(w['mean_const']), w['noise_var'])
+
+
+def test_against_oracle_n2000(B):
+  """ BASELINE config 2 geometry (Hartmann-6, Matern-2.5, N = 2000) on a 600-candidate sample. """
+  from dragonfly_b200 import synth_data
+  w = synth_data.make_workload('c2_hartmann6_matern_ucb', n_cand=600)
+  O, ogp = _oracle_gp(w)
+  k = w['kernel']
+  gp = B.gp_core.GP(w['X'], w['Y'], B.kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                    const_mean(w['mean_const']), w['noise_var'])
+  close(gp.compute_log_marginal_likelihood(), ogp.compute_log_marginal_likelihood(), rtol=1e-10)
+  close(gp.alpha, ogp.alpha, rtol=1e-7, atol=1e-8)
+  mu_o, var_o = O.eval_std_diag(ogp, w['candidates'])
+  mu, sd = gp.eval(w['candidates'], 'std')
+  close(mu, mu_o, atol=MU_TOL); close(sd ** 2, var_o, atol=VAR_TOL)
+  beta = O.ucb_beta_th(6, 2000)
+  _, idx, _ = gp._fused_score(B.device.make_acq_desc('ucb', beta=beta), w['candidates'])
+  assert idx == O.np_argmax_first(O.acq_ucb(mu_o, np.sqrt(var_o), beta))
+
+
+def test_properties_at_n5000(B):
+  """ The metric's N (5000): properties that need no CPU reference --
+      (i) at the training inputs mu + noise * alpha reproduces y (K alpha = y_c - noise alpha),
+      (ii) 0 <= sigma^2 <= kss, (iii) sigma^2 at a training point is below the noise-limited bound,
+      (iv) arg-max returned == arg-max of the returned scores, first index on ties,
+      (v) duplicated candidates score identically. """
+  from dragonfly_b200 import synth_data
+  w = synth_data.make_workload('headline_hartmann6_matern_ei', n_cand=4000)
+  k = w['kernel']
+  gp = B.gp_core.GP(w['X'], w['Y'], B.kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                    const_mean(w['mean_const']), w['noise_var'])
+  Xs = w['X'][:512]
+  mu, sd = gp.eval(Xs, 'std')
+  y_c = w['Y'][:512] - w['mean_const']
+  close(mu - w['mean_const'] + w['noise_var'] * gp.alpha[:512], y_c, atol=1e-9)
+  assert (sd ** 2 <= w['noise_var'] * 1.0000001).all() and (sd ** 2 >= 0).all()
+  C = np.concatenate((w['candidates'], w['candidates'][:100]), axis=0)
+  acq = B.device.make_acq_desc('ei', best=float(w['Y'].max()))
+  best, idx, scores = gp._fused_score(acq, C, want_scores=True)
+  assert idx == int(np.argmax(scores)) and best == scores[idx]
+  assert (scores[-100:] == scores[:100]).all()
+  mu_c, sd_c = gp.eval(C, 'std')
+  assert (sd_c ** 2 <= k['scale'] * (1 + 1e-12)).all() and (sd_c ** 2 >= 0).all()

