@@ -81,6 +81,27 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   return c.off + 256;
 }
 
+static size_t carve_ts(dfb_handle* h, char* base, int64_t n_max, int64_t mb) {
+  const int64_t npad = round_up(n_max < 1 ? 1 : n_max, TILE);
+  const int64_t mbp = round_up(mb < 1 ? 1 : mb, TILE);
+  Carver c(base);
+  double* Vt = c.take<double>((size_t)mbp * npad);
+  double* cxs = c.take<double>((size_t)mbp * DFB_MAX_SLOTS);
+  double* cnrm = c.take<double>((size_t)mbp * DFB_MAX_FACTORS);
+  double* Cov = c.take<double>((size_t)mbp * mbp);
+  double* T2 = c.take<double>((size_t)(2 * mbp + TILE) * mbp);
+  double* Ut = c.take<double>((size_t)256 * mbp);
+  double* Sm = c.take<double>((size_t)256 * mbp);
+  double* mu = c.take<double>((size_t)mbp);
+  double* red = c.take<double>(8);
+  int* info = c.take<int>(4);
+  if (h != nullptr && base != nullptr) {
+    h->ts_Vt = Vt; h->ts_cxs = cxs; h->ts_cnrm = cnrm; h->ts_Cov = Cov; h->ts_T = T2; h->ts_Ut = Ut;
+    h->ts_Sm = Sm; h->ts_mu = mu; h->ts_red = red; h->ts_info = info; h->ts_mb = mbp;
+  }
+  return c.off + 256;
+}
+
 static int check_desc(const dfb_kernel_desc* d) {
   if (d == nullptr) { set_error("kernel descriptor is NULL"); return -1; }
   if (d->n_terms < 1 || d->n_terms > DFB_MAX_TERMS || d->n_factors < 1 ||
@@ -516,19 +537,107 @@ int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* 
   return 0;
 }
 
+// mu and the padded posterior covariance (h->ts_Cov, ld = mbp) of one block of m candidates:
+// K_* -> V^T = K_* W^T -> Cov = K** - V^T V    (gp_core.py:173-181)
+static int posterior_covariance(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc,
+                                double mean_const, int64_t* mbp_out) {
+  const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
+  const dfb_kernel_desc* d_desc = h->have_test_kernel ? h->d_desc_te : h->d_desc_tr;
+  const ScaledSet& ss = h->have_test_kernel ? h->te : h->tr;
+  if (h->ts_ws == nullptr) { set_error("no Thompson-sampling workspace: call dfb_set_ts_workspace first"); return -1; }
+  if (dc != desc.cand_dim) { set_error("candidates have %d columns, the kernel descriptor expects %d", dc, desc.cand_dim); return -1; }
+  const int64_t mbp = round_up(m, TILE);
+  if (m < 1 || mbp > h->ts_mb || mbp > h->chunk) { set_error("block of %lld candidates exceeds the TS workspace (%lld) / chunk (%lld)", (long long)m, (long long)h->ts_mb, (long long)h->chunk); return -1; }
+  DFB_TRY(ensure_train_scaled(h));
+  DFB_TRY(ensure_test_scaled(h));
+  const int64_t npad = h->npad;
+  const int nb = (int)(npad / TILE), mbb = (int)(mbp / TILE);
+  // K_* rows (zero rows beyond m) and mu
+  DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, Xc_dev, m, dc, mbp, h->Ks, npad,
+                       h->n, npad, mean_const, h->ts_mu, nullptr));
+  // V^T[a][i] = sum_{k <= i} K_*[a][k] W[i][k]
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = h->Ks; g.lda = npad; g.B = h->W; g.ldb = npad; g.D = h->ts_Vt; g.ldd = npad; g.alpha = 1.0;
+  g.mode = MODE_GENERIC; g.n_rb = mbb; g.n_cb = nb; g.K = (int)npad; g.tri = 2;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, mbb * nb));
+  // K** = kernel(X_test, X_test) (gp_core.py:179) with the candidates as both sides
+  DFB_TRY(launch_prep_scaled(h, d_desc, 0, Xc_dev, m, dc, h->ts_cxs, h->ts_cnrm, mbp));
+  DFB_TRY(launch_kstar(h, d_desc, desc, 0, h->ts_cxs, h->ts_cnrm, mbp, nullptr, Xc_dev, m, dc, mbp, h->ts_Cov,
+                       mbp, m, mbp, 0.0, nullptr, nullptr));
+  // Cov = K** - V^T V
+  memset(&g, 0, sizeof(g));
+  g.A = h->ts_Vt; g.lda = npad; g.B = h->ts_Vt; g.ldb = npad; g.C = h->ts_Cov; g.ldc = mbp;
+  g.D = h->ts_Cov; g.ldd = mbp; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = mbb; g.n_cb = mbb;
+  g.K = (int)npad;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, mbb * mbb));
+  *mbp_out = mbp;
+  return 0;
+}
+
+size_t dfb_ts_workspace_bytes(int64_t n_max, int64_t mb) { return carve_ts(nullptr, nullptr, n_max, mb); }
+
+int dfb_set_ts_workspace(dfb_handle* h, void* workspace_dev, size_t bytes, int64_t mb) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  if (workspace_dev == nullptr || mb < 1) { set_error("bad TS workspace arguments"); return -1; }
+  const size_t want = carve_ts(nullptr, nullptr, h->n_max, mb);
+  if (bytes < want) { set_error("TS workspace too small: %zu bytes given, %zu needed", bytes, want); return -1; }
+  if ((reinterpret_cast<uintptr_t>(workspace_dev) & 255) != 0) { set_error("TS workspace must be 256-byte aligned"); return -1; }
+  h->ts_ws = static_cast<char*>(workspace_dev);
+  carve_ts(h, h->ts_ws, h->n_max, mb);
+  return 0;
+}
+
 int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
                    double* mu_dev, double* covar_dev) {
-  (void)h; (void)Xc_dev; (void)m; (void)dc; (void)mean_const; (void)mu_dev; (void)covar_dev;
-  set_error("dfb_eval_covar: not implemented in this build");
-  return -3;
+  DFB_TRY(need(h, true, true, true, true, true));
+  if (Xc_dev == nullptr || mu_dev == nullptr || covar_dev == nullptr) { set_error("bad eval_covar arguments"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  int64_t mbp = 0;
+  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp));
+  DFB_TRY(launch_copy_pad(h, h->ts_mu, m, mu_dev, m));
+  DFB_TRY(launch_copy_rows(h, h->ts_Cov, mbp, covar_dev, m, m, m));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
-                 const double* U_dev, int32_t S, double jitter, double* samples_dev, double* max_diag_host) {
-  (void)h; (void)Xc_dev; (void)m; (void)dc; (void)mean_const; (void)U_dev; (void)S; (void)jitter;
-  (void)samples_dev; (void)max_diag_host;
-  set_error("dfb_ts_draws: not implemented in this build");
-  return -3;
+                 const double* Ut_dev, int32_t S, double jitter, double* samples_dev, double* mu_dev,
+                 double* max_diag_host) {
+  DFB_TRY(need(h, true, true, true, true, true));
+  if (Xc_dev == nullptr || Ut_dev == nullptr || samples_dev == nullptr || S < 1 || S > 256) { set_error("bad ts_draws arguments (1 <= S <= 256)"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  int64_t mbp = 0;
+  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp));
+  DFB_TRY(launch_diag_max(h, h->ts_Cov, mbp, m, h->ts_red));
+  // stable_cholesky(K) (general_utils.py:224-229): factorise Cov + jitter I (identity padding)
+  DFB_CUDA_OK(cudaMemsetAsync(h->ts_info, 0, sizeof(int) * 4, h->stream));
+  DFB_CUDA_OK(cudaMemsetAsync(h->ts_T, 0, sizeof(double) * (size_t)(2 * mbp + TILE) * mbp, h->stream));
+  DFB_TRY(launch_copy_rows(h, h->ts_Cov, mbp, h->ts_T, mbp, mbp, mbp));
+  DFB_TRY(launch_set_diag(h, h->ts_T, mbp, 0, m, jitter, 1));
+  DFB_TRY(launch_set_diag(h, h->ts_T, mbp, m, mbp, 1.0, 0));
+  DFB_TRY(factorise_tall(h, h->ts_T, mbp, h->Dinv, h->ts_info, false));
+  // samples^T = L_post U: samples[s][a] = sum_{b <= a} U^T[s][b] L[a][b]
+  const int64_t Sp = round_up(S, TILE);
+  DFB_CUDA_OK(cudaMemsetAsync(h->ts_Ut, 0, sizeof(double) * (size_t)Sp * mbp, h->stream));
+  DFB_TRY(launch_copy_rows(h, Ut_dev, m, h->ts_Ut, mbp, S, m));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = h->ts_Ut; g.lda = mbp; g.B = h->ts_T; g.ldb = mbp; g.D = h->ts_Sm; g.ldd = mbp; g.alpha = 1.0;
+  g.mode = MODE_GENERIC; g.n_rb = (int)(Sp / TILE); g.n_cb = (int)(mbp / TILE); g.K = (int)mbp; g.tri = 2;
+  g.info = h->ts_info;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, g.n_rb * g.n_cb));
+  DFB_TRY(launch_add_row_vector(h, h->ts_Sm, mbp, S, m, h->ts_mu));
+  DFB_TRY(launch_copy_rows(h, h->ts_Sm, mbp, samples_dev, m, S, m));
+  if (mu_dev != nullptr) DFB_TRY(launch_copy_pad(h, h->ts_mu, m, mu_dev, m));
+  double mx = 0.0;
+  int info = 0;
+  DFB_CUDA_OK(cudaMemcpyAsync(&mx, h->ts_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(&info, h->ts_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (max_diag_host != nullptr) *max_diag_host = mx;
+  if (info != 0) { set_error("posterior covariance is not positive definite at jitter %g (pivot %d)", jitter, info - 1); return info; }
+  return 0;
 }
 
 int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }

@@ -93,6 +93,20 @@ struct dfb_handle {
   dfb_kernel_desc* d_desc_te = nullptr;
   dfb_kernel_desc* d_desc_tmp = nullptr;
 
+  // optional Thompson-sampling workspace (api.cu: carve_ts())
+  char* ts_ws = nullptr;
+  int64_t ts_mb = 0;          // padded block capacity
+  double* ts_Vt = nullptr;    // mbp x npad   (L^-1 K_*^T)^T
+  double* ts_cxs = nullptr;   // slots x mbp  scaled candidate coordinates (SoA)
+  double* ts_cnrm = nullptr;  // factors x mbp
+  double* ts_Cov = nullptr;   // mbp x mbp    posterior covariance
+  double* ts_T = nullptr;     // (2 mbp + 128) x mbp factorisation buffer
+  double* ts_Ut = nullptr;    // 256 x mbp
+  double* ts_Sm = nullptr;    // 256 x mbp
+  double* ts_mu = nullptr;    // mbp
+  double* ts_red = nullptr;   // 4
+  int* ts_info = nullptr;
+
   // model state
   dfb_kernel_desc desc_tr;
   dfb_kernel_desc desc_te;

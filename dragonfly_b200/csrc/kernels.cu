@@ -32,37 +32,32 @@ __device__ __forceinline__ double base_kernel_value(const dfb_factor_desc& f, do
   return __dmul_rn(f.scale, u);
 }
 
-// (X**2).sum(axis=1) in NumPy's own association order (general_utils.py:66-67): add.reduce seeds the
-// output with the first element and adds pairwise_sum(rest): sequential from 0 for fewer than 8
-// remaining elements, else eight interleaved accumulators combined as ((r0+r1)+(r2+r3)) +
-// ((r4+r5)+(r6+r7)) plus a sequential tail (n <= 128: no recursive split).  Matching it keeps the
-// rounding noise of D2(x, x) = (|x|^2 + |x|^2) - 2 x.x -- which sqrt() amplifies to ~1e-8 for
-// Matern-1/2 -- identical to the reference's.
+// (X**2).sum(axis=1) in NumPy's own association order (general_utils.py:66-67): add.reduce starts
+// from the identity 0 and adds pairwise_sum(row): sequential for fewer than 8 elements, else eight
+// interleaved accumulators combined as ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) plus a sequential
+// tail (n <= 128: no recursive split).  Matching it keeps the rounding noise of
+// D2(x, x) = (|x|^2 + |x|^2) - 2 x.x -- which sqrt() amplifies to ~1e-8 for Matern-1/2 -- identical
+// to the reference's.
 template <typename F>
 __device__ __forceinline__ double numpy_sumsq(int n, F get) {
-  if (n <= 0) return 0.0;
-  const double x0 = get(0);
-  const double first = __dmul_rn(x0, x0);
-  const int m = n - 1;
-  if (m == 0) return first;
   double res;
-  if (m < 8) {
+  if (n < 8) {
     res = 0.0;
-    for (int i = 0; i < m; i++) { const double v = get(1 + i); res = __dadd_rn(res, __dmul_rn(v, v)); }
+    for (int i = 0; i < n; i++) { const double v = get(i); res = __dadd_rn(res, __dmul_rn(v, v)); }
   } else {
     double r[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { const double v = get(1 + q); r[q] = __dmul_rn(v, v); }
+    for (int q = 0; q < 8; q++) { const double v = get(q); r[q] = __dmul_rn(v, v); }
     int i = 8;
-    for (; i < m - (m % 8); i += 8) {
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-      for (int q = 0; q < 8; q++) { const double v = get(1 + i + q); r[q] = __dadd_rn(r[q], __dmul_rn(v, v)); }
+      for (int q = 0; q < 8; q++) { const double v = get(i + q); r[q] = __dadd_rn(r[q], __dmul_rn(v, v)); }
     }
     res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                     __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < m; i++) { const double v = get(1 + i); res = __dadd_rn(res, __dmul_rn(v, v)); }
+    for (; i < n; i++) { const double v = get(i); res = __dadd_rn(res, __dmul_rn(v, v)); }
   }
-  return __dadd_rn(first, res);
+  return res;
 }
 
 // ---- scaled training set: x~ = x / bw (SoA, j contiguous) and per-factor squared norms ----------
@@ -535,6 +530,22 @@ __global__ void set_diag_kernel(double* M, int64_t ld, int64_t from, int64_t to,
   if (i < to) M[i * ld + i] = add ? (M[i * ld + i] + v) : v;
 }
 
+// max over the first n diagonal entries (stable_cholesky's np.diag(M).max(), general_utils.py:184)
+__global__ void diag_max_kernel(const double* __restrict__ M, int64_t ld, int64_t n, double* out) {
+  __shared__ double sh[32];
+  double v = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v = fmax(v, M[i * ld + i]);
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (blockDim.x >> 5) ? sh[lane] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) out[0] = v;
+  }
+}
+
 // ================================================================================================
 // Host launchers
 // ================================================================================================
@@ -695,6 +706,13 @@ int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, in
   if (rows * cols <= 0) return 0;
   add_row_vector_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, h->stream>>>(M, ld, rows,
                                                                                     cols, v);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_diag_max(dfb_handle* h, const double* M, int64_t ld, int64_t n, double* out) {
+  diag_max_kernel<<<1, 1024, 0, h->stream>>>(M, ld, n, out);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;

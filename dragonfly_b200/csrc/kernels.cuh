@@ -30,6 +30,7 @@ int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const d
 int launch_reset_best(dfb_handle* h);
 int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, int64_t cols,
                           const double* v);
+int launch_diag_max(dfb_handle* h, const double* M, int64_t ld, int64_t n, double* out);
 int launch_fill(dfb_handle* h, double* p, int64_t n, double v);
 int launch_set_diag(dfb_handle* h, double* M, int64_t ld, int64_t from, int64_t to, double v, int add);
 

@@ -149,6 +149,51 @@ class DevicePosterior(object):
         C.byref(bi)), 'dfb_score_argmax')
     return bs.value, bi.value, sc
 
+  # -- joint posterior over one block: covariance and Thompson draws -----------------------------
+  TS_BLOCK = 4096
+
+  def _ensure_ts_workspace(self, m):
+    mb = getattr(self, '_ts_mb', 0)
+    if mb >= m:
+      return
+    mb = max(int(m), 512)
+    nbytes = self.lib.dfb_ts_workspace_bytes(self.n_max, mb)
+    self._ts_workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+    ptr = (self._ts_workspace.data_ptr() + 255) // 256 * 256
+    _lib.check(self.lib.dfb_set_ts_workspace(self.h, C.c_void_p(ptr), C.c_size_t(nbytes), mb),
+               'dfb_set_ts_workspace')
+    self._ts_mb = mb
+
+  def eval_covar(self, Xc, mean_const=0.0):
+    """ (mu, covar) of GP.eval(X, 'covar') for one block; host ndarray in -> host ndarrays out. """
+    Xd = _dev_f64(Xc, self.device)
+    m, dc = int(Xd.shape[0]), int(Xd.shape[1])
+    self._ensure_ts_workspace(m)
+    mu = torch.empty((m,), dtype=torch.float64, device=self.device)
+    cov = torch.empty((m, m), dtype=torch.float64, device=self.device)
+    _lib.check(self.lib.dfb_eval_covar(self.h, C.c_void_p(Xd.data_ptr()), m, dc, float(mean_const),
+                                       C.c_void_p(mu.data_ptr()), C.c_void_p(cov.data_ptr())),
+               'dfb_eval_covar')
+    if isinstance(Xc, torch.Tensor):
+      return mu, cov
+    return mu.cpu().numpy(), cov.cpu().numpy()
+
+  def ts_draws(self, Xc, Ut, mean_const=0.0, jitter=0.0):
+    """ One attempt of draw_gaussian_samples on a block: returns (info, samples (S, m), max_diag). """
+    Xd = _dev_f64(Xc, self.device)
+    Ud = _dev_f64(Ut, self.device)
+    m, dc = int(Xd.shape[0]), int(Xd.shape[1])
+    S = int(Ud.shape[0])
+    assert int(Ud.shape[1]) == m
+    self._ensure_ts_workspace(m)
+    out = torch.empty((S, m), dtype=torch.float64, device=self.device)
+    mx = C.c_double(0.0)
+    info = _lib.check(self.lib.dfb_ts_draws(self.h, C.c_void_p(Xd.data_ptr()), m, dc, float(mean_const),
+                                            C.c_void_p(Ud.data_ptr()), S, float(jitter),
+                                            C.c_void_p(out.data_ptr()), None, C.byref(mx)),
+                      'dfb_ts_draws')
+    return info, out, mx.value
+
   def launch_count(self):
     return int(self.lib.dfb_launch_count(self.h))
 

@@ -256,8 +256,20 @@ class GP(object):
     if self.num_tr_data == 0:
       raise NotImplementedError('eval with no training data is outside the device path.')
     if uncert_form == 'covar':
-      raise NotImplementedError('uncert_form="covar" is served by draw_samples / dfb_ts_draws.')
+      return self._eval_covar_on(self._post, X_test)
     return self._eval_on(self._post, X_test, uncert_form == 'std')
+
+  def _eval_covar_on(self, post, X_test):
+    """ The full M x M posterior covariance (gp_core.py:179-185) -- one device block, so M is
+        bounded (DevicePosterior.TS_BLOCK); 'std' is the path for large M. """
+    Xm = self._test_matrix(X_test)
+    if len(Xm) > post.TS_BLOCK:
+      raise NotImplementedError('uncert_form="covar" materialises an M x M matrix; M = %d exceeds '
+                                'the device block of %d.' % (len(Xm), post.TS_BLOCK))
+    if self._mean_const is not None:
+      return post.eval_covar(Xm, mean_const=self._mean_const)
+    mu, cov = post.eval_covar(Xm, mean_const=0.0)
+    return np.asarray(self.mean_func(X_test)) + mu, cov
 
   def _augmented_posterior(self, X_halluc):
     """ gp_core.py:200-206: the GP with the pending points appended, variance only.  alpha is the
@@ -280,9 +292,9 @@ class GP(object):
       raise ValueError('uncert_form should be none, covar or std.')
     if uncert_form == 'none' or len(X_halluc) == 0:
       return self.eval(X_test, uncert_form)
-    if uncert_form == 'covar':
-      raise NotImplementedError('uncert_form="covar" is served by draw_samples / dfb_ts_draws.')
     post = self._augmented_posterior(X_halluc)
+    if uncert_form == 'covar':
+      return self._eval_covar_on(post, X_test)
     return self._eval_on(post, X_test, True)
 
   # -- fused acquisition scoring (the body of gpb_acquisitions' objectives + np.argmax) -----------
@@ -317,11 +329,49 @@ class GP(object):
                             train_coords=[int(g) for g in group_j], cand_coords=list(range(d_j)))
 
   # -- sampling (gp_core.py:250-261) --------------------------------------------------------------------
+  def _draw_samples_on(self, post, num_samples, X_test):
+    """ draw_gaussian_samples (general_utils.py:224-232) per block of <= TS_BLOCK candidates:
+        L = stable_cholesky(covar) with the same jitter ladder, U = np.random.normal(size=(M, S))
+        drawn ONCE from the global RNG exactly like the reference, samples = (L U)^T + mu.
+        Blocks are sampled independently of each other: exact for M <= TS_BLOCK. """
+    from warnings import warn as _warn
+    Xm = self._test_matrix(X_test)
+    if self._mean_const is None:
+      raise NotImplementedError('Thompson sampling on device needs a constant mean function.')
+    M = len(Xm)
+    U = np.random.normal(size=(M, int(num_samples)))
+    out = np.empty((int(num_samples), M))
+    for lo in range(0, M, post.TS_BLOCK):
+      hi = min(M, lo + post.TS_BLOCK)
+      xb = Xm[lo:hi]
+      for s_lo in range(0, int(num_samples), 256):
+        s_hi = min(int(num_samples), s_lo + 256)
+        Ut = np.ascontiguousarray(U[lo:hi, s_lo:s_hi].T)
+        info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=0.0)
+        power = -11
+        while info != 0:
+          jitter = (10 ** power) * max_diag
+          info, smp, _ = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=jitter)
+          if info != 0:
+            power += 1
+            if power >= 5:
+              raise ValueError('Could not compute Cholesky decomposition despite adding %0.4f to '
+                               'the diagonal.' % (jitter))
+        out[s_lo:s_hi, lo:hi] = smp.cpu().numpy()
+    return out
+
   def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None):
-    raise NotImplementedError('draw_samples: the Thompson-sampling block path is not built yet.')
+    """ gp_core.py:250-254 """
+    if X_test is None:
+      raise NotImplementedError('draw_samples from a caller-supplied (mean, covar) is host-side '
+                                'NumPy in the reference and outside the device path.')
+    return self._draw_samples_on(self._post, num_samples, X_test)
 
   def draw_samples_with_hallucinated_observations(self, num_samples, X_test, X_halluc):
-    raise NotImplementedError('draw_samples: the Thompson-sampling block path is not built yet.')
+    """ gp_core.py:256-261 """
+    if len(X_halluc) == 0:
+      return self.draw_samples(num_samples, X_test)
+    return self._draw_samples_on(self._augmented_posterior(X_halluc), num_samples, X_test)
 
   def __str__(self):
     return '%s, noise-var=%0.3f (n=%d)' % (self._child_str(), self.noise_var, len(self.Y))

@@ -346,6 +346,91 @@ def _get_fidel_to_opt_gp(mfgp, fidel_to_opt):
   return _FidelToOptGP(mfgp, fidel_to_opt)
 
 
+def _add_ucb_for_boca(mfgp, fidel_to_opt, mean_funcs, anc_data):
+  """ :334-388 -- Add-UCB on the z = fidel_to_opt slice of an MF-GP whose domain kernel is additive:
+      K_*j = scale * k_F(Z_train, z) o k_j(X*_j, X[:, g_j]),  K**_j = scale * k_F(z, z) * k_j(X*_j, X*_j),
+      scored against the MF-GP's full L and alpha. """
+  if mean_funcs is not None:
+    raise NotImplementedError('per-group mean functions are not used by GPBandit.')
+  if not _check_rand_euclidean(anc_data):
+    raise NotImplementedError("Add-UCB on device needs acq_opt_method == 'rand'.")
+  from .kernel import CoordinateProductKernel
+  domain_kernel_list = mfgp.domain_kernel.kernel_list
+  groupings = mfgp.domain_kernel.groupings
+  total_max_evals = anc_data.max_evals
+  kern_scale = mfgp.kernel.hyperparams['scale']
+  domain_bounds = np.asarray(anc_data.domain_bounds)
+  num_groups = len(domain_kernel_list)
+  f2o = np.asarray(fidel_to_opt, dtype=np.float64).reshape(-1)
+  dz = len(f2o)
+  train_dim = mfgp._train_matrix().shape[1]
+  group_points = []
+  num_coordinates = 0
+  anc_data.max_evals = total_max_evals // num_groups
+  for group_j, kernel_j in zip(groupings, domain_kernel_list):
+    d_j = len(group_j)
+    betath_j = _get_add_ucb_beta_th(d_j, anc_data.t)
+    prod_j = CoordinateProductKernel(dz + d_j, kern_scale, [mfgp.fidel_kernel, kernel_j],
+                                     [list(range(dz)), list(range(dz, dz + d_j))])
+    train_coords = [mfgp.fidel_coords[i] for i in range(dz)] + \
+                   [mfgp.domain_coords[int(g)] for g in group_j]
+    desc_j = build_descriptor(prod_j, train_dim=train_dim, cand_dim=dz + d_j,
+                              train_coords=train_coords, cand_coords=list(range(dz + d_j)))
+    acq = make_acq_desc('ucb', beta=betath_j)
+    anc_data_j = copy(anc_data)
+    anc_data_j.domain = EuclideanDomain(domain_bounds[group_j])
+    def scorer(pts, _d=desc_j, _a=acq):
+      zx = np.concatenate((np.repeat(f2o.reshape(1, -1), len(pts), axis=0), pts), axis=1)
+      return mfgp._fused_score(_a, zx, [], test_desc=_d, mean_const=0.0)
+    point_j = _fused_maximise(scorer, anc_data_j)
+    group_points.append(point_j)
+    num_coordinates += len(point_j)
+  anc_data.max_evals = total_max_evals
+  ret = np.zeros((num_coordinates,))
+  for point_j, group_j in zip(group_points, groupings):
+    ret[group_j] = point_j
+  return ret
+
+
+def asy_add_ucb_for_boca(mfgp, fidel_to_opt, anc_data):
+  return _add_ucb_for_boca(mfgp, fidel_to_opt, None, anc_data)
+
+
+def boca(select_pt_func, mfgp, anc_data, func_caller):
+  """ :399-439 -- BOCA: (1) pick x with an ordinary acquisition on the fidel_to_opt slice (the
+      batched device path), (2) evaluate sigma at the candidate fidelities of that single x and
+      threshold against cost ratio x information gap (tiny; host logic kept as in the reference). """
+  if anc_data.curr_acq == 'add_ucb':
+    next_eval_point = asy_add_ucb_for_boca(mfgp, func_caller.fidel_to_opt, anc_data)
+  else:
+    fidel_to_opt_gp = _get_fidel_to_opt_gp(mfgp, func_caller.fidel_to_opt)
+    next_eval_point = select_pt_func(fidel_to_opt_gp, anc_data)
+  candidate_fidels, cost_ratios = func_caller.get_candidate_fidels_and_cost_ratios(
+      next_eval_point, filter_by_cost=True)
+  num_candidates = len(candidate_fidels)
+  cost_ratios = np.array(cost_ratios)
+  sqrt_cost_ratios = np.sqrt(cost_ratios)
+  information_gaps = np.array(func_caller.get_information_gap(candidate_fidels))
+  _, cand_fidel_stds = mfgp.eval_at_fidel(candidate_fidels, [next_eval_point] * num_candidates,
+                                          uncert_form='std')
+  cand_fidel_stds = cand_fidel_stds / np.sqrt(mfgp.kernel.hyperparams['scale'])
+  std_thresholds = anc_data.boca_thresh_coeff * anc_data.y_range * sqrt_cost_ratios * \
+                   information_gaps
+  qualifying_idxs = np.where(cand_fidel_stds > std_thresholds)[0]
+  if len(qualifying_idxs) == 0:
+    next_eval_fidel = func_caller.fidel_to_opt
+  else:
+    qualifying_fidels = [candidate_fidels[idx] for idx in qualifying_idxs]
+    qualifying_sqrt_cost_ratios = sqrt_cost_ratios[qualifying_idxs]
+    qualifying_cost_ratios = cost_ratios[qualifying_idxs]
+    next_eval_fidel_idx = qualifying_sqrt_cost_ratios.argmin()
+    if qualifying_cost_ratios[next_eval_fidel_idx] > anc_data.boca_max_low_fidel_cost_ratio:
+      next_eval_fidel = func_caller.fidel_to_opt
+    else:
+      next_eval_fidel = qualifying_fidels[next_eval_fidel_idx]
+  return next_eval_fidel, next_eval_point
+
+
 # The operator tables looked up by name at gp_bandit.py:490,510,651,681 ---------------------------
 syn = Namespace(ucb=syn_ucb, add_ucb=syn_add_ucb, ei=syn_ei, pi=syn_pi, ttei=syn_ttei, ts=syn_ts,
                 rand=syn_rand)

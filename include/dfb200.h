@@ -165,8 +165,13 @@ int dfb_set_alpha(dfb_handle* h, const double* alpha_dev, int64_t n);
  * Never materialises the M x M covariance.  sd may be NULL (uncert_form 'none').  */
 int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t space,
              double mean_const, double* mu, double* sd);
-/* GP.eval(X_test, 'covar'): full M x M posterior covariance (device pointers only; M bounded by the
- * workspace chunk).  Used by draw_samples (gp_core.py:250-254).  */
+/* Optional second workspace for the block-exact joint posterior (covariance / Thompson sampling)
+ * of up to `mb` candidates at a time (mb <= the scoring chunk).  */
+size_t dfb_ts_workspace_bytes(int64_t n_max, int64_t mb);
+int    dfb_set_ts_workspace(dfb_handle* h, void* workspace_dev, size_t bytes, int64_t mb);
+
+/* GP.eval(X_test, 'covar') (gp_core.py:165-187): mu (m) and the full m x m posterior covariance
+ * K** - V^T V, V = L^-1 K_*^T (device pointers; m <= mb).  Used by draw_samples (gp_core.py:250-254). */
 int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
                    double* mu_dev, double* covar_dev);
 
@@ -184,11 +189,13 @@ int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* 
 
 /* Thompson sampling (asy_ts, gpb_acquisitions.py:119-127; GP.draw_samples, gp_core.py:250-254;
  * draw_gaussian_samples, general_utils.py:224-232): samples = (L_post U)^T + mu with
- * L_post = chol(K** - V^T V [+ jitter]) for ONE block of m candidates (m bounded by the workspace).
- * U_dev is the m x S matrix of standard normals (host-drawn for parity).  samples_dev is S x m.
- * Returns info > 0 if the posterior covariance is not PD at this jitter.  */
+ * L_post = chol(K** - V^T V + jitter I) for ONE block of m <= mb candidates.  Ut_dev is U^T, the
+ * S x m matrix of standard normals (drawn on the host with np.random.normal for parity),
+ * samples_dev is S x m, mu_dev (m) may be NULL.  max_diag_host receives max(diag covariance), the
+ * scale of stable_cholesky's jitter ladder.  Returns info > 0 if the covariance is not PD at this
+ * jitter (the host then walks the ladder, general_utils.py:183-203).  S <= 256 per call.  */
 int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, double mean_const,
-                 const double* U_dev, int32_t S, double jitter, double* samples_dev,
+                 const double* Ut_dev, int32_t S, double jitter, double* samples_dev, double* mu_dev,
                  double* max_diag_host);
 
 /* Counters for bench.py: number of kernels this handle has launched. */

@@ -275,7 +275,87 @@ def case_lml_grid():
   save('lml_grid', X=X, Y=Y, hps=hps, lmls=np.array(lmls), mean_const=m0)
 
 
+def case_extra():
+  """ TTEI / synchronous batches / covariance / Thompson e2e / BOCA -- the remaining operator-table
+      entries, end to end through the reference with the global RNG seeded. """
+  from fake_mf_caller import FakeMFCaller
+  w = synth_data.make_workload('c1_branin_se_ei', n_cand=2000)
+  X, Y, C = w['X'], w['Y'], w['candidates']
+  k = w['kernel']
+  kern = SEKernel(2, k['scale'], k['dim_bandwidths'])
+  gp = GP(X, Y, kern, const_mean(w['mean_const']), w['noise_var'])
+  out = dict(X=X, Y=Y, C=C, scale=k['scale'], bws=k['dim_bandwidths'], mean_const=w['mean_const'],
+             noise_var=w['noise_var'], t=50, curr_best=float(Y.max()))
+  # TTEI: one seed per branch of the coin flip (gpb_acquisitions.py:284)
+  seeds = {}
+  for seed in range(40):
+    np.random.seed(seed)
+    branch = 'ei' if np.random.random() < 0.5 else 'tt'
+    if branch not in seeds:
+      seeds[branch] = seed
+    if len(seeds) == 2:
+      break
+  for branch, seed in seeds.items():
+    np.random.seed(seed)
+    out['ttei_%s_seed' % branch] = seed
+    out['ttei_%s_point' % branch] = ref_acq.asy.ttei(gp, anc('ttei', 1200, 50, 2, float(Y.max())))
+  # synchronous batches: worker k sees the previous picks as hallucinations
+  for name in ['ucb', 'ei']:
+    np.random.seed(21)
+    pts = getattr(ref_acq.syn, name)(3, gp, anc(name, 800, 50, 2, float(Y.max())))
+    out['syn_%s_points' % name] = np.array(pts)
+  # full covariance on 96 candidates
+  mu, covar = gp.eval(C[:96], 'covar')
+  out['covar_mu'] = mu
+  out['covar'] = covar
+  # Thompson sampling end to end (single joint draw over all candidates)
+  np.random.seed(4)
+  out['ts_point'] = ref_acq.asy.ts(gp, anc('ts', 700, 50, 2, float(Y.max())))
+  np.random.seed(4)
+  out['ts_point_halluc'] = ref_acq.asy.ts(gp, anc('ts', 500, 50, 2, float(Y.max()),
+                                                in_progress=list(C[:2])))
+  save('extra_c1', **out)
+
+  # BOCA on the MF GP of case_mf
+  rs = np.random.RandomState(0)
+  n, dz, dx = 150, 1, 4
+  Z = rs.random_sample((n, dz)); Xd = rs.random_sample((n, dx))
+  Ymf = synth_data.park1(Xd) * (0.7 + 0.3 * Z[:, 0])
+  kF = SEKernel(dz, 1.0, [0.7]); kD = MaternKernel(dx, 2.5, 1.0, [0.4] * dx)
+  scale = float(Ymf.var()); noise = 0.01 * float(Ymf.var()); m0 = float(np.median(Ymf))
+  mfgp = EuclideanMFGP(list(Z), list(Xd), list(Ymf), None, scale, kF, kD, const_mean(m0), noise)
+  caller = FakeMFCaller([1.0])
+  res = {}
+  for coeff in [1e-4, 0.5]:
+    np.random.seed(8)
+    a = anc('ucb', 600, n, dx, float(Ymf.max()), boca_thresh_coeff=coeff,
+            y_range=float(Ymf.max() - Ymf.min()), boca_max_low_fidel_cost_ratio=0.9)
+    a.is_mf = True
+    a.eval_fidel_points_in_progress = []
+    fid, pt = ref_acq.boca(ref_acq.asy.ucb, mfgp, a, caller)
+    tag = str(coeff).replace('.', 'p').replace('-', 'm')
+    res['boca_fidel_%s' % tag] = np.asarray(fid, dtype=np.float64)
+    res['boca_point_%s' % tag] = pt
+  # additive domain kernel: add_ucb_for_boca
+  groups = [[0, 1], [2, 3]]
+  kDa = AdditiveKernel(1.0, [MaternKernel(2, 2.5, 1.0, [0.4, 0.5]), SEKernel(2, 1.0, [0.3, 0.6])], groups)
+  mfgp_a = EuclideanMFGP(list(Z), list(Xd), list(Ymf), None, scale / 2, kF, kDa, const_mean(m0), noise)
+  np.random.seed(9)
+  a = anc('add_ucb', 600, n, dx, float(Ymf.max()), boca_thresh_coeff=1e-4,
+          y_range=float(Ymf.max() - Ymf.min()), boca_max_low_fidel_cost_ratio=0.9)
+  a.is_mf = True
+  a.eval_fidel_points_in_progress = []
+  fid, pt = ref_acq.boca(None, mfgp_a, a, caller)
+  res['boca_add_fidel'] = np.asarray(fid, dtype=np.float64)
+  res['boca_add_point'] = pt
+  res['alpha_add'] = mfgp_a.alpha
+  save('extra_mf', Z=Z, Xd=Xd, Y=Ymf, scale=scale, noise_var=noise, mean_const=m0, **res)
+
+
 if __name__ == '__main__':
+  if len(sys.argv) > 1 and sys.argv[1] == 'extra':
+    case_extra()
+    sys.exit(0)
   known_answers()
   case_c1_se()
   case_matern()
@@ -284,3 +364,4 @@ if __name__ == '__main__':
   case_ts()
   case_jitter()
   case_lml_grid()
+  case_extra()

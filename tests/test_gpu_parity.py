@@ -356,3 +356,112 @@ def test_properties_at_n5000(B):
   assert (scores[-100:] == scores[:100]).all()
   mu_c, sd_c = gp.eval(C, 'std')
   assert (sd_c ** 2 <= k['scale'] * (1 + 1e-12)).all() and (sd_c ** 2 >= 0).all()
+
+
+# ---- TTEI, synchronous batches, full covariance, Thompson sampling end to end -----------------------------
+@pytest.fixture(scope='module')
+def extra_c1(B):
+  g = load_golden('extra_c1')
+  kern = B.kernel.SEKernel(2, float(g['scale']), g['bws'])
+  gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  return g, gp
+
+
+@pytest.mark.parametrize('branch', ['ei', 'tt'])
+def test_ttei_end_to_end(B, extra_c1, branch):
+  """ asy_ttei: coin flip, EI arg-max as the reference arm, second maximisation (:269-294). """
+  g, gp = extra_c1
+  np.random.seed(int(g['ttei_%s_seed' % branch]))
+  pt = B.acq.asy.ttei(gp, anc(B, 'ttei', 1200, int(g['t']), 2, float(g['curr_best'])))
+  assert (pt == g['ttei_%s_point' % branch]).all()
+
+
+@pytest.mark.parametrize('name', ['ucb', 'ei'])
+def test_synchronous_batch(B, extra_c1, name):
+  """ syn_<acq>: worker k scores against the GP hallucinated with picks 0..k-1 (:90-115). """
+  g, gp = extra_c1
+  np.random.seed(21)
+  pts = getattr(B.acq.syn, name)(3, gp, anc(B, name, 800, int(g['t']), 2, float(g['curr_best'])))
+  assert (np.array(pts) == g['syn_%s_points' % name]).all()
+
+
+def test_eval_covar(B, extra_c1):
+  g, gp = extra_c1
+  mu, covar = gp.eval(g['C'][:96], 'covar')
+  close(mu, g['covar_mu'], atol=MU_TOL)
+  close(covar, g['covar'], atol=VAR_TOL)
+  assert covar.shape == (96, 96)
+  mu_s, sd = gp.eval(g['C'][:96], 'std')
+  close(sd ** 2, np.diag(covar), atol=1e-12)
+
+
+def test_thompson_end_to_end(B, extra_c1):
+  """ asy_ts: one joint posterior draw over all candidates (M x M covariance, stable_cholesky,
+      normals from the global RNG), arg-max of the draw -- identical point to the reference. """
+  g, gp = extra_c1
+  np.random.seed(4)
+  pt = B.acq.asy.ts(gp, anc(B, 'ts', 700, int(g['t']), 2, float(g['curr_best'])))
+  assert (pt == g['ts_point']).all()
+  np.random.seed(4)
+  pt = B.acq.asy.ts(gp, anc(B, 'ts', 500, int(g['t']), 2, float(g['curr_best']),
+                           in_progress=list(g['C'][:2])))
+  assert (pt == g['ts_point_halluc']).all()
+
+
+def test_thompson_draws_with_supplied_normals(B):
+  """ gp.draw_samples against the reference's samples for the same normal matrix (golden ts.npz):
+      the global RNG is re-seeded so np.random.normal hands out the recorded U. """
+  g = load_golden('ts')
+  kern = B.kernel.MaternKernel(20, 2.5, float(g['scale']), g['bws'])
+  gp = B.gp_core.GP(g['X'], g['Y'], kern, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  np.random.seed(2)
+  samples = gp.draw_samples(8, g['C'])
+  assert samples.shape == (8, 256)
+  close(samples, g['samples'], atol=2e-6)      # L_post of a near-singular covariance: cond * eps
+  assert (samples.argmax(axis=1) == g['argmax']).all()
+  mu, covar = gp.eval(g['C'], 'covar')
+  close(mu, g['mu'], atol=MU_TOL)
+  close(np.diag(covar), g['covar_diag'], atol=VAR_TOL)
+
+
+# ---- BOCA (multi-fidelity selection) ------------------------------------------------------------------------------
+def _mf_anc(B, acq, g, coeff, dx=4):
+  a = anc(B, acq, 600, 150, dx, float(g['Y'].max()), boca_thresh_coeff=coeff,
+          y_range=float(g['Y'].max() - g['Y'].min()), boca_max_low_fidel_cost_ratio=0.9)
+  a.is_mf = True
+  a.eval_fidel_points_in_progress = []
+  return a
+
+
+def test_boca(B):
+  import os, sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  from fake_mf_caller import FakeMFCaller
+  g = load_golden('extra_mf')
+  kF = B.kernel.SEKernel(1, 1.0, [0.7]); kD = B.kernel.MaternKernel(4, 2.5, 1.0, [0.4] * 4)
+  mfgp = B.mf_gp.EuclideanMFGP(list(g['Z']), list(g['Xd']), list(g['Y']), None, float(g['scale']), kF, kD,
+                               const_mean(float(g['mean_const'])), float(g['noise_var']))
+  caller = FakeMFCaller([1.0])
+  for coeff in [1e-4, 0.5]:
+    tag = str(coeff).replace('.', 'p').replace('-', 'm')
+    np.random.seed(8)
+    fid, pt = B.acq.boca(B.acq.asy.ucb, mfgp, _mf_anc(B, 'ucb', g, coeff), caller)
+    assert (pt == g['boca_point_%s' % tag]).all()
+    assert (np.asarray(fid, dtype=np.float64) == g['boca_fidel_%s' % tag]).all()
+
+
+def test_add_ucb_for_boca(B):
+  import os, sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  from fake_mf_caller import FakeMFCaller
+  g = load_golden('extra_mf')
+  kF = B.kernel.SEKernel(1, 1.0, [0.7])
+  kDa = B.kernel.AdditiveKernel(1.0, [B.kernel.MaternKernel(2, 2.5, 1.0, [0.4, 0.5]),
+                                      B.kernel.SEKernel(2, 1.0, [0.3, 0.6])], [[0, 1], [2, 3]])
+  mfgp = B.mf_gp.EuclideanMFGP(list(g['Z']), list(g['Xd']), list(g['Y']), None, float(g['scale']) / 2, kF,
+                               kDa, const_mean(float(g['mean_const'])), float(g['noise_var']))
+  close(mfgp.alpha, g['alpha_add'], rtol=1e-8, atol=1e-9)
+  np.random.seed(9)
+  fid, pt = B.acq.boca(None, mfgp, _mf_anc(B, 'add_ucb', g, 1e-4), FakeMFCaller([1.0]))
+  assert (pt == g['boca_add_point']).all()
+  assert (np.asarray(fid, dtype=np.float64) == g['boca_add_fidel']).all()
