@@ -1,0 +1,145 @@
+"""
+The hyper-parameter "grid" objective of GPFitter on the device:
+
+  GPFitter._tuning_objective (gp_core.py:551-563)  = LML of the GP built from one hp vector
+  GPFitter.build_gp (gp_core.py:501-543)           : [mean const if mean_func_type == 'tune'],
+                                                     [log noise if noise_var_type == 'tune'], child hps
+  EuclideanGPFitter._child_build_gp (euclidean_gp.py:325-339) /
+  get_euclidean_integral_gp_kernel_with_scale (:808-900): log scale, log bandwidth (x d or x 1),
+                                                     discrete nu for Matern
+  _rand_exp_sampling_wrap (gp_core.py:439-445)     : probs = exp(lml - max lml), normalised
+
+Each objective evaluation is one DFB_BUILD_LML_ONLY factorisation (K build + blocked Cholesky with
+the y row riding along; no L^-1, no alpha).  The samples are independent, so under torch.distributed
+they shard across ranks with one all-gather of the LML values at the end (NCCL on GPUs, gloo in the
+CPU tests of the sharding logic).
+"""
+import numpy as np
+
+from . import _lib
+from .kernel import SEKernel, MaternKernel, build_descriptor
+from .gp_core import stable_cholesky_on_device
+
+
+class EuclideanHPLayout(object):
+  """ How a continuous hp vector maps to (mean const, noise var, kernel) for an SE / Matern GP. """
+
+  def __init__(self, dim, kernel_type='matern', nu=2.5, use_same_bandwidth=False,
+               mean_func_type='median', mean_func_const=0.0, noise_var_type='tune',
+               noise_var_label=0.05, noise_var_value=0.1):
+    if kernel_type not in ('se', 'matern'):
+      raise NotImplementedError('kernel_type %s is outside the B200 hot-path scope.' % (kernel_type))
+    self.dim, self.kernel_type, self.nu = dim, kernel_type, nu
+    self.use_same_bandwidth = use_same_bandwidth
+    self.mean_func_type, self.mean_func_const = mean_func_type, mean_func_const
+    self.noise_var_type = noise_var_type
+    self.noise_var_label, self.noise_var_value = noise_var_label, noise_var_value
+
+  def num_hps(self):
+    n = 1 + (1 if self.use_same_bandwidth else self.dim)
+    n += 1 if self.mean_func_type == 'tune' else 0
+    n += 1 if self.noise_var_type == 'tune' else 0
+    return n
+
+  def unpack(self, hp, Y, nu=None):
+    """ gp_core.py:509-538 + euclidean_gp.py:801-861 """
+    hp = list(np.asarray(hp, dtype=np.float64))
+    Y = np.asarray(Y, dtype=np.float64)
+    if self.mean_func_type == 'mean':
+      mean_const = np.mean(Y)
+    elif self.mean_func_type == 'median':
+      mean_const = np.median(Y)
+    elif self.mean_func_type == 'upper_bound':
+      mean_const = np.mean(Y) + 3 * np.std(Y)
+    elif self.mean_func_type == 'const':
+      mean_const = self.mean_func_const
+    elif self.mean_func_type == 'tune':
+      mean_const = hp.pop(0)
+    else:
+      mean_const = 0
+    if self.noise_var_type == 'tune':
+      noise_var = np.exp(hp.pop(0))
+    elif self.noise_var_type == 'label':
+      noise_var = self.noise_var_label * (Y.std() ** 2)
+    else:
+      noise_var = self.noise_var_value
+    scale = np.exp(hp.pop(0))
+    if self.use_same_bandwidth:
+      bws = [np.exp(hp.pop(0))] * self.dim
+    else:
+      bws = [np.exp(hp.pop(0)) for _ in range(self.dim)]
+    assert len(hp) == 0
+    if self.kernel_type == 'se':
+      kern = SEKernel(self.dim, scale, bws)
+    else:
+      kern = MaternKernel(self.dim, self.nu if nu is None else nu, scale, bws)
+    return float(mean_const), float(noise_var), kern
+
+
+def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None):
+  """ LML of the GP built from each hp vector (rows of `hps`); `nus` optionally gives the discrete
+      Matern nu per sample.  Returns (lmls, post) -- `post` can be passed back in to reuse the
+      device workspace. """
+  from .device import DevicePosterior
+  X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+  Y = np.asarray(Y, dtype=np.float64)
+  if post is None or post.n_max < len(X):
+    post = DevicePosterior(len(X), device=device)
+  lmls = np.empty(len(hps))
+  last_mean = None
+  for i, hp in enumerate(hps):
+    mean_const, noise_var, kern = layout.unpack(hp, Y, None if nus is None else nus[i])
+    if last_mean is None or mean_const != last_mean:
+      post.set_train(X, Y - mean_const)
+      last_mean = mean_const
+    post.set_kernel(build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
+    lml, _ = stable_cholesky_on_device(post, noise_var, flags=_lib.DFB_BUILD_LML_ONLY)
+    lmls[i] = lml
+  return lmls, post
+
+
+def rand_exp_sampling_probs(lml_vals):
+  """ gp_core.py:443-444 """
+  lml_vals = np.asarray(lml_vals, dtype=np.float64)
+  probs = np.exp(lml_vals - max(lml_vals))
+  return probs / probs.sum()
+
+
+def sharded_lml_grid(X, Y, hps, layout, nus=None, device=None, group=None):
+  """ Rank r evaluates hps[lo:hi]; one all-gather of the fp64 LML values.  Every rank returns the
+      full vector and the rand_exp_sampling probabilities. """
+  import torch
+  import torch.distributed as dist
+  from .dist import shard_bounds
+  hps = np.asarray(hps, dtype=np.float64)
+  H = len(hps)
+  if not (dist.is_available() and dist.is_initialized()):
+    lmls, _ = lml_for_hyperparams(X, Y, hps, layout, nus, device=device)
+    return lmls, rand_exp_sampling_probs(lmls)
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  lo, hi = shard_bounds(H, rank, world)
+  mine, _ = lml_for_hyperparams(X, Y, hps[lo:hi], layout, None if nus is None else nus[lo:hi],
+                                device=device) if hi > lo else (np.empty(0), None)
+  return gather_shards(mine, H, group=group, device=device)
+
+
+def gather_shards(mine, total, group=None, device=None):
+  """ All-gather of variable-length fp64 shards (padded to the largest shard). """
+  import torch
+  import torch.distributed as dist
+  from .dist import shard_bounds
+  world = dist.get_world_size(group)
+  backend = dist.get_backend(group)
+  dev = torch.device('cpu') if backend == 'gloo' else (
+      torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device('cuda', device))
+  cap = max(shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world))
+  buf = torch.zeros(max(cap, 1), dtype=torch.float64, device=dev)
+  buf[:len(mine)] = torch.from_numpy(np.asarray(mine, dtype=np.float64)).to(dev)
+  out = [torch.empty_like(buf) for _ in range(world)]
+  dist.all_gather(out, buf, group=group)
+  parts = []
+  for r in range(world):
+    lo, hi = shard_bounds(total, r, world)
+    parts.append(out[r][:hi - lo].cpu().numpy())
+  lmls = np.concatenate(parts) if parts else np.empty(0)
+  return lmls, rand_exp_sampling_probs(lmls)

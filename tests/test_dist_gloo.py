@@ -74,3 +74,32 @@ def test_reduce_pairs_order():
   assert np.isnan(s) and i == 4
   assert D.reduce_pairs([0.0, 5.0], [-1, 2]) == (5.0, 2)
   assert D.reduce_pairs([], []) == (0.0, -1)
+
+
+def _gather_worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT)
+  import torch.distributed as dist
+  from dragonfly_b200 import hp_grid
+  from dragonfly_b200 import dist as D
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  total = 7
+  lo, hi = D.shard_bounds(total, rank, world)
+  mine = np.arange(lo, hi, dtype=np.float64) * -1.5 - 3.0        # stand-in LML values
+  lmls, probs = hp_grid.gather_shards(mine, total)
+  np.save(os.path.join(out_dir, 'gather_%d.npy' % rank), np.stack([lmls, probs]))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_rank_hp_grid_gather(tmp_path):
+  """ The hp-grid all-gather (uneven shards 3 + 4) and the rand_exp_sampling weights. """
+  port = 31500 + (os.getpid() % 2000)
+  mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  want = np.arange(7, dtype=np.float64) * -1.5 - 3.0
+  w = np.exp(want - want.max()); w /= w.sum()
+  for r in range(2):
+    lmls, probs = np.load(os.path.join(str(tmp_path), 'gather_%d.npy' % r))
+    assert (lmls == want).all()
+    assert np.allclose(probs, w, rtol=1e-15)

@@ -392,7 +392,7 @@ def test_eval_covar(B, extra_c1):
   close(covar, g['covar'], atol=VAR_TOL)
   assert covar.shape == (96, 96)
   mu_s, sd = gp.eval(g['C'][:96], 'std')
-  close(sd ** 2, np.diag(covar), atol=1e-12)
+  close(sd ** 2, np.diag(covar), rtol=1e-11, atol=1e-12)
 
 
 def test_thompson_end_to_end(B, extra_c1):
@@ -465,3 +465,19 @@ def test_add_ucb_for_boca(B):
   fid, pt = B.acq.boca(None, mfgp, _mf_anc(B, 'add_ucb', g, 1e-4), FakeMFCaller([1.0]))
   assert (pt == g['boca_add_point']).all()
   assert (np.asarray(fid, dtype=np.float64) == g['boca_add_fidel']).all()
+
+
+def test_hp_grid_through_the_fitter_layout(B):
+  """ GPFitter's objective (gp_core.py:551-563) for hp vectors laid out as build_gp /
+      _child_build_gp unpack them; rand_exp_sampling weights (gp_core.py:443-444). """
+  from dragonfly_b200 import hp_grid
+  g = load_golden('lml_grid')
+  layout = hp_grid.EuclideanHPLayout(6, 'matern', nu=2.5, mean_func_type='median', noise_var_type='tune')
+  assert layout.num_hps() == 8
+  lmls, post = hp_grid.lml_for_hyperparams(g['X'], g['Y'], g['hps'], layout)
+  close(lmls, g['lmls'], rtol=1e-10)
+  probs = hp_grid.rand_exp_sampling_probs(lmls)
+  want = np.exp(g['lmls'] - g['lmls'].max()); want /= want.sum()
+  close(probs, want, rtol=1e-7, atol=1e-12)
+  lmls2, _ = hp_grid.sharded_lml_grid(g['X'], g['Y'], g['hps'][:3], layout)   # no process group: local
+  close(lmls2[0], g['lmls'][:3], rtol=1e-10)
