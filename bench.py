@@ -325,7 +325,7 @@ def run_ours(args):
       'gpu_launches': int(n_launch),
       'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                    'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
-                   'kernel': 'gemm_tn_kernel<EPI_SUMSQ> (fp64 DMMA: V = L^-1 K_*^T fused with |v|^2)',
+                   'kernel': 'score_tma_kernel (fp64 DMMA, TMA + mbarrier ring: V = L^-1 K_*^T fused with |v|^2)',
                    'flops_per_candidate': flops_per_cand,
                    'launch_ms_avg': gemm_ms / max(gemm_launches, 1), 'launches_timed': int(gemm_launches),
                    'peak_source': 'live cuBLAS DGEMM 8192^3 burst on this GPU (MEASURED_PEAKS.json has '

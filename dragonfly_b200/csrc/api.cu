@@ -2,7 +2,9 @@
 // No CPU fallback anywhere: every entry point drives CUDA kernels on the handle's stream.
 #include <stdarg.h>
 #include <new>
+#include <stdlib.h>
 #include "kernels.cuh"
+#include "gemm_tma.h"
 
 namespace dfb {
 
@@ -271,7 +273,13 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       g.n_rb = nb; g.n_cb = (int)(m_rows / TILE); g.K = (int)npad;
       g.partial = h->partial; g.ld_partial = Mc;
       DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
-      DFB_TRY(launch_gemm(h, g, EPI_SUMSQ, g.n_rb * g.n_cb));
+      if (h->gemm_impl == 1 && h->tma_ready) {
+        ScoreTmaArgs ta;
+        ta.n_rb = g.n_rb; ta.n_cb = g.n_cb; ta.K = g.K; ta.partial = g.partial; ta.ld_partial = g.ld_partial;
+        DFB_TRY(launch_score_tma(h, h->tmW, h->tmK, ta));
+      } else {
+        DFB_TRY(launch_gemm(h, g, EPI_SUMSQ, g.n_rb * g.n_cb));
+      }
       DFB_TRY(prof_end(h, DFB_PROF_GEMM, (double)mc));
     }
     if (want_std || do_argmax || sc_dev != nullptr) {
@@ -322,6 +330,8 @@ int dfb_create(dfb_handle** out, int device) {
   dfb_handle* h = new (std::nothrow) dfb_handle();
   if (h == nullptr) { set_error("out of host memory"); return -2; }
   h->device = device;
+  const char* impl = getenv("DFB200_GEMM");       // "v1" = cp.async ring, "tma" = TMA + mbarrier ring
+  h->gemm_impl = (impl != nullptr && strcmp(impl, "v1") == 0) ? 0 : 1;   // default: TMA ring
   *out = h;
   return 0;
 }
@@ -447,6 +457,12 @@ int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t 
   h->noise_plus_jitter = noise_var + jitter;
   h->have_post = true;
   h->have_w = with_bottom;
+  h->tma_ready = false;
+  if (with_bottom && h->gemm_impl == 1) {
+    DFB_TRY(make_tensor_map_2d_f64(&h->tmW, h->W, npad, npad, npad));
+    DFB_TRY(make_tensor_map_2d_f64(&h->tmK, h->Ks, h->chunk, npad, npad));
+    h->tma_ready = true;
+  }
   if (lml_out_host != nullptr) {
     const double quad = (flags == DFB_BUILD_FULL) ? red[1] : red[2];
     *lml_out_host = -0.5 * quad - red[0] - 0.5 * (double)n * log(2.0 * M_PI);
@@ -641,6 +657,26 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
 }
 
 int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }
+
+int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (name == nullptr) { set_error("option name is NULL"); return -1; }
+  if (strcmp(name, "gemm_impl") == 0) {
+    if (value != 0 && value != 1) { set_error("gemm_impl must be 0 (cp.async) or 1 (TMA)"); return -1; }
+    h->gemm_impl = (int)value;
+    h->tma_ready = false;
+    if (value == 1 && h->have_post && h->have_w) {
+      DFB_CUDA_OK(cudaSetDevice(h->device));
+      DFB_TRY(make_tensor_map_2d_f64(&h->tmW, h->W, h->npad, h->npad, h->npad));
+      DFB_TRY(make_tensor_map_2d_f64(&h->tmK, h->Ks, h->chunk, h->npad, h->npad));
+      h->tma_ready = true;
+    }
+    return 0;
+  }
+  if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
+  set_error("unknown option '%s'", name);
+  return -1;
+}
 
 int dfb_profile_enable(dfb_handle* h, int on) {
   DFB_TRY(need(h, false, false, false, false, false));

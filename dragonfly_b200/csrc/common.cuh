@@ -1,5 +1,6 @@
 // Shared declarations for libdfb200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -106,6 +107,13 @@ struct dfb_handle {
   double* ts_mu = nullptr;    // mbp
   double* ts_red = nullptr;   // 4
   int* ts_info = nullptr;
+
+  // TMA path of the scoring contraction (gemm_tma.cuh)
+  int gemm_impl = 1;          // 0 = v1 cp.async ring, 1 = v2 TMA + mbarrier ring (default)
+  int kstar_fast = 1;         // specialised K_* kernel for plain SE / Matern on <= 8 dims
+  bool tma_ready = false;
+  CUtensorMap tmW;            // W  (npad x npad)
+  CUtensorMap tmK;            // Ks (chunk x npad)
 
   // model state
   dfb_kernel_desc desc_tr;

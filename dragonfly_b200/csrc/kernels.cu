@@ -2,6 +2,7 @@
 // the diagonal-block Cholesky/inverse, small vector kernels and the acquisition + arg-max.
 // sm_100a only.  Reference paths are relative to the reference tree (dragonfly-opt 0.1.7).
 #include "kernels.cuh"
+#include "gemm_tma.cuh"
 
 namespace dfb {
 
@@ -220,6 +221,140 @@ kstar_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coo
   if (mu != nullptr) {
 #pragma unroll
     for (int r = 0; r < KSTAR_R; r++) {
+      double s = mu_acc[r];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int64_t cand = cand0 + r;
+      if (lane == 0 && cand < m) mu[cand] = mean_const + s;
+    }
+  }
+}
+
+// ---- fast path of kstar_kernel for the plain SE / Matern kernels (1 term, 1 factor, d <= 8) ------------
+// Same arithmetic, same operation order; what changes is the bookkeeping: kind, p and d are compile
+// time, the candidate coordinates live in registers and each warp carries KF_R independent candidate
+// rows through the exp/sqrt dependency chains.  (The generic kernel spends ~220 of its ~270
+// instructions per entry interpreting the descriptor: profiles/r01_kstar_ncu_summary.txt.)
+constexpr int KF_R = 4;
+constexpr int KF_WARPS = 4;
+constexpr int KF_CANDS = KF_R * KF_WARPS;
+
+template <int KIND, int P>
+__device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, double d2) {
+  if (KIND == DFB_BASE_SE) return __dmul_rn(f.scale, exp(__dmul_rn(d2, -0.5)));
+  const double dist = sqrt(d2);
+  const double mm = __dmul_rn(f.s8, dist);
+  double u;
+  if (P == 0) {
+    u = __dadd_rn(0.0, __dmul_rn(f.coeffs[0], 1.0));
+  } else if (P == 1) {
+    u = __dadd_rn(0.0, __dmul_rn(f.coeffs[0], mm));
+    u = __dadd_rn(u, __dmul_rn(f.coeffs[1], 1.0));
+  } else {
+    u = __dadd_rn(0.0, __dmul_rn(f.coeffs[0], __dmul_rn(mm, mm)));
+    u = __dadd_rn(u, __dmul_rn(f.coeffs[1], mm));
+    u = __dadd_rn(u, __dmul_rn(f.coeffs[2], 1.0));
+  }
+  const double w = __dmul_rn(f.gamma_ratio, exp(__dmul_rn(-f.s2, dist)));
+  return __dmul_rn(f.scale, __dmul_rn(u, w));
+}
+
+template <int KIND, int P, int D>
+__global__ void __launch_bounds__(KF_WARPS * 32)
+kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coords,
+                  const double* __restrict__ xsT, const double* __restrict__ nrmT, int64_t npad_tr,
+                  const double* __restrict__ alpha, const double* __restrict__ Xc, int64_t m, int dc,
+                  int64_t m_rows, double* __restrict__ Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
+                  double mean_const, double* __restrict__ mu, double* __restrict__ kss_out) {
+  __shared__ dfb_factor_desc fsh;
+  __shared__ int coord_sh[8];
+  __shared__ double bw_sh[8];
+  __shared__ double scal_sh[2];
+  if (threadIdx.x == 0) {
+    fsh = desc_g->factors[0];
+    scal_sh[0] = desc_g->term_pre_scale[0];
+    scal_sh[1] = desc_g->post_scale;
+  }
+  if (threadIdx.x < D) {
+    coord_sh[threadIdx.x] = cand_uses_train_coords ? desc_g->slot_train_coord[threadIdx.x]
+                                                   : desc_g->slot_cand_coord[threadIdx.x];
+    bw_sh[threadIdx.x] = desc_g->slot_bandwidth[threadIdx.x];
+  }
+  __syncthreads();
+  const dfb_factor_desc f = fsh;
+  const double pre = scal_sh[0], post = scal_sh[1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t cand0 = (int64_t)blockIdx.x * KF_CANDS + warp * KF_R;
+  if (cand0 >= m_rows) return;
+
+  double xc[KF_R][D], nc[KF_R];
+#pragma unroll
+  for (int r = 0; r < KF_R; r++) {
+    const int64_t cand = cand0 + r;
+#pragma unroll
+    for (int q = 0; q < D; q++) xc[r][q] = (cand < m) ? Xc[cand * dc + coord_sh[q]] / bw_sh[q] : 0.0;
+    double s = 0.0;                    // numpy_sumsq for n < 8; n == 8 uses the 8-accumulator form
+    if (D < 8) {
+#pragma unroll
+      for (int q = 0; q < D; q++) s = __dadd_rn(s, __dmul_rn(xc[r][q], xc[r][q]));
+    } else {
+      s = numpy_sumsq(D, [&](int q) { return xc[r][q]; });
+    }
+    nc[r] = s;
+  }
+  if (kss_out != nullptr && lane == 0) {
+#pragma unroll
+    for (int r = 0; r < KF_R; r++) {
+      const int64_t cand = cand0 + r;
+      if (cand < m) {
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) dot = fma(xc[r][q], xc[r][q], dot);
+        double d2 = __dadd_rn(__dadd_rn(nc[r], nc[r]), -2.0 * dot);
+        d2 = fmax(d2, 0.0);
+        const double prod = __dmul_rn(pre, base_value_fast<KIND, P>(f, d2));
+        kss_out[cand] = __dmul_rn(post, __dadd_rn(0.0, prod));
+      }
+    }
+  }
+
+  double mu_acc[KF_R];
+#pragma unroll
+  for (int r = 0; r < KF_R; r++) mu_acc[r] = 0.0;
+  for (int64_t j = lane; j < n_write; j += 32) {
+    double kv[KF_R];
+#pragma unroll
+    for (int r = 0; r < KF_R; r++) kv[r] = 0.0;
+    double aj = 0.0;
+    if (j < n_valid) {
+      double xt[D];
+#pragma unroll
+      for (int q = 0; q < D; q++) xt[q] = xsT[(int64_t)q * npad_tr + j];
+      const double nt2 = nrmT[j];
+      if (alpha != nullptr) aj = alpha[j];
+#pragma unroll
+      for (int r = 0; r < KF_R; r++) {
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) dot = fma(xc[r][q], xt[q], dot);
+        double d2 = __dadd_rn(__dadd_rn(nt2, nc[r]), -2.0 * dot);
+        d2 = fmax(d2, 0.0);
+        const double prod = __dmul_rn(pre, base_value_fast<KIND, P>(f, d2));
+        kv[r] = __dmul_rn(post, __dadd_rn(0.0, prod));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < KF_R; r++) {
+      const int64_t cand = cand0 + r;
+      if (cand < m_rows) {
+        const double v = (cand < m) ? kv[r] : 0.0;
+        Ks[cand * ldk + j] = v;
+        mu_acc[r] = fma(v, aj, mu_acc[r]);
+      }
+    }
+  }
+  if (mu != nullptr) {
+#pragma unroll
+    for (int r = 0; r < KF_R; r++) {
       double s = mu_acc[r];
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const int64_t cand = cand0 + r;
@@ -575,6 +710,55 @@ int launch_gemm(dfb_handle* h, const GemmArgs& g, int epi, int n_blocks) {
   return 0;
 }
 
+// ---- TMA tensor maps + the v2 scoring kernel ---------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int make_tensor_map_2d_f64(CUtensorMap* out, const double* base, int64_t rows, int64_t cols_ld,
+                           int64_t cols) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DFB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return -2;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols_ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)TILE};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+static bool g_tma_attr = false;
+int launch_score_tma(dfb_handle* h, const CUtensorMap& tmW, const CUtensorMap& tmK,
+                     const ScoreTmaArgs& g) {
+  const int n_blocks = g.n_rb * g.n_cb;
+  if (n_blocks <= 0) return 0;
+  if (!g_tma_attr) {
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)TMA_SMEM_BYTES));
+    g_tma_attr = true;
+  }
+  score_tma_kernel<<<n_blocks, TMA_THREADS, TMA_SMEM_BYTES, h->stream>>>(tmW, tmK, g);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_prep_scaled(dfb_handle* h, const dfb_kernel_desc* d_desc, int use_train_coords,
                        const double* X, int64_t n, int d, double* xs, double* nrm, int64_t npad) {
   const int threads = 128;
@@ -585,12 +769,51 @@ int launch_prep_scaled(dfb_handle* h, const dfb_kernel_desc* d_desc, int use_tra
   return 0;
 }
 
+template <int KIND, int P>
+static bool launch_kstar_fast_d(dfb_handle* h, int d, unsigned blocks, const dfb_kernel_desc* d_desc,
+                                int ctc, const double* xsT, const double* nrmT, int64_t npad_tr,
+                                const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows,
+                                double* Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
+                                double mean_const, double* mu, double* kss_out) {
+#define DFB_KF_CASE(DD)                                                                              \
+  case DD:                                                                                           \
+    kstar_fast_kernel<KIND, P, DD><<<blocks, KF_WARPS * 32, 0, h->stream>>>(                         \
+        d_desc, ctc, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid, n_write,        \
+        mean_const, mu, kss_out);                                                                    \
+    return true;
+  switch (d) {
+    DFB_KF_CASE(1) DFB_KF_CASE(2) DFB_KF_CASE(3) DFB_KF_CASE(4)
+    DFB_KF_CASE(5) DFB_KF_CASE(6) DFB_KF_CASE(7) DFB_KF_CASE(8)
+    default: return false;
+  }
+#undef DFB_KF_CASE
+}
+
 int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
                  int cand_uses_train_coords, const double* xsT, const double* nrmT, int64_t npad_tr,
                  const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows, double* Ks,
                  int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const, double* mu,
                  double* kss_out) {
   if (m_rows <= 0) return 0;
+  // fast path: plain SE / Matern(p <= 2) on <= 8 coordinates
+  if (h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
+      desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2)) {
+    const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
+    const int d = desc.factors[0].n_dims;
+    bool ok = false;
+#define DFB_KF_ARGS h, d, fblocks, d_desc, cand_uses_train_coords, xsT, nrmT, npad_tr, alpha, Xc, m, dc, \
+                    m_rows, Ks, ldk, n_valid, n_write, mean_const, mu, kss_out
+    if (desc.factors[0].kind == DFB_BASE_SE) ok = launch_kstar_fast_d<DFB_BASE_SE, 0>(DFB_KF_ARGS);
+    else if (desc.factors[0].p == 0) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 0>(DFB_KF_ARGS);
+    else if (desc.factors[0].p == 1) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 1>(DFB_KF_ARGS);
+    else ok = launch_kstar_fast_d<DFB_BASE_MATERN, 2>(DFB_KF_ARGS);
+#undef DFB_KF_ARGS
+    if (ok) {
+      h->launches++;
+      DFB_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
   const size_t smem = ((sizeof(dfb_kernel_desc) + 15) / 16) * 16 +
                       sizeof(double) * KSTAR_CANDS * (size_t)(desc.n_slots + desc.n_factors);
   const unsigned blocks = (unsigned)((m_rows + KSTAR_CANDS - 1) / KSTAR_CANDS);

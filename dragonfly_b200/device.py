@@ -197,6 +197,9 @@ class DevicePosterior(object):
   def launch_count(self):
     return int(self.lib.dfb_launch_count(self.h))
 
+  def set_option(self, name, value):
+    _lib.check(self.lib.dfb_set_option(self.h, name.encode('utf-8'), int(value)), 'dfb_set_option')
+
   def profile_enable(self, on=True):
     _lib.check(self.lib.dfb_profile_enable(self.h, 1 if on else 0), 'dfb_profile_enable')
 

@@ -201,6 +201,11 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
 /* Counters for bench.py: number of kernels this handle has launched. */
 int64_t dfb_launch_count(dfb_handle* h);
 
+/* Tuning switches.  "gemm_impl": 0 = cp.async-ring DMMA kernel, 1 = TMA + mbarrier warp-specialised
+ * DMMA kernel for the scoring contraction (also selectable with the environment variable
+ * DFB200_GEMM=v1|tma read at dfb_create). */
+int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
+
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
  * class 0 = K_* build (+mu), 1 = the DMMA contraction |L^-1 k_*|^2, 2 = acquisition + arg-max,
  * 3 = posterior build (whole dfb_build_posterior).  dfb_profile_read synchronises, returns the

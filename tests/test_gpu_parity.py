@@ -480,4 +480,27 @@ def test_hp_grid_through_the_fitter_layout(B):
   want = np.exp(g['lmls'] - g['lmls'].max()); want /= want.sum()
   close(probs, want, rtol=1e-7, atol=1e-12)
   lmls2, _ = hp_grid.sharded_lml_grid(g['X'], g['Y'], g['hps'][:3], layout)   # no process group: local
-  close(lmls2[0], g['lmls'][:3], rtol=1e-10)
+  close(lmls2, g['lmls'][:3], rtol=1e-10)
+
+
+def test_tma_kernel_matches_cp_async_kernel(B):
+  """ The two implementations of the dominant contraction (cp.async ring vs TMA + mbarrier ring)
+      contract the same k-ranges in a different lane order: sigma^2 agrees to rounding, arg-max
+      identical -- on a ragged multi-chunk shape with several row blocks. """
+  from dragonfly_b200 import synth_data
+  w = synth_data.make_workload('c2_hartmann6_matern_ucb', n_train=700, n_cand=3000)
+  k = w['kernel']
+  res = []
+  for impl in (0, 1):
+    post = B.device.DevicePosterior(700, chunk=1024)
+    post.set_option('gemm_impl', impl)
+    post.set_kernel(B.kernel.build_descriptor(B.kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths'])))
+    post.set_train(w['X'], w['Y'] - w['mean_const'])
+    info, lml = post.build(w['noise_var'])
+    assert info == 0
+    mu, sd = post.eval(w['candidates'], mean_const=w['mean_const'])
+    acq = B.device.make_acq_desc('ucb', beta=2.0)
+    res.append((mu, sd, post.score_argmax(acq, w['candidates'], mean_const=w['mean_const'])[:2]))
+  assert (res[0][0] == res[1][0]).all()
+  close(res[0][1] ** 2, res[1][1] ** 2, atol=1e-13)
+  assert res[0][2][1] == res[1][2][1]
