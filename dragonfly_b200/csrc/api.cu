@@ -56,6 +56,10 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   double* te_xs = c.take<double>((size_t)npad * DFB_MAX_SLOTS);
   double* te_nrm = c.take<double>((size_t)npad * DFB_MAX_FACTORS);
   double* Ks = c.take<double>((size_t)chunk * npad);
+  int8_t* Wi8 = c.take<int8_t>((size_t)6 * npad * npad);
+  int8_t* Ki8 = c.take<int8_t>((size_t)6 * chunk * npad);
+  double* rowscale = c.take<double>((size_t)npad);
+  double* rowinv = c.take<double>((size_t)npad);
   double* partial = c.take<double>((size_t)nb * chunk);
   double* mu = c.take<double>((size_t)chunk);
   double* sd = c.take<double>((size_t)chunk);
@@ -74,7 +78,7 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   if (h != nullptr && base != nullptr) {
     h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
     h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
-    h->Ks = Ks; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
+    h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
     h->blk_score = blk_score; h->blk_index = blk_index; h->best_score = best_score;
     h->best_index = best_index; h->red = red; h->info = info;
     h->d_desc_tr = d0; h->d_desc_te = d1; h->d_desc_tmp = d2;
@@ -228,6 +232,17 @@ static int prof_end(dfb_handle* h, int cls, double units) {
   return 0;
 }
 
+// Digit planes of W = L^-1 for the tcgen05 path + the tensor maps of both operands.
+static int prepare_i8(dfb_handle* h) {
+  const int64_t npad = h->npad;
+  DFB_TRY(launch_row_exponent(h, h->W, npad, npad, npad, h->rowscale, h->rowinv));
+  DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, npad * npad, npad));
+  DFB_TRY(make_tensor_map_3d_u8(&h->tmWi8, h->Wi8, npad, npad, 6, npad, npad * npad, 64, 128));
+  DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, npad, h->chunk, 6, npad, h->chunk * npad, 64, 64));
+  h->i8_ready = true;
+  return 0;
+}
+
 struct ChunkOut {
   double* mu; double* sd; double* score;   // user pointers (space given), may be NULL
 };
@@ -273,7 +288,16 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       g.n_rb = nb; g.n_cb = (int)(m_rows / TILE); g.K = (int)npad;
       g.partial = h->partial; g.ld_partial = Mc;
       DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
-      if (h->gemm_impl == 1 && h->tma_ready) {
+      if (h->score_impl == 1 && h->i8_ready) {
+        // K_* = 2^F * digits: |K_*| <= k(x,x) for every supported (stationary, non-negative) kernel
+        int e = 0;
+        frexp(desc.kss * (1.0 + 1e-9), &e);
+        const double colscale = ldexp(1.0, e + 1);
+        DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
+                                h->chunk * npad, npad));
+        DFB_TRY(launch_score_i8_args(h, h->tmWi8, h->tmKi8, nb, (int)(m_rows / 64), (int)npad, h->partial, Mc,
+                                     h->rowscale, colscale));
+      } else if (h->gemm_impl == 1 && h->tma_ready) {
         ScoreTmaArgs ta;
         ta.n_rb = g.n_rb; ta.n_cb = g.n_cb; ta.K = g.K; ta.partial = g.partial; ta.ld_partial = g.ld_partial;
         DFB_TRY(launch_score_tma(h, h->tmW, h->tmK, ta));
@@ -332,6 +356,8 @@ int dfb_create(dfb_handle** out, int device) {
   h->device = device;
   const char* impl = getenv("DFB200_GEMM");       // "v1" = cp.async ring, "tma" = TMA + mbarrier ring
   h->gemm_impl = (impl != nullptr && strcmp(impl, "v1") == 0) ? 0 : 1;   // default: TMA ring
+  const char* simpl = getenv("DFB200_SCORE");     // "i8" = int8-slice tcgen05 contraction
+  h->score_impl = (simpl != nullptr && strcmp(simpl, "i8") == 0) ? 1 : 0;
   *out = h;
   return 0;
 }
@@ -457,6 +483,8 @@ int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t 
   h->noise_plus_jitter = noise_var + jitter;
   h->have_post = true;
   h->have_w = with_bottom;
+  h->i8_ready = false;
+  if (with_bottom && h->score_impl == 1) DFB_TRY(prepare_i8(h));
   h->tma_ready = false;
   if (with_bottom && h->gemm_impl == 1) {
     DFB_TRY(make_tensor_map_2d_f64(&h->tmW, h->W, npad, npad, npad));
@@ -674,6 +702,16 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
     return 0;
   }
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
+  if (strcmp(name, "score_impl") == 0) {
+    if (value != 0 && value != 1) { set_error("score_impl must be 0 (fp64 DMMA) or 1 (int8-slice tcgen05)"); return -1; }
+    h->score_impl = (int)value;
+    h->i8_ready = false;
+    if (value == 1 && h->have_post && h->have_w) {
+      DFB_CUDA_OK(cudaSetDevice(h->device));
+      DFB_TRY(prepare_i8(h));
+    }
+    return 0;
+  }
   set_error("unknown option '%s'", name);
   return -1;
 }

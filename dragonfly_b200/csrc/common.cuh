@@ -115,6 +115,15 @@ struct dfb_handle {
   CUtensorMap tmW;            // W  (npad x npad)
   CUtensorMap tmK;            // Ks (chunk x npad)
 
+  // integer-slice tcgen05 path (gemm_i8.cuh)
+  int score_impl = 0;         // 0 = fp64 DMMA, 1 = int8-slice UTCIMMA (error-bounded)
+  bool i8_ready = false;
+  int8_t* Wi8 = nullptr;      // [6][npad][npad]
+  int8_t* Ki8 = nullptr;      // [6][chunk][npad]
+  double* rowscale = nullptr; // npad  2^E_i
+  double* rowinv = nullptr;   // npad  2^-E_i
+  CUtensorMap tmWi8, tmKi8;
+
   // model state
   dfb_kernel_desc desc_tr;
   dfb_kernel_desc desc_te;

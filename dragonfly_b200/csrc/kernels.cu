@@ -3,6 +3,7 @@
 // sm_100a only.  Reference paths are relative to the reference tree (dragonfly-opt 0.1.7).
 #include "kernels.cuh"
 #include "gemm_tma.cuh"
+#include "gemm_i8.cuh"
 
 namespace dfb {
 
@@ -681,6 +682,50 @@ __global__ void diag_max_kernel(const double* __restrict__ M, int64_t ld, int64_
   }
 }
 
+// ---- integer digit planes for the tcgen05 path (gemm_i8.cuh) ------------------------------------------
+// rowscale[i] = 2^E_i with |M[i,:]| * 2^-E_i < 1/2  (rowinv = 2^-E_i); one warp per row.
+__global__ void row_exponent_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int64_t cols,
+                                    double* rowscale, double* rowinv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  double mx = 0.0;
+  for (int64_t c = lane; c < cols; c += 32) mx = fmax(mx, fabs(M[row * ld + c]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    int e = 0;
+    if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);
+    rowscale[row] = ldexp(1.0, e + 1);
+    rowinv[row] = ldexp(1.0, -(e + 1));
+  }
+}
+
+// Exact expansion of x = M * 2^-E (|x| < 1/2) into I8_S signed 7-bit digits: y = 128 x, a = rint(y),
+// x <- y - a (all exact in fp64); four consecutive columns per thread, one 32-bit store per plane.
+__global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int64_t cols4,
+                                const double* __restrict__ rowinv, double inv_const,
+                                uint32_t* __restrict__ out, int64_t plane_words, int64_t out_ld_words) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols4) return;
+  const int64_t row = idx / cols4, c4 = idx - row * cols4;
+  const double inv = (rowinv != nullptr) ? rowinv[row] : inv_const;
+  const double4 in = *reinterpret_cast<const double4*>(M + row * ld + 4 * c4);
+  double x[4] = {in.x * inv, in.y * inv, in.z * inv, in.w * inv};
+#pragma unroll
+  for (int s = 0; s < I8_S; s++) {
+    uint32_t pack = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double y = x[q] * 128.0;
+      double a = rint(y);
+      x[q] = y - a;
+      a = fmin(fmax(a, -127.0), 127.0);
+      pack |= ((uint32_t)((int)a) & 0xffu) << (8 * q);
+    }
+    out[(int64_t)s * plane_words + row * out_ld_words + c4] = pack;
+  }
+}
+
 // ================================================================================================
 // Host launchers
 // ================================================================================================
@@ -740,6 +785,76 @@ int make_tensor_map_2d_f64(CUtensorMap* out, const double* base, int64_t rows, i
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return -2;
   }
+  return 0;
+}
+
+int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t planes,
+                          int64_t row_ld_bytes, int64_t plane_stride_bytes, int box_cols, int box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DFB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return -2;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  const cuuint64_t gstride[2] = {(cuuint64_t)row_ld_bytes, (cuuint64_t)plane_stride_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)planes};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d u8) failed with CUresult %d", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+static bool g_i8_attr = false;
+int launch_score_i8(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreI8Args& g) {
+  const int n_blocks = g.n_rb * g.n_cb;
+  if (n_blocks <= 0) return 0;
+  if (!g_i8_attr) {
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)I8_SMEM_BYTES));
+    g_i8_attr = true;
+  }
+  score_i8_kernel<<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, g);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, int n_rb, int n_cb,
+                         int K, double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
+  ScoreI8Args g;
+  g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
+  g.rowscale = rowscale; g.colscale = colscale;
+  return launch_score_i8(h, tmA, tmB, g);
+}
+
+int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
+                        double* rowscale, double* rowinv) {
+  row_exponent_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, h->stream>>>(M, ld, rows, cols, rowscale, rowinv);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
+                    const double* rowinv, double inv_const, void* out, int64_t plane_bytes, int64_t out_ld_bytes) {
+  const int64_t total = rows * (cols / 4);
+  if (total <= 0) return 0;
+  slice_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
+      M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4,
+      out_ld_bytes / 4);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
