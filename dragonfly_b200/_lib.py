@@ -74,6 +74,7 @@ PROTOTYPES = {
   'dfb_ts_draws': (C.c_int, [_P, _P, _I64, _I32, _D, _P, _I32, _D, _P, _P, C.POINTER(_D)]),
   'dfb_launch_count': (_I64, [_P]),
   'dfb_set_option': (C.c_int, [_P, C.c_char_p, _I64]),
+  'dfb_query': (C.c_int, [_P, C.c_char_p, C.POINTER(_D)]),
   'dfb_profile_enable': (C.c_int, [_P, C.c_int]),
   'dfb_profile_read': (C.c_int, [_P, C.c_int, C.POINTER(_D), C.POINTER(_I64), C.POINTER(_D)]),
 }

@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+constexpr int SHORTLIST_CAP = 4096;
+
 static int64_t default_chunk(int64_t npad) {
   int64_t c = ((int64_t)32 << 20) / npad;   // ~256 MB of K_* rows per chunk
   c = c / TILE * TILE;
@@ -60,6 +62,9 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   int8_t* Ki8 = c.take<int8_t>((size_t)6 * chunk * npad);
   double* rowscale = c.take<double>((size_t)npad);
   double* rowinv = c.take<double>((size_t)npad);
+  int64_t* list_idx = c.take<int64_t>((size_t)SHORTLIST_CAP);
+  double* list_X = c.take<double>((size_t)SHORTLIST_CAP * DFB_MAX_SLOTS);
+  int* list_count = c.take<int>(4);
   double* partial = c.take<double>((size_t)nb * chunk);
   double* mu = c.take<double>((size_t)chunk);
   double* sd = c.take<double>((size_t)chunk);
@@ -78,7 +83,7 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   if (h != nullptr && base != nullptr) {
     h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
     h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
-    h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
+    h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->list_idx = list_idx; h->list_X = list_X; h->list_count = list_count; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
     h->blk_score = blk_score; h->blk_index = blk_index; h->best_score = best_score;
     h->best_index = best_index; h->red = red; h->info = info;
     h->d_desc_tr = d0; h->d_desc_te = d1; h->d_desc_tmp = d2;
@@ -236,9 +241,13 @@ static int prof_end(dfb_handle* h, int cls, double units) {
 static int prepare_i8(dfb_handle* h) {
   const int64_t npad = h->npad;
   DFB_TRY(launch_row_exponent(h, h->W, npad, npad, npad, h->rowscale, h->rowinv));
-  DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, npad * npad, npad));
-  DFB_TRY(make_tensor_map_3d_u8(&h->tmWi8, h->Wi8, npad, npad, 6, npad, npad * npad, 64, 128));
-  DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, npad, h->chunk, 6, npad, h->chunk * npad, 64, 64));
+  DFB_TRY(launch_vec_max(h, h->rowscale, h->n, h->red + 4));
+  DFB_CUDA_OK(cudaMemcpyAsync(&h->i8_rowscale_max, h->red + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  // pair-interleaved digit planes: 3 planes of rows x (2 * npad) bytes
+  DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, 2 * npad * npad, 2 * npad));
+  DFB_TRY(make_tensor_map_3d_u8(&h->tmWi8, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 128, 128));
+  DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 128, 64));
   h->i8_ready = true;
   return 0;
 }
@@ -248,8 +257,34 @@ struct ChunkOut {
 };
 
 // Scores m candidates chunk by chunk: K_* rows + mu -> |L^-1 k_*|^2 -> sd / acquisition / arg-max.
+// A-priori bound on the int8-slice path's absolute sigma^2 error for the active kernel: digits carry
+// 42 bits below the row / column scales 2^E_i, 2^F; the constant is calibrated on the measured
+// worst case (tools/check_i8.py) with a 4x safety factor.
+static double i8_colscale(const dfb_kernel_desc& desc) {
+  int e = 0;
+  frexp(desc.kss * (1.0 + 1e-9), &e);
+  return ldexp(1.0, e + 1);
+}
+static double i8_sigma2_bound(const dfb_handle* h, const dfb_kernel_desc& desc) {
+  return 16.0 * h->i8_rowscale_max * i8_colscale(desc) * ldexp(1.0, -43) * sqrt(desc.kss);
+}
+static bool i8_usable(const dfb_handle* h, const dfb_kernel_desc& desc) {
+  if (!h->i8_ready || !(desc.kss > 0.0)) return false;
+  const double b = i8_sigma2_bound(h, desc);
+  return b <= 1e-9 * (desc.kss > 1.0 ? desc.kss : 1.0);
+}
+
+struct ChunkMode {
+  bool want_std, do_argmax;
+  bool use_i8;                 // int8-slice tcgen05 contraction instead of fp64 DMMA
+  bool collect;                // gather the shortlist for the exact re-score
+  double margin, sd_min;       // shortlist thresholds
+  const int64_t* idx_map;      // global index of each row (re-score pass), NULL = c0 + i
+};
+
 static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, int64_t m, int32_t dc,
-                      int32_t space, double mean_const, ChunkOut out, bool want_std, bool do_argmax) {
+                      int32_t space, double mean_const, ChunkOut out, const ChunkMode& md) {
+  const bool want_std = md.want_std, do_argmax = md.do_argmax;
   const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
   const dfb_kernel_desc* d_desc = h->have_test_kernel ? h->d_desc_te : h->d_desc_tr;
   const ScaledSet& ss = h->have_test_kernel ? h->te : h->tr;
@@ -276,7 +311,8 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     }
     double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : h->mu;
     double* sd_dev = (space == DFB_DEVICE && out.sd) ? out.sd + c0 : h->sd;
-    double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0 : (out.score ? h->score : nullptr);
+    double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0
+                                                         : ((out.score || md.collect) ? h->score : nullptr);
     DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
     DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
                          h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
@@ -288,18 +324,17 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       g.n_rb = nb; g.n_cb = (int)(m_rows / TILE); g.K = (int)npad;
       g.partial = h->partial; g.ld_partial = Mc;
       DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
-      if (h->score_impl == 1 && h->i8_ready) {
+      if (md.use_i8) {
         // K_* = 2^F * digits: |K_*| <= k(x,x) for every supported (stationary, non-negative) kernel
-        int e = 0;
-        frexp(desc.kss * (1.0 + 1e-9), &e);
-        const double colscale = ldexp(1.0, e + 1);
+        const double colscale = i8_colscale(desc);
         DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
-                                h->chunk * npad, npad));
+                                2 * h->chunk * npad, 2 * npad));
         DFB_TRY(launch_score_i8_args(h, h->tmWi8, h->tmKi8, nb, (int)(m_rows / 64), (int)npad, h->partial, Mc,
                                      h->rowscale, colscale));
       } else if (h->gemm_impl == 1 && h->tma_ready) {
         ScoreTmaArgs ta;
         ta.n_rb = g.n_rb; ta.n_cb = g.n_cb; ta.K = g.K; ta.partial = g.partial; ta.ld_partial = g.ld_partial;
+        ta.cb_group = h->tma_cb_group;
         DFB_TRY(launch_score_tma(h, h->tmW, h->tmK, ta));
       } else {
         DFB_TRY(launch_gemm(h, g, EPI_SUMSQ, g.n_rb * g.n_cb));
@@ -309,7 +344,10 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     if (want_std || do_argmax || sc_dev != nullptr) {
       DFB_TRY(prof_begin(h, DFB_PROF_ACQ));
       DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, Mc, nb, h->kssv, mc, c0, want_std ? 1 : 0,
-                         want_std ? sd_dev : nullptr, sc_dev, do_argmax));
+                         want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map));
+      if (md.collect)
+        DFB_TRY(launch_collect_shortlist(h, sc_dev, sd_dev, mc, c0, md.margin, md.sd_min, xc_dev, dc,
+                                         h->list_idx, h->list_X, h->list_count, SHORTLIST_CAP));
       DFB_TRY(prof_end(h, DFB_PROF_ACQ, (double)mc));
     }
     if (space == DFB_HOST) {
@@ -357,7 +395,9 @@ int dfb_create(dfb_handle** out, int device) {
   const char* impl = getenv("DFB200_GEMM");       // "v1" = cp.async ring, "tma" = TMA + mbarrier ring
   h->gemm_impl = (impl != nullptr && strcmp(impl, "v1") == 0) ? 0 : 1;   // default: TMA ring
   const char* simpl = getenv("DFB200_SCORE");     // "i8" = int8-slice tcgen05 contraction
-  h->score_impl = (simpl != nullptr && strcmp(simpl, "i8") == 0) ? 1 : 0;
+  h->score_impl = 2;                              // auto
+  if (simpl != nullptr && strcmp(simpl, "i8") == 0) h->score_impl = 1;
+  if (simpl != nullptr && strcmp(simpl, "fp64") == 0) h->score_impl = 0;
   *out = h;
   return 0;
 }
@@ -484,7 +524,7 @@ int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t 
   h->have_post = true;
   h->have_w = with_bottom;
   h->i8_ready = false;
-  if (with_bottom && h->score_impl == 1) DFB_TRY(prepare_i8(h));
+  if (with_bottom && (h->score_impl == 1 || (h->score_impl == 2 && h->n >= 1024))) DFB_TRY(prepare_i8(h));
   h->tma_ready = false;
   if (with_bottom && h->gemm_impl == 1) {
     DFB_TRY(make_tensor_map_2d_f64(&h->tmW, h->W, npad, npad, npad));
@@ -535,7 +575,11 @@ int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t spa
   memset(&acq, 0, sizeof(acq));
   acq.kind = DFB_ACQ_MEAN;
   ChunkOut out = {mu, sd, nullptr};
-  DFB_TRY(run_chunks(h, acq, Xc, m, dc, space, mean_const, out, sd != nullptr, false));
+  const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
+  ChunkMode md = {sd != nullptr, false, false, false, 0.0, 0.0, nullptr};
+  md.use_i8 = (sd != nullptr) && (h->score_impl == 1) && i8_usable(h, desc);
+  h->last_used_i8 = md.use_i8 ? 1 : 0;
+  DFB_TRY(run_chunks(h, acq, Xc, m, dc, space, mean_const, out, md));
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -550,9 +594,46 @@ int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, i
   if (acq->kind < DFB_ACQ_MEAN || acq->kind > DFB_ACQ_TTEI) { set_error("unknown acquisition kind %d", acq->kind); return -1; }
   DFB_CUDA_OK(cudaSetDevice(h->device));
   ChunkOut out = {nullptr, nullptr, scores};
-  DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, want_std, true));
+  const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
+  const bool fast = want_std && h->score_impl != 0 && i8_usable(h, desc);
+  ChunkMode md = {want_std, true, fast, false, 0.0, 0.0, nullptr};
+  h->last_used_i8 = fast ? 1 : 0;
+  h->last_shortlist = 0;
   double bs = 0.0;
   int64_t bi = -1;
+  bool need_exact_pass = !fast;
+  if (fast) {
+    // Pass 1: int8-slice scoring of everything, collecting the shortlist of candidates that could be
+    // the exact arg-max.  Natural score scale: UCB |mu| + beta sigma ~ (1 + beta) sqrt(kss); EI/TTEI
+    // <= sigma ~ sqrt(kss); PI <= 1.  The fast path's score error is <= sens * B2 / (2 sigma) with
+    // sigma >= sd_min, far below margin = 1e-6 * scale for every acquisition (DESIGN.md, int8 path).
+    const double sk = sqrt(desc.kss);
+    double scale = sk;
+    if (acq->kind == DFB_ACQ_UCB) scale = (1.0 + fabs(acq->beta)) * sk + fabs(mean_const);
+    else if (acq->kind == DFB_ACQ_PI) scale = 1.0;
+    md.collect = true;
+    md.margin = 1e-6 * scale;
+    md.sd_min = sqrt(1e-3 * desc.kss);
+    DFB_CUDA_OK(cudaMemsetAsync(h->list_count, 0, sizeof(int) * 4, h->stream));
+    DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, md));
+    int count = 0;
+    DFB_CUDA_OK(cudaMemcpyAsync(&count, h->list_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (count > SHORTLIST_CAP || count > h->chunk) {
+      h->last_shortlist = -1;          // too many near-ties / suspects: exact pass over everything
+      need_exact_pass = true;
+    } else {
+      // Pass 2: exact fp64 (DMMA) re-score of the shortlist; indices map back to the caller's rows.
+      h->last_shortlist = count;
+      ChunkMode ex = {want_std, true, false, false, 0.0, 0.0, h->list_idx};
+      ChunkOut none = {nullptr, nullptr, nullptr};
+      DFB_TRY(run_chunks(h, *acq, h->list_X, count, dc, DFB_DEVICE, mean_const, none, ex));
+    }
+  }
+  if (need_exact_pass) {
+    ChunkMode ex = {want_std, true, false, false, 0.0, 0.0, nullptr};
+    DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, ex));
+  }
   DFB_CUDA_OK(cudaMemcpyAsync(&bs, h->best_score, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   DFB_CUDA_OK(cudaMemcpyAsync(&bi, h->best_index, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -686,6 +767,18 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
 
 int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }
 
+int dfb_query(dfb_handle* h, const char* name, double* out) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (name == nullptr || out == nullptr) { set_error("bad query arguments"); return -1; }
+  const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
+  if (strcmp(name, "i8_sigma2_bound") == 0) { *out = h->i8_ready ? i8_sigma2_bound(h, desc) : -1.0; return 0; }
+  if (strcmp(name, "last_used_i8") == 0) { *out = (double)h->last_used_i8; return 0; }
+  if (strcmp(name, "last_shortlist") == 0) { *out = (double)h->last_shortlist; return 0; }
+  if (strcmp(name, "i8_ready") == 0) { *out = h->i8_ready ? 1.0 : 0.0; return 0; }
+  set_error("unknown query '%s'", name);
+  return -1;
+}
+
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   DFB_TRY(need(h, false, false, false, false, false));
   if (name == nullptr) { set_error("option name is NULL"); return -1; }
@@ -702,11 +795,13 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
     return 0;
   }
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
+  if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }
+  if (strcmp(name, "i8_cb_group") == 0 && value >= 1) { h->i8_cb_group = (int)value; return 0; }
   if (strcmp(name, "score_impl") == 0) {
-    if (value != 0 && value != 1) { set_error("score_impl must be 0 (fp64 DMMA) or 1 (int8-slice tcgen05)"); return -1; }
+    if (value < 0 || value > 2) { set_error("score_impl must be 0 (fp64 DMMA), 1 (int8-slice tcgen05) or 2 (auto)"); return -1; }
     h->score_impl = (int)value;
     h->i8_ready = false;
-    if (value == 1 && h->have_post && h->have_w) {
+    if ((value == 1 || (value == 2 && h->n >= 1024)) && h->have_post && h->have_w) {
       DFB_CUDA_OK(cudaSetDevice(h->device));
       DFB_TRY(prepare_i8(h));
     }

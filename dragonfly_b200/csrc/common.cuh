@@ -110,13 +110,22 @@ struct dfb_handle {
 
   // TMA path of the scoring contraction (gemm_tma.cuh)
   int gemm_impl = 1;          // 0 = v1 cp.async ring, 1 = v2 TMA + mbarrier ring (default)
+  int tma_cb_group = 1 << 20;       // candidate tiles per scheduling group (sweep: no gain, see profiles/)
+  int i8_cb_group = 1 << 20;        // idem, int8 kernel
   int kstar_fast = 1;         // specialised K_* kernel for plain SE / Matern on <= 8 dims
   bool tma_ready = false;
   CUtensorMap tmW;            // W  (npad x npad)
   CUtensorMap tmK;            // Ks (chunk x npad)
 
   // integer-slice tcgen05 path (gemm_i8.cuh)
-  int score_impl = 0;         // 0 = fp64 DMMA, 1 = int8-slice UTCIMMA (error-bounded)
+  int score_impl = 2;         // 0 = fp64 DMMA, 1 = int8-slice UTCIMMA everywhere, 2 = auto: int8 pass +
+                              // exact fp64 re-score of the shortlist in dfb_score_argmax, fp64 in dfb_eval
+  double i8_rowscale_max = 0.0;   // max_i 2^E_i of the current posterior
+  int64_t* list_idx = nullptr;    // shortlist (cap entries)
+  double* list_X = nullptr;       // cap x DFB_MAX_SLOTS
+  int* list_count = nullptr;
+  int64_t last_shortlist = 0;     // diagnostics: size of the last shortlist, -1 = overflow -> exact pass
+  int last_used_i8 = 0;
   bool i8_ready = false;
   int8_t* Wi8 = nullptr;      // [6][npad][npad]
   int8_t* Ki8 = nullptr;      // [6][chunk][npad]

@@ -14,8 +14,12 @@
 // two orders inside the 1e-8 contract (tests/test_gpu_parity.py::test_i8_*).
 //
 // CTA = one 128 (rows of W) x 64 (candidates) tile, 6 warps:
-//   warp 0  TMA producer: two 3-D boxes per stage (all 6 digit planes of A: 128 x 64 B each, and of
-//           B: 64 x 64 B each), SWIZZLE_64B, 3-stage full/empty mbarrier ring (72 KB per stage)
+//   warp 0  TMA producer: two 3-D boxes per stage (all 6 digit planes of A and of B for a K-block of
+//           64), SWIZZLE_128B, 3-stage full/empty mbarrier ring (72 KB per stage).  Digit planes are
+//           stored pair-interleaved -- every 128-byte row holds 64 k-values of digit 2p followed by the
+//           same 64 k-values of digit 2p+1 -- so that each TMA row request moves 128 B: the first
+//           version with 64-byte rows was bound by the TMA request rate (23 B/clk/SM, tensor pipe 42 %
+//           busy; profiles/r01_i8_ncu_summary.txt)
 //   warp 1  TMEM allocator + MMA issuer (one elected thread): 42 UTCIMMA (M128 N64 K32) per stage,
 //           tcgen05.commit releases the stage / signals the accumulators
 //   warps 2-5 epilogue: tcgen05.ld 32x32b, fp64 recombination, row scale, square, warp-shuffle
@@ -31,10 +35,10 @@ namespace dfb {
 constexpr int I8_S = 6;                       // digits per operand
 constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 64;
 constexpr int I8_STAGES = 3;
-constexpr int I8_A_SLICE = I8_BM * I8_BK;     // 8192 B
-constexpr int I8_B_SLICE = I8_BN * I8_BK;     // 4096 B
-constexpr int I8_A_BYTES = I8_S * I8_A_SLICE;
-constexpr int I8_B_BYTES = I8_S * I8_B_SLICE;
+constexpr int I8_A_PAIR = I8_BM * 2 * I8_BK;  // 16384 B: 128 rows x (64 B digit 2p | 64 B digit 2p+1)
+constexpr int I8_B_PAIR = I8_BN * 2 * I8_BK;  // 8192 B
+constexpr int I8_A_BYTES = (I8_S / 2) * I8_A_PAIR;
+constexpr int I8_B_BYTES = (I8_S / 2) * I8_B_PAIR;
 constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 73728
 constexpr int I8_THREADS = 192;
 constexpr int I8_TMEM_COLS = 512;
@@ -46,6 +50,7 @@ constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I
 
 struct ScoreI8Args {
   int n_rb, n_cb, K;
+  int cb_group;             // candidate tiles per scheduling group
   double* partial;
   int64_t ld_partial;
   const double* rowscale;   // 2^E_i per row of W
@@ -60,10 +65,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4,
-// LBO = 1, SBO = 512 B (8 rows x 64 B), version 1 (sm_100), layout type 4.
-__device__ __forceinline__ uint64_t umma_desc_sw64(unsigned smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4,
+// LBO = 1, SBO = 1024 B (8 rows x 128 B), version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(unsigned smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, uint64_t da, uint64_t db, unsigned accumulate) {
   asm volatile(
@@ -98,9 +103,15 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* accum_bar = empty_bar + I8_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
+  // Tile order: groups of `cb_group` candidate tiles; inside a group the heaviest row blocks first.
+  // The CTAs resident at any time then share a few K_* digit tiles and sweep W, which stays L2
+  // resident across groups (W digits 79 MB + one group of K_* digits 16 MB < 126 MB of L2).
   const int bid = blockIdx.x;
-  const int rb = g.n_rb - 1 - bid / g.n_cb;          // heaviest row blocks first
-  const int cb = bid % g.n_cb;
+  const int per_group = g.cb_group * g.n_rb;
+  const int grp = bid / per_group, rem = bid - grp * per_group;
+  const int rb = g.n_rb - 1 - rem / g.cb_group;
+  const int cb = grp * g.cb_group + rem % g.cb_group;
+  if (cb >= g.n_cb) return;                         // ragged last group (uniform per CTA)
   const int k_hi = min(g.K, (rb + 1) * TILE);
   const int nk = k_hi / I8_BK;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,8 +142,8 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&empty_bar[s], (n & 1u) ^ 1u);
         mbar_expect_tx(&full_bar[s], (unsigned)I8_STAGE_BYTES);
         unsigned char* dst = tiles + (size_t)s * I8_STAGE_BYTES;
-        tma_load_3d(dst, &tmA, kt * I8_BK, rb * I8_BM, 0, &full_bar[s]);
-        tma_load_3d(dst + I8_A_BYTES, &tmB, kt * I8_BK, cb * I8_BN, 0, &full_bar[s]);
+        tma_load_3d(dst, &tmA, kt * 2 * I8_BK, rb * I8_BM, 0, &full_bar[s]);
+        tma_load_3d(dst + I8_A_BYTES, &tmB, kt * 2 * I8_BK, cb * I8_BN, 0, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -144,18 +155,26 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&full_bar[s], n & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const unsigned a0 = smem_u32(tiles + (size_t)s * I8_STAGE_BYTES);
-        const unsigned b0 = a0 + I8_A_BYTES;
+        // descriptor = {hi: SBO 1024 B | version 1 | SWIZZLE_128B, lo: (addr >> 4) | LBO 1}; within a
+        // stage only the 14-bit address field changes, by compile-time offsets.
+        const unsigned a_lo = ((a0 & 0x3FFFFu) >> 4) | 0x10000u;
+        const unsigned b_lo = (((a0 + I8_A_BYTES) & 0x3FFFFu) >> 4) | 0x10000u;
+        constexpr uint64_t DESC_HI = ((uint64_t)(64u | (1u << 14) | (2u << 29))) << 32;
+        // One digit-sum group (= one TMEM accumulator) at a time, so consecutive MMAs accumulate into
+        // the same tensor-memory tile like the k-loop of an ordinary GEMM.
 #pragma unroll
-        for (int kh = 0; kh < I8_BK / 32; kh++) {
+        for (int d = 2; d <= I8_S + 1; d++) {
+          const unsigned acc = (unsigned)((d - 2) * I8_BN);   // literal TMEM address (base 0, see epilogue)
 #pragma unroll
-          for (int sa = 1; sa <= I8_S; sa++) {
-            const uint64_t da = umma_desc_sw64(a0 + (sa - 1) * I8_A_SLICE + kh * 32);
+          for (int sa = 1; sa <= d - 1; sa++) {
+            const int tb = d - sa;
 #pragma unroll
-            for (int tb = 1; tb <= I8_S + 1 - sa; tb++) {
-              const uint64_t db = umma_desc_sw64(b0 + (tb - 1) * I8_B_SLICE + kh * 32);
-              const unsigned acc = tmem_base + (unsigned)((sa + tb - 2) * I8_BN);
-              // the first product of every digit-sum group (sa == 1) overwrites the accumulator
-              umma_i8(acc, da, db, (kt == 0 && kh == 0 && sa == 1) ? 0u : 1u);
+            for (int kh = 0; kh < I8_BK / 32; kh++) {
+              const unsigned aoff = ((sa - 1) >> 1) * I8_A_PAIR + ((sa - 1) & 1) * I8_BK + kh * 32;
+              const unsigned boff = ((tb - 1) >> 1) * I8_B_PAIR + ((tb - 1) & 1) * I8_BK + kh * 32;
+              const uint64_t da = DESC_HI | (uint64_t)(a_lo + (aoff >> 4));
+              const uint64_t db = DESC_HI | (uint64_t)(b_lo + (boff >> 4));
+              umma_i8(acc, da, db, (kt == 0 && sa == 1 && kh == 0) ? 0u : 1u);
             }
           }
         }
@@ -169,7 +188,9 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int row = q * 32 + lane;
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const double rs = g.rowscale[(int64_t)rb * I8_BM + row] * g.colscale;
+    // tmem_base != 0 would mean the literal accumulator addresses above were wrong: poison the result
+    const double rs = (tmem_base == 0u) ? g.rowscale[(int64_t)rb * I8_BM + row] * g.colscale
+                                        : __longlong_as_double(0x7ff8000000000000ll);
     const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
     for (int c0 = 0; c0 < I8_BN; c0 += 8) {
       int r[I8_S][8];

@@ -78,9 +78,14 @@ score_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * TILE);
   uint64_t* empty_bar = full_bar + TMA_STAGES;
 
+  // Tile order: groups of `cb_group` candidate tiles, heaviest row blocks first inside a group, so the
+  // resident CTAs share a few K_* panels while W (105 MB) stays in the 126 MB L2 across groups.
   const int bid = blockIdx.x;
-  const int rb = g.n_rb - 1 - bid / g.n_cb;          // heaviest row blocks first
-  const int cb = bid % g.n_cb;
+  const int per_group = g.cb_group * g.n_rb;
+  const int grp = bid / per_group, rem = bid - grp * per_group;
+  const int rb = g.n_rb - 1 - rem / g.cb_group;
+  const int cb = grp * g.cb_group + rem % g.cb_group;
+  if (cb >= g.n_cb) return;                         // ragged last group (uniform per CTA)
   const int k_hi = min(g.K, (rb + 1) * TILE);
   const int nk = k_hi / GEMM_BK;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -7,6 +7,7 @@ namespace dfb {
 
 struct ScoreTmaArgs {
   int n_rb, n_cb, K;
+  int cb_group;             // candidate tiles per scheduling group
   double* partial;
   int64_t ld_partial;
 };

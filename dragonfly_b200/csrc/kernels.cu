@@ -555,9 +555,8 @@ __device__ __forceinline__ bool better(double sa, int64_t ia, double sb, int64_t
 __global__ void __launch_bounds__(256)
 acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* __restrict__ partial,
            int64_t ld_partial, int nrb, const double* __restrict__ kss, int64_t m, int64_t idx_base,
-           int want_std,
-           double* __restrict__ sd_out, double* __restrict__ score_out, double* blk_score,
-           int64_t* blk_index) {
+           int want_std, double* __restrict__ sd_out, double* __restrict__ score_out, double* blk_score,
+           int64_t* blk_index, const int64_t* __restrict__ idx_map) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double score = 0.0;
   int64_t index = -1;
@@ -592,7 +591,7 @@ acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* 
         score = mean;
     }
     if (score_out != nullptr) score_out[i] = score;
-    index = idx_base + i;
+    index = (idx_map != nullptr) ? idx_map[i] : idx_base + i;
   }
   if (blk_score == nullptr) return;
   // block arg-max
@@ -666,6 +665,43 @@ __global__ void set_diag_kernel(double* M, int64_t ld, int64_t from, int64_t to,
   if (i < to) M[i * ld + i] = add ? (M[i * ld + i] + v) : v;
 }
 
+// Shortlist for the exact re-score that follows a fast (int8-slice) scoring pass: every candidate whose
+// fast score is within `margin` of the running best (a superset of those within `margin` of the final
+// best, since the running best only grows), every NaN, and every candidate whose sigma is small enough
+// for the fast path's absolute sigma^2 error to matter.  Rows are gathered so host-staged chunks can be
+// re-scored later.
+__global__ void collect_shortlist_kernel(const double* __restrict__ score, const double* __restrict__ sd,
+                                         int64_t mc, int64_t idx_base, const double* best_score,
+                                         const int64_t* best_index, double margin, double sd_min,
+                                         const double* __restrict__ Xc, int dc, int64_t* list_idx,
+                                         double* list_X, int* list_count, int cap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mc) return;
+  const double s = score[i], b = *best_score;
+  const double sg = sd[i];
+  const bool keep = (*best_index < 0) || isnan(s) || isnan(b) || s >= b - margin || !(sg >= sd_min);
+  if (!keep) return;
+  const int pos = atomicAdd(list_count, 1);
+  if (pos >= cap) return;
+  list_idx[pos] = idx_base + i;
+  for (int q = 0; q < dc; q++) list_X[(int64_t)pos * dc + q] = Xc[i * dc + q];
+}
+
+__global__ void vec_max_kernel(const double* __restrict__ v, int64_t n, double* out) {
+  __shared__ double sh[32];
+  double m = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, v[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    m = lane < (blockDim.x >> 5) ? sh[lane] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[0] = m;
+  }
+}
+
 // max over the first n diagonal entries (stable_cholesky's np.diag(M).max(), general_utils.py:184)
 __global__ void diag_max_kernel(const double* __restrict__ M, int64_t ld, int64_t n, double* out) {
   __shared__ double sh[32];
@@ -701,16 +737,21 @@ __global__ void row_exponent_kernel(const double* __restrict__ M, int64_t ld, in
 }
 
 // Exact expansion of x = M * 2^-E (|x| < 1/2) into I8_S signed 7-bit digits: y = 128 x, a = rint(y),
-// x <- y - a (all exact in fp64); four consecutive columns per thread, one 32-bit store per plane.
+// x <- y - a (all exact in fp64); four consecutive columns per thread, one 32-bit store per digit.
+// Output layout (pair-interleaved planes, see gemm_i8.cuh): byte offset of (digit s, row, k) =
+//   (s/2) * plane_bytes + row * 2*cols + (k/64) * 128 + (s%2) * 64 + (k%64).
 __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int64_t cols4,
                                 const double* __restrict__ rowinv, double inv_const,
-                                uint32_t* __restrict__ out, int64_t plane_words, int64_t out_ld_words) {
+                                uint32_t* __restrict__ out, int64_t plane_words) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols4) return;
   const int64_t row = idx / cols4, c4 = idx - row * cols4;
   const double inv = (rowinv != nullptr) ? rowinv[row] : inv_const;
   const double4 in = *reinterpret_cast<const double4*>(M + row * ld + 4 * c4);
   double x[4] = {in.x * inv, in.y * inv, in.z * inv, in.w * inv};
+  const int64_t k = 4 * c4;
+  const int64_t row_words = 2 * cols4;                       // 2 * cols bytes
+  const int64_t base = row * row_words + (k >> 6) * 32 + ((k & 63) >> 2);
 #pragma unroll
   for (int s = 0; s < I8_S; s++) {
     uint32_t pack = 0;
@@ -722,7 +763,7 @@ __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_
       a = fmin(fmax(a, -127.0), 127.0);
       pack |= ((uint32_t)((int)a) & 0xffu) << (8 * q);
     }
-    out[(int64_t)s * plane_words + row * out_ld_words + c4] = pack;
+    out[(int64_t)(s >> 1) * plane_words + base + (s & 1) * 16] = pack;
   }
 }
 
@@ -806,7 +847,7 @@ int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int6
   const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)planes};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (3d u8) failed with CUresult %d", (int)r);
@@ -817,14 +858,17 @@ int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int6
 
 static bool g_i8_attr = false;
 int launch_score_i8(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreI8Args& g) {
-  const int n_blocks = g.n_rb * g.n_cb;
+  ScoreI8Args ga = g;
+  if (ga.cb_group > ga.n_cb) ga.cb_group = ga.n_cb;
+  const int n_groups = (ga.n_cb + ga.cb_group - 1) / ga.cb_group;
+  const int n_blocks = ga.n_rb * ga.cb_group * n_groups;
   if (n_blocks <= 0) return 0;
   if (!g_i8_attr) {
     DFB_CUDA_OK(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)I8_SMEM_BYTES));
     g_i8_attr = true;
   }
-  score_i8_kernel<<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, g);
+  score_i8_kernel<<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, ga);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -835,6 +879,7 @@ int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMa
   ScoreI8Args g;
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
+  g.cb_group = h->i8_cb_group;
   return launch_score_i8(h, tmA, tmB, g);
 }
 
@@ -848,11 +893,11 @@ int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows
 
 int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
                     const double* rowinv, double inv_const, void* out, int64_t plane_bytes, int64_t out_ld_bytes) {
+  (void)out_ld_bytes;
   const int64_t total = rows * (cols / 4);
   if (total <= 0) return 0;
   slice_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
-      M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4,
-      out_ld_bytes / 4);
+      M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -861,14 +906,17 @@ int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, in
 static bool g_tma_attr = false;
 int launch_score_tma(dfb_handle* h, const CUtensorMap& tmW, const CUtensorMap& tmK,
                      const ScoreTmaArgs& g) {
-  const int n_blocks = g.n_rb * g.n_cb;
+  ScoreTmaArgs ga = g;
+  if (ga.cb_group > ga.n_cb) ga.cb_group = ga.n_cb;
+  const int n_groups = (ga.n_cb + ga.cb_group - 1) / ga.cb_group;
+  const int n_blocks = ga.n_rb * ga.cb_group * n_groups;
   if (n_blocks <= 0) return 0;
   if (!g_tma_attr) {
     DFB_CUDA_OK(cudaFuncSetAttribute(score_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)TMA_SMEM_BYTES));
     g_tma_attr = true;
   }
-  score_tma_kernel<<<n_blocks, TMA_THREADS, TMA_SMEM_BYTES, h->stream>>>(tmW, tmK, g);
+  score_tma_kernel<<<n_blocks, TMA_THREADS, TMA_SMEM_BYTES, h->stream>>>(tmW, tmK, ga);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1012,15 +1060,14 @@ int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* d
 }
 
 int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
-               int64_t ld_partial, int nrb, const double* __restrict__ kss, int64_t m, int64_t idx_base,
-           int want_std,
-               double* sd_out, double* score_out, bool do_argmax) {
+               int64_t ld_partial, int nrb, const double* kss, int64_t m, int64_t idx_base, int want_std,
+               double* sd_out, double* score_out, bool do_argmax, const int64_t* idx_map) {
   if (m <= 0) return 0;
   const unsigned blocks = (unsigned)((m + 255) / 256);
   acq_kernel<<<blocks, 256, 0, h->stream>>>(acq, mu, partial, ld_partial, nrb, kss, m, idx_base,
                                             want_std, sd_out, score_out,
                                             do_argmax ? h->blk_score : nullptr,
-                                            do_argmax ? h->blk_index : nullptr);
+                                            do_argmax ? h->blk_index : nullptr, idx_map);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   if (do_argmax) {
@@ -1044,6 +1091,25 @@ int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, in
   if (rows * cols <= 0) return 0;
   add_row_vector_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, h->stream>>>(M, ld, rows,
                                                                                     cols, v);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_collect_shortlist(dfb_handle* h, const double* score, const double* sd, int64_t mc,
+                             int64_t idx_base, double margin, double sd_min, const double* Xc, int dc,
+                             int64_t* list_idx, double* list_X, int* list_count, int cap) {
+  if (mc <= 0) return 0;
+  collect_shortlist_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, h->stream>>>(
+      score, sd, mc, idx_base, h->best_score, h->best_index, margin, sd_min, Xc, dc, list_idx, list_X,
+      list_count, cap);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_vec_max(dfb_handle* h, const double* v, int64_t n, double* out) {
+  vec_max_kernel<<<1, 1024, 0, h->stream>>>(v, n, out);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -26,7 +26,12 @@ int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* d
                      int64_t rows, int64_t cols);
 int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
                int64_t ld_partial, int nrb, const double* kss, int64_t m, int64_t idx_base,
-               int want_std, double* sd_out, double* score_out, bool do_argmax);
+               int want_std, double* sd_out, double* score_out, bool do_argmax,
+               const int64_t* idx_map = nullptr);
+int launch_collect_shortlist(dfb_handle* h, const double* score, const double* sd, int64_t mc,
+                             int64_t idx_base, double margin, double sd_min, const double* Xc, int dc,
+                             int64_t* list_idx, double* list_X, int* list_count, int cap);
+int launch_vec_max(dfb_handle* h, const double* v, int64_t n, double* out);
 int launch_reset_best(dfb_handle* h);
 int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, int64_t cols,
                           const double* v);

@@ -28,6 +28,11 @@ def _dev_f64(arr, device):
   return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=np.float64))).to(device)
 
 
+# Options applied to every new DevicePosterior (name -> int), e.g. {'score_impl': 0} to force the fp64
+# DMMA contraction everywhere.  See dfb_set_option in include/dfb200.h.
+DEFAULT_OPTIONS = {}
+
+
 class DevicePosterior(object):
   """ One handle + workspace.  Immutable once built (GP objects replace, never mutate, it), so
       shallow / deep copies of a GP may share it (gpb_acquisitions.py:104, unittest_mf_gp.py:109). """
@@ -50,6 +55,8 @@ class DevicePosterior(object):
     self.n = 0
     self.dim = 0
     self.lml = None
+    for _name, _value in DEFAULT_OPTIONS.items():
+      self.set_option(_name, _value)
     self._keep = []      # tensors that must outlive asynchronous use
 
   def __del__(self):
@@ -199,6 +206,11 @@ class DevicePosterior(object):
 
   def set_option(self, name, value):
     _lib.check(self.lib.dfb_set_option(self.h, name.encode('utf-8'), int(value)), 'dfb_set_option')
+
+  def query(self, name):
+    out = C.c_double(0.0)
+    _lib.check(self.lib.dfb_query(self.h, name.encode('utf-8'), C.byref(out)), 'dfb_query')
+    return out.value
 
   def profile_enable(self, on=True):
     _lib.check(self.lib.dfb_profile_enable(self.h, 1 if on else 0), 'dfb_profile_enable')

@@ -201,10 +201,21 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
 /* Counters for bench.py: number of kernels this handle has launched. */
 int64_t dfb_launch_count(dfb_handle* h);
 
-/* Tuning switches.  "gemm_impl": 0 = cp.async-ring DMMA kernel, 1 = TMA + mbarrier warp-specialised
- * DMMA kernel for the scoring contraction (also selectable with the environment variable
- * DFB200_GEMM=v1|tma read at dfb_create). */
+/* Tuning switches.
+ *  "gemm_impl"  : 0 = cp.async-ring DMMA kernel, 1 = TMA + mbarrier warp-specialised DMMA kernel for the
+ *                 fp64 scoring contraction (env DFB200_GEMM=v1|tma at dfb_create; default tma).
+ *  "score_impl" : how |L^-1 k_*|^2 is contracted (env DFB200_SCORE=fp64|i8|auto; default auto):
+ *                 0 = fp64 DMMA everywhere;
+ *                 1 = int8-slice tcgen05 path (exact digit expansion of both fp64 operands, int32
+ *                     accumulation in tensor memory, error-bounded: |d sigma^2| <~ 1e-10 k(x,x)) everywhere;
+ *                 2 = auto: dfb_eval stays fp64; dfb_score_argmax scores with the int8 path, then re-scores
+ *                     in fp64 the shortlist of candidates that could be the arg-max, so the returned index
+ *                     and score are the fp64 ones.  The int8 path is skipped when its a-priori error bound
+ *                     (query "i8_sigma2_bound") exceeds 1e-9 max(1, k(x,x)) or n < 1024.
+ *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
+/* Diagnostics: "i8_sigma2_bound", "i8_ready", "last_used_i8", "last_shortlist" (-1 = overflow -> fp64 pass). */
+int dfb_query(dfb_handle* h, const char* name, double* out);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
  * class 0 = K_* build (+mu), 1 = the DMMA contraction |L^-1 k_*|^2, 2 = acquisition + arg-max,

@@ -504,3 +504,116 @@ def test_tma_kernel_matches_cp_async_kernel(B):
   assert (res[0][0] == res[1][0]).all()
   close(res[0][1] ** 2, res[1][1] ** 2, atol=1e-13)
   assert res[0][2][1] == res[1][2][1]
+
+
+# ---- the int8-slice tcgen05 contraction (score_impl 1 / auto) ------------------------------------------------
+def _post_pair(B, kern, X, Y, mean_const, noise_var, chunk=0):
+  posts = []
+  for impl in (0, 1):
+    post = B.device.DevicePosterior(len(X), chunk=chunk)
+    post.set_option('score_impl', impl)
+    post.set_kernel(B.kernel.build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
+    post.set_train(X, np.asarray(Y) - mean_const)
+    info, _ = post.build(noise_var)
+    assert info == 0
+    posts.append(post)
+  return posts
+
+
+def _i8_kernels(B):
+  add_groups = [[0, 1, 2], [3, 4, 5]]
+  return {
+    'se': B.kernel.SEKernel(6, 0.7, [0.3, 0.35, 0.4, 0.3, 0.5, 0.45]),
+    'matern05': B.kernel.MaternKernel(6, 0.5, 0.7, 0.4),
+    'matern15': B.kernel.MaternKernel(6, 1.5, 0.7, 0.4),
+    'matern25': B.kernel.MaternKernel(6, 2.5, 0.7, 0.3),
+    'additive': B.kernel.AdditiveKernel(0.35, [B.kernel.MaternKernel(3, 2.5, 1.0, 0.5),
+                                               B.kernel.SEKernel(3, 1.0, 0.4)], add_groups),
+    'mf_product': B.kernel.CoordinateProductKernel(6, 0.7, [B.kernel.SEKernel(1, 1.0, [0.7]),
+                                                             B.kernel.MaternKernel(5, 2.5, 1.0, 0.4)],
+                                                   [[0], [1, 2, 3, 4, 5]]),
+  }
+
+
+@pytest.mark.parametrize('name', ['se', 'matern05', 'matern15', 'matern25', 'additive', 'mf_product'])
+def test_i8_sigma2_within_contract(B, name):
+  """ Digit-sliced tensor-core contraction vs fp64 DMMA on the same posterior: mu identical (it never
+      leaves fp64), |d sigma^2| far inside the 1e-8 contract and inside the library's own a-priori
+      bound, for every kernel family, over several row blocks and ragged chunks. """
+  from dragonfly_b200 import synth_data
+  rs = np.random.RandomState(3)
+  X = rs.random_sample((1100, 6)); Y = synth_data.hartmann6(X)
+  C = rs.random_sample((5000, 6))
+  kern = _i8_kernels(B)[name]
+  fp, i8 = _post_pair(B, kern, X, Y, float(np.median(Y)), 0.01 * 0.7, chunk=2048)
+  assert i8.query('i8_ready') == 1.0
+  mu0, sd0 = fp.eval(C, mean_const=1.0)
+  mu1, sd1 = i8.eval(C, mean_const=1.0)
+  assert fp.query('last_used_i8') == 0.0 and i8.query('last_used_i8') == 1.0
+  assert (mu0 == mu1).all()
+  err = np.abs(sd0 ** 2 - sd1 ** 2).max()
+  assert err <= 1e-9, err
+  assert err <= i8.query('i8_sigma2_bound')
+
+
+def test_i8_against_reference_golden(B):
+  """ Forced int8 path against the reference itself (golden matern_h6, N = 300). """
+  g = load_golden('matern_h6')
+  kern = B.kernel.MaternKernel(6, 2.5, float(g['scale']), g['bws'])
+  _, i8 = _post_pair(B, kern, g['X'], g['Y'], float(g['mean_const']), float(g['noise_var']))
+  mu, sd = i8.eval(g['C'], mean_const=float(g['mean_const']))
+  assert i8.query('last_used_i8') == 1.0
+  close(mu, g['mu_2p5'], atol=MU_TOL)
+  close(sd ** 2, g['sd_2p5'] ** 2, atol=VAR_TOL)
+
+
+@pytest.mark.parametrize('acq_name', ['ucb', 'ei', 'pi', 'ttei'])
+def test_auto_mode_returns_the_fp64_argmax(B, acq_name):
+  """ Default mode: int8 pass + exact fp64 re-score of the shortlist == pure fp64 result, bit for bit. """
+  from dragonfly_b200 import synth_data
+  rs = np.random.RandomState(5)
+  X = rs.random_sample((1200, 6)); Y = synth_data.hartmann6(X)
+  C = rs.random_sample((30000, 6))
+  kern = B.kernel.MaternKernel(6, 2.5, float(Y.var()), 0.3)
+  m0 = float(np.median(Y))
+  res = {}
+  for impl in (0, 2):
+    post = B.device.DevicePosterior(len(X), chunk=4096)
+    post.set_option('score_impl', impl)
+    post.set_kernel(B.kernel.build_descriptor(kern)); post.set_train(X, Y - m0)
+    assert post.build(0.01 * float(Y.var()))[0] == 0
+    acq = {'ucb': B.device.make_acq_desc('ucb', beta=3.0),
+           'ei': B.device.make_acq_desc('ei', best=float(Y.max())),
+           'pi': B.device.make_acq_desc('pi', best=float(Y.max())),
+           'ttei': B.device.make_acq_desc('ttei', ref_mean=float(Y.max()) - 0.2, ref_std=0.1)}[acq_name]
+    bs, bi, _ = post.score_argmax(acq, C, mean_const=m0)
+    res[impl] = (bs, bi, post.query('last_used_i8'), post.query('last_shortlist'))
+  assert res[0][2] == 0.0 and res[2][2] == 1.0
+  assert 1 <= res[2][3] <= 4096
+  assert res[0][1] == res[2][1] and res[0][0] == res[2][0]
+
+
+def test_auto_mode_guard_and_overflow(B):
+  """ (i) an ill-conditioned posterior (tiny noise) exceeds the a-priori int8 bound -> fp64 is used;
+      (ii) a candidate set of exact ties overflows the shortlist -> full fp64 pass, first index wins. """
+  from dragonfly_b200 import synth_data
+  rs = np.random.RandomState(6)
+  X = rs.random_sample((1100, 6)); Y = synth_data.hartmann6(X)
+  kern = B.kernel.SEKernel(6, float(Y.var()), 0.6)
+  post = B.device.DevicePosterior(len(X))
+  post.set_kernel(B.kernel.build_descriptor(kern)); post.set_train(X, Y - float(np.median(Y)))
+  info, _ = post.build(1e-9 * float(Y.var()), 1e-9 * float(Y.var()))
+  assert info == 0
+  acq = B.device.make_acq_desc('ucb', beta=2.0)
+  C = rs.random_sample((3000, 6))
+  post.score_argmax(acq, C)
+  assert post.query('last_used_i8') == 0.0
+  assert post.query('i8_sigma2_bound') > 1e-9
+  post2 = B.device.DevicePosterior(len(X))
+  post2.set_kernel(B.kernel.build_descriptor(B.kernel.MaternKernel(6, 2.5, float(Y.var()), 0.3)))
+  post2.set_train(X, Y - float(np.median(Y)))
+  assert post2.build(0.01 * float(Y.var()))[0] == 0
+  ties = np.repeat(C[:1], 6000, axis=0)
+  bs, bi, _ = post2.score_argmax(acq, ties)
+  assert post2.query('last_used_i8') == 1.0 and post2.query('last_shortlist') == -1.0
+  assert bi == 0
