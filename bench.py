@@ -290,13 +290,21 @@ def run_ours(args):
   for name, cls in [('kstar', 0), ('gemm', 1), ('acq', 2)]:
     prof[name] = gp._post.profile_read(cls)
   gp._post.profile_enable(False)
-  gp2 = gp_core.GP(Xh, Yh, kern, mean, w['noise_var'], device=local)
-  del gp2
+  used_i8 = bool(gp._post.query('last_used_i8'))
+  shortlist = int(gp._post.query('last_shortlist'))
+  i8_bound = gp._post.query('i8_sigma2_bound')
+  del gp
+  # the same step with the int8 path disabled: pure fp64 DMMA contraction, for reference
+  device.DEFAULT_OPTIONS['score_impl'] = 0
+  one_step(cands_dev)
+  barrier()
+  ms_fp64 = timed(cands_dev, 2)
+  device.DEFAULT_OPTIONS.pop('score_impl')
 
-  t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+  t = torch.tensor([ms_dev, ms_e2e, ms_fp64], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_dev, ms_e2e = float(t[0]), float(t[1])
+  ms_dev, ms_e2e, ms_fp64 = float(t[0]), float(t[1]), float(t[2])
   value = M * world * args.steps / (ms_dev * 1e-3)
   e2e_value = M * world * args.steps / (ms_e2e * 1e-3)
 
@@ -304,34 +312,66 @@ def run_ours(args):
     N = args.n_train
     gemm_ms, gemm_launches, gemm_cands = prof['gemm']
     flops_per_cand = float(N) * float(N + 1)       # triangular W: sum_i 2(i+1) = N(N+1) flops
-    achieved = gemm_cands * flops_per_cand / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
-    peak = measure_dgemm_peak(torch, dev)
+    fp64_equiv = gemm_cands * flops_per_cand / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+    dgemm_peak = measure_dgemm_peak(torch, dev)
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # pylint: disable=broad-except
+      pass
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
     if os.path.exists(tpath):
       try:
-        traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        traffic = json.load(open(tpath)).get('dram_bytes_per_launch_i8' if used_i8 else 'dram_bytes_per_launch')
       except Exception:  # pylint: disable=broad-except
         traffic = None
+    share = {kname: prof[kname][0] / max(sum(p[0] for p in prof.values()), 1e-9) for kname in prof}
+    if used_i8:
+      # dominant kernel: score_i8_kernel (+ its digit-slicing pre-pass, timed together).  Algorithmic
+      # work: 21 int8 digit products per fp64 multiply-add of the triangular contraction.
+      ops_per_cand = 21.0 * flops_per_cand
+      achieved = gemm_cands * ops_per_cand / (gemm_ms * 1e-3) * 1e-12
+      bf16_peak = float(peaks.get('bf16_tflops', 1590.0))
+      peak = 2.0 * bf16_peak
+      roofline = {
+        'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TOP/s (int8)',
+        'frac': achieved / peak, 'traffic': traffic,
+        'kernel': 'score_i8_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, TMA ring) + slice_i8_kernel: '
+                  'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2',
+        'ops_per_candidate': ops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
+        'launches_timed': int(gemm_launches),
+        'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (%s; int8:bf16 dense ratio is 2:1 on B200)' % (
+            'measured' if 'bf16_tflops' in peaks else 'fallback 1590'),
+        'fp64_equivalent_tflops': fp64_equiv,
+        'fp64_equivalent_vs_cublas_dgemm': fp64_equiv / dgemm_peak if dgemm_peak > 0 else None,
+        'cublas_dgemm_tflops_live': dgemm_peak, 'share_of_scoring': share,
+        'i8_sigma2_error_bound': i8_bound, 'argmax_shortlist_rescored_fp64': shortlist}
+    else:
+      roofline = {
+        'bound': 'tensor', 'achieved': fp64_equiv, 'peak': dgemm_peak, 'unit': 'TFLOP/s',
+        'frac': fp64_equiv / dgemm_peak if dgemm_peak > 0 else None, 'traffic': traffic,
+        'kernel': 'score_tma_kernel (fp64 DMMA, TMA + mbarrier ring: V = L^-1 K_*^T fused with |v|^2)',
+        'flops_per_candidate': flops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
+        'launches_timed': int(gemm_launches),
+        'peak_source': 'live cuBLAS DGEMM 8192^3 burst on this GPU (MEASURED_PEAKS.json has no fp64 '
+                       'figure; DMMA issue peak measured 37.1 TFLOP/s)', 'share_of_scoring': share}
     step_ms = ms_dev / args.steps
     line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
-      'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
+      'vs_baseline': None,
+      'dtype': 'f64' + (' (sigma^2 contraction: exact int8 digit expansion of the fp64 operands on tcgen05, '
+                        '|d sigma^2| <= %.1e; arg-max re-scored in fp64 DMMA)' % i8_bound if used_i8 else ''),
+      'data': 'synthetic', 'config': workload_config(args, world),
       'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT,
               'h2d_bytes_per_step': int(M * 6 * 8 + N * 6 * 8 + N * 8),
               'd2h_bytes_per_step': 16},
       'gpu_launches': int(n_launch),
-      'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                   'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
-                   'kernel': 'score_tma_kernel (fp64 DMMA, TMA + mbarrier ring: V = L^-1 K_*^T fused with |v|^2)',
-                   'flops_per_candidate': flops_per_cand,
-                   'launch_ms_avg': gemm_ms / max(gemm_launches, 1), 'launches_timed': int(gemm_launches),
-                   'peak_source': 'live cuBLAS DGEMM 8192^3 burst on this GPU (MEASURED_PEAKS.json has '
-                                  'no fp64 figure; DMMA issue peak measured 37.1 TFLOP/s)',
-                   'share_of_scoring': {kname: prof[kname][0] / max(sum(p[0] for p in prof.values()), 1e-9)
-                                        for kname in prof}},
+      'roofline': roofline,
+      'fp64_dmma_only': {'value': M * world * 2 / (ms_fp64 * 1e-3), 'unit': UNIT,
+                         'note': 'same step with DFB200_SCORE=fp64 (no int8 path), 2 timed steps'},
     }
     if not args.no_cpu_baseline:
       wc = synth_data.make_workload('headline_hartmann6_matern_ei', n_train=args.n_train,
