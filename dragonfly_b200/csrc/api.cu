@@ -322,8 +322,14 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0
                                                          : ((out.score || md.collect) ? h->score : nullptr);
     DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
-    DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
-                         h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
+    int fused_digits = 0;
+    if (want_std && md.use_i8 && h->i8_fuse)
+      DFB_TRY(launch_kstar_i8(h, d_desc, desc, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows, h->n, npad,
+                              mean_const, mu_dev, h->kssv, h->Ki8, 2 * h->chunk * npad, 2 * npad,
+                              1.0 / i8_colscale(desc), &fused_digits));
+    if (!fused_digits)
+      DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
+                           h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
     DFB_TRY(prof_end(h, DFB_PROF_KSTAR, (double)mc));
     if (want_std) {
       GemmArgs g;
@@ -335,8 +341,9 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       if (md.use_i8) {
         // K_* = 2^F * digits: |K_*| <= k(x,x) for every supported (stationary, non-negative) kernel
         const double colscale = i8_colscale(desc);
-        DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
-                                2 * h->chunk * npad, 2 * npad));
+        if (!fused_digits)
+          DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
+                                  2 * h->chunk * npad, 2 * npad));
         DFB_TRY(launch_score_i8_args(h, h->tmWi8, h->tmKi8, nb, (int)(m_rows / 64), (int)npad, h->partial, Mc,
                                      h->rowscale, colscale));
       } else if (h->gemm_impl == 1 && h->tma_ready) {
@@ -806,6 +813,8 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
     return 0;
   }
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
+  if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
+  if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
   if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }
   if (strcmp(name, "i8_cb_group") == 0 && value >= 1) { h->i8_cb_group = (int)value; return 0; }
   if (strcmp(name, "score_impl") == 0) {

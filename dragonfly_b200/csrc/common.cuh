@@ -127,6 +127,8 @@ struct dfb_handle {
   int64_t last_shortlist = 0;     // diagnostics: size of the last shortlist, -1 = overflow -> exact pass
   int last_used_i8 = 0;
   bool i8_ready = false;
+  int i8_fuse = 1;            // K_* kernel emits the digit planes itself (no fp64 K_* round trip)
+  int i8_ts = 0;              // 1 = A digits staged in tensor memory (tcgen05.cp + TS-form MMA)
   int8_t* Wi8 = nullptr;      // [6][npad][npad]
   int8_t* Ki8 = nullptr;      // [6][chunk][npad]
   double* rowscale = nullptr; // npad  2^E_i

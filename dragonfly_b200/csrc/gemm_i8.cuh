@@ -80,6 +80,22 @@ __device__ __forceinline__ void umma_i8(unsigned tmem_d, uint64_t da, uint64_t d
       "l"(da), "l"(db), "r"(I8_IDESC), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (TS form): the digit tile was copied there once with tcgen05.cp, so the
+// 21 products of a K-block re-read only B from shared memory.
+__device__ __forceinline__ void umma_i8_ts(unsigned tmem_d, unsigned tmem_a, uint64_t db, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(I8_IDESC), "r"(accumulate)
+      : "memory");
+}
+// 128 rows x 256 bit (= one int8 digit tile of K = 32) shared -> tensor memory, 8 columns
+__device__ __forceinline__ void utccp_128x256b(unsigned tmem_dst, uint64_t src_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(src_desc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
                    smem_u32(bar))
@@ -91,6 +107,10 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, int (&r)[8]) {
                : "r"(taddr));
 }
 
+constexpr unsigned I8_TMEM_A0 = I8_S * I8_BN;          // first column of the A digit buffers (TS form)
+constexpr unsigned I8_TMEM_ABUF = I8_S * 8;            // columns per buffer: 6 digits x 32 bytes per row
+
+template <bool TS>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ScoreI8Args g) {
@@ -160,6 +180,31 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const unsigned a_lo = ((a0 & 0x3FFFFu) >> 4) | 0x10000u;
         const unsigned b_lo = (((a0 + I8_A_BYTES) & 0x3FFFFu) >> 4) | 0x10000u;
         constexpr uint64_t DESC_HI = ((uint64_t)(64u | (1u << 14) | (2u << 29))) << 32;
+        if (TS) {
+          // K-half by K-half: copy the six A digit tiles of this K = 32 block into the tensor-memory
+          // buffer (double-buffered by kh), then issue the 21 products grouped by accumulator.  The
+          // tcgen05 pipeline executes cp and mma of one thread in issue order.
+#pragma unroll
+          for (int kh = 0; kh < I8_BK / 32; kh++) {
+            const unsigned abuf = I8_TMEM_A0 + (unsigned)kh * I8_TMEM_ABUF;
+#pragma unroll
+            for (int s0 = 0; s0 < I8_S; s0++) {
+              const unsigned aoff = (s0 >> 1) * I8_A_PAIR + (s0 & 1) * I8_BK + kh * 32;
+              utccp_128x256b(abuf + (unsigned)s0 * 8u, DESC_HI | (uint64_t)(a_lo + (aoff >> 4)));
+            }
+#pragma unroll
+            for (int d = 2; d <= I8_S + 1; d++) {
+              const unsigned acc = (unsigned)((d - 2) * I8_BN);
+#pragma unroll
+              for (int sa = 1; sa <= d - 1; sa++) {
+                const int tb = d - sa;
+                const unsigned boff = ((tb - 1) >> 1) * I8_B_PAIR + ((tb - 1) & 1) * I8_BK + kh * 32;
+                const uint64_t db = DESC_HI | (uint64_t)(b_lo + (boff >> 4));
+                umma_i8_ts(acc, abuf + (unsigned)(sa - 1) * 8u, db, (kt == 0 && kh == 0 && sa == 1) ? 0u : 1u);
+              }
+            }
+          }
+        } else {
         // One digit-sum group (= one TMEM accumulator) at a time, so consecutive MMAs accumulate into
         // the same tensor-memory tile like the k-loop of an ordinary GEMM.
 #pragma unroll
@@ -177,6 +222,7 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               umma_i8(acc, da, db, (kt == 0 && sa == 1 && kh == 0) ? 0u : 1u);
             }
           }
+        }
         }
         umma_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
       }

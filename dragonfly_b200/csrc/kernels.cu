@@ -259,13 +259,23 @@ __device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, doub
   return __dmul_rn(f.scale, __dmul_rn(u, w));
 }
 
-template <int KIND, int P, int D>
+// I8OUT: instead of the fp64 K_* rows, emit their six signed 7-bit digit planes (pair-interleaved layout
+// of gemm_i8.cuh) for the tcgen05 contraction -- the fp64 matrix is then never written.
+struct KstarI8Out {
+  uint8_t* planes;        // Ki8
+  int64_t plane_bytes;    // 2 * chunk * npad
+  int64_t row_bytes;      // 2 * npad
+  double inv_colscale;    // 2^-F
+};
+
+template <int KIND, int P, int D, bool I8OUT>
 __global__ void __launch_bounds__(KF_WARPS * 32)
 kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coords,
                   const double* __restrict__ xsT, const double* __restrict__ nrmT, int64_t npad_tr,
                   const double* __restrict__ alpha, const double* __restrict__ Xc, int64_t m, int dc,
                   int64_t m_rows, double* __restrict__ Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
-                  double mean_const, double* __restrict__ mu, double* __restrict__ kss_out) {
+                  double mean_const, double* __restrict__ mu, double* __restrict__ kss_out,
+                  const KstarI8Out i8o) {
   __shared__ dfb_factor_desc fsh;
   __shared__ int coord_sh[8];
   __shared__ double bw_sh[8];
@@ -348,7 +358,21 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
       const int64_t cand = cand0 + r;
       if (cand < m_rows) {
         const double v = (cand < m) ? kv[r] : 0.0;
-        Ks[cand * ldk + j] = v;
+        if (I8OUT) {
+          // exact digit expansion of v * 2^-F (see slice_i8_kernel); one byte per digit plane
+          double x = v * i8o.inv_colscale;
+          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j >> 6) * 128 + (j & 63);
+#pragma unroll
+          for (int sd = 0; sd < I8_S; sd++) {
+            const double y = x * 128.0;
+            double a = rint(y);
+            x = y - a;
+            a = fmin(fmax(a, -127.0), 127.0);
+            dst[(int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * 64] = (uint8_t)(int8_t)(int)a;
+          }
+        } else {
+          Ks[cand * ldk + j] = v;
+        }
         mu_acc[r] = fma(v, aj, mu_acc[r]);
       }
     }
@@ -864,11 +888,16 @@ int launch_score_i8(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tm
   const int n_blocks = ga.n_rb * ga.cb_group * n_groups;
   if (n_blocks <= 0) return 0;
   if (!g_i8_attr) {
-    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)I8_SMEM_BYTES));
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)I8_SMEM_BYTES));
     g_i8_attr = true;
   }
-  score_i8_kernel<<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, ga);
+  if (h->i8_ts)
+    score_i8_kernel<true><<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, ga);
+  else
+    score_i8_kernel<false><<<n_blocks, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(tmA, tmB, ga);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -937,12 +966,19 @@ static bool launch_kstar_fast_d(dfb_handle* h, int d, unsigned blocks, const dfb
                                 int ctc, const double* xsT, const double* nrmT, int64_t npad_tr,
                                 const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows,
                                 double* Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
-                                double mean_const, double* mu, double* kss_out) {
+                                double mean_const, double* mu, double* kss_out, const KstarI8Out* i8o) {
+  KstarI8Out none;
+  memset(&none, 0, sizeof(none));
 #define DFB_KF_CASE(DD)                                                                              \
   case DD:                                                                                           \
-    kstar_fast_kernel<KIND, P, DD><<<blocks, KF_WARPS * 32, 0, h->stream>>>(                         \
-        d_desc, ctc, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid, n_write,        \
-        mean_const, mu, kss_out);                                                                    \
+    if (i8o != nullptr)                                                                              \
+      kstar_fast_kernel<KIND, P, DD, true><<<blocks, KF_WARPS * 32, 0, h->stream>>>(                 \
+          d_desc, ctc, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid, n_write,      \
+          mean_const, mu, kss_out, *i8o);                                                            \
+    else                                                                                             \
+      kstar_fast_kernel<KIND, P, DD, false><<<blocks, KF_WARPS * 32, 0, h->stream>>>(                \
+          d_desc, ctc, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid, n_write,      \
+          mean_const, mu, kss_out, none);                                                            \
     return true;
   switch (d) {
     DFB_KF_CASE(1) DFB_KF_CASE(2) DFB_KF_CASE(3) DFB_KF_CASE(4)
@@ -950,6 +986,38 @@ static bool launch_kstar_fast_d(dfb_handle* h, int d, unsigned blocks, const dfb
     default: return false;
   }
 #undef DFB_KF_CASE
+}
+
+// Returns 1 in *emitted_i8 when the digit planes were written by the K_* kernel itself (fused path).
+int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
+                    const double* xsT, const double* nrmT, int64_t npad_tr, const double* alpha,
+                    const double* Xc, int64_t m, int dc, int64_t m_rows, int64_t n_valid, int64_t n_write,
+                    double mean_const, double* mu, double* kss_out, void* planes, int64_t plane_bytes,
+                    int64_t row_bytes, double inv_colscale, int* emitted_i8) {
+  *emitted_i8 = 0;
+  if (m_rows <= 0) return 0;
+  if (!(h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
+        desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2)))
+    return 0;
+  KstarI8Out o;
+  o.planes = reinterpret_cast<uint8_t*>(planes); o.plane_bytes = plane_bytes; o.row_bytes = row_bytes;
+  o.inv_colscale = inv_colscale;
+  const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
+  const int d = desc.factors[0].n_dims;
+  bool ok = false;
+#define DFB_KF_ARGS h, d, fblocks, d_desc, 0, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, nullptr, 0,  \
+                    n_valid, n_write, mean_const, mu, kss_out, &o
+  if (desc.factors[0].kind == DFB_BASE_SE) ok = launch_kstar_fast_d<DFB_BASE_SE, 0>(DFB_KF_ARGS);
+  else if (desc.factors[0].p == 0) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 0>(DFB_KF_ARGS);
+  else if (desc.factors[0].p == 1) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 1>(DFB_KF_ARGS);
+  else ok = launch_kstar_fast_d<DFB_BASE_MATERN, 2>(DFB_KF_ARGS);
+#undef DFB_KF_ARGS
+  if (ok) {
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+    *emitted_i8 = 1;
+  }
+  return 0;
 }
 
 int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
@@ -965,7 +1033,7 @@ int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_
     const int d = desc.factors[0].n_dims;
     bool ok = false;
 #define DFB_KF_ARGS h, d, fblocks, d_desc, cand_uses_train_coords, xsT, nrmT, npad_tr, alpha, Xc, m, dc, \
-                    m_rows, Ks, ldk, n_valid, n_write, mean_const, mu, kss_out
+                    m_rows, Ks, ldk, n_valid, n_write, mean_const, mu, kss_out, nullptr
     if (desc.factors[0].kind == DFB_BASE_SE) ok = launch_kstar_fast_d<DFB_BASE_SE, 0>(DFB_KF_ARGS);
     else if (desc.factors[0].p == 0) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 0>(DFB_KF_ARGS);
     else if (desc.factors[0].p == 1) ok = launch_kstar_fast_d<DFB_BASE_MATERN, 1>(DFB_KF_ARGS);

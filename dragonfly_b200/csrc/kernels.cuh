@@ -12,6 +12,11 @@ int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_
                  const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows, double* Ks,
                  int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const, double* mu,
                  double* kss_out);
+int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
+                    const double* xsT, const double* nrmT, int64_t npad_tr, const double* alpha,
+                    const double* Xc, int64_t m, int dc, int64_t m_rows, int64_t n_valid, int64_t n_write,
+                    double mean_const, double* mu, double* kss_out, void* planes, int64_t plane_bytes,
+                    int64_t row_bytes, double inv_colscale, int* emitted_i8);
 int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double diag_add,
                      const double* yc, int with_bottom);
 int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info);

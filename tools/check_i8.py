@@ -14,6 +14,8 @@ def run(n_train, n_cand, chunk=0):
   for impl in (0, 1):
     post = device.DevicePosterior(n_train, chunk=chunk)
     post.set_option('score_impl', impl)
+    post.set_option('i8_ts', int(os.environ.get('I8_TS', '0')))
+    post.set_option('i8_fuse', int(os.environ.get('I8_FUSE', '1')))
     post.set_kernel(desc)
     post.set_train(w['X'], w['Y'] - w['mean_const'])
     info, lml = post.build(w['noise_var'])
@@ -22,12 +24,14 @@ def run(n_train, n_cand, chunk=0):
     mu, sd = post.eval(cd, mean_const=w['mean_const'])
     torch.cuda.synchronize()
     ms, nl, units = post.profile_read(1)
+    ms_k, _, _ = post.profile_read(0)
+    ms += ms_k
     acq = device.make_acq_desc('ei', best=float(w['Y'].max()))
     bs, bi, _ = post.score_argmax(acq, cd, mean_const=w['mean_const'])
     out.append((mu.cpu().numpy(), sd.cpu().numpy(), bs, bi, ms, nl))
   (mu0, sd0, bs0, bi0, ms0, nl0), (mu1, sd1, bs1, bi1, ms1, nl1) = out
   dv = np.abs(sd0 ** 2 - sd1 ** 2)
-  print('N=%d M=%d scale=%.4f: mu equal %s | max|dvar| %.3e (rel to scale %.3e) mean %.3e | nan %d/%d | argmax %d vs %d | gemm ms fp64 %.3f (%d launches) i8 %.3f (%d)' % (
+  print('N=%d M=%d scale=%.4f: mu equal %s | max|dvar| %.3e (rel to scale %.3e) mean %.3e | nan %d/%d | argmax %d vs %d | kstar+gemm ms fp64 %.3f (%d launches) i8 %.3f (%d)' % (
       n_train, n_cand, k['scale'], bool((mu0 == mu1).all()), np.nanmax(dv), np.nanmax(dv) / k['scale'], np.nanmean(dv),
       int(np.isnan(sd1).sum()), int(np.isnan(sd0).sum()), bi0, bi1, ms0, nl0, ms1, nl1))
   idx = int(np.nanargmax(dv))
