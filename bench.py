@@ -332,17 +332,21 @@ def run_ours(args):
       # work: 21 int8 digit products per fp64 multiply-add of the triangular contraction.
       ops_per_cand = 21.0 * flops_per_cand
       achieved = gemm_cands * ops_per_cand / (gemm_ms * 1e-3) * 1e-12
-      bf16_peak = float(peaks.get('bf16_tflops', 1590.0))
-      peak = 2.0 * bf16_peak
+      # int8 tensor peak: MEASURED_PEAKS.json has no int8 figure, so the denominator is the measured
+      # tcgen05.mma kind::i8 issue rate of tools/ubench_i8.cu on this pool's B200
+      # (profiles/r01_ubench_tcgen05_i8.txt): 4577 TOP/s for N >= 128; 2777 TOP/s for the N = 64 shape
+      # that six TMEM accumulators force on this kernel.
+      peak, peak_n64 = 4577.2, 2777.1
       roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TOP/s (int8)',
-        'frac': achieved / peak, 'traffic': traffic,
-        'kernel': 'score_i8_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, TMA ring) + slice_i8_kernel: '
-                  'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2',
+        'frac': achieved / peak, 'frac_of_shape_limited_peak': achieved / peak_n64, 'traffic': traffic,
+        'kernel': 'score_i8_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, TMA ring), digit planes '
+                  'emitted by the K_* kernel: V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2',
         'ops_per_candidate': ops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
         'launches_timed': int(gemm_launches),
-        'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops (%s; int8:bf16 dense ratio is 2:1 on B200)' % (
-            'measured' if 'bf16_tflops' in peaks else 'fallback 1590'),
+        'peak_source': 'measured tcgen05 kind::i8 issue rate, M128 N256 K32, tools/ubench_i8.cu on this pool '
+                       '(profiles/r01_ubench_tcgen05_i8.txt); MEASURED_PEAKS.json bf16 burst = %s TF/s for '
+                       'comparison' % peaks.get('bf16_tflops', 'n/a'),
         'fp64_equivalent_tflops': fp64_equiv,
         'fp64_equivalent_vs_cublas_dgemm': fp64_equiv / dgemm_peak if dgemm_peak > 0 else None,
         'cublas_dgemm_tflops_live': dgemm_peak, 'share_of_scoring': share,
