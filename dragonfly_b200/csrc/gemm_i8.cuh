@@ -22,8 +22,9 @@
 //           busy; profiles/r01_i8_ncu_summary.txt)
 //   warp 1  TMEM allocator + MMA issuer (one elected thread): 42 UTCIMMA (M128 N64 K32) per stage,
 //           tcgen05.commit releases the stage / signals the accumulators
-//   warps 2-5 epilogue: tcgen05.ld 32x32b, fp64 recombination, row scale, square, warp-shuffle
-//           column reduction, deterministic partial sums (same `partial` layout as the DMMA kernels)
+//   warps 2-9 epilogue (two per TMEM lane quarter): tcgen05.ld 32x32b, fp64 recombination, row scale,
+//           square, halving-butterfly column reduction, deterministic partial sums (same `partial`
+//           layout as the DMMA kernels)
 // W is lower triangular: row block rb only contracts k < 128 (rb + 1).
 #pragma once
 #include <cuda.h>
@@ -40,7 +41,7 @@ constexpr int I8_B_PAIR = I8_BN * 2 * I8_BK;  // 8192 B
 constexpr int I8_A_BYTES = (I8_S / 2) * I8_A_PAIR;
 constexpr int I8_B_BYTES = (I8_S / 2) * I8_B_PAIR;
 constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 73728
-constexpr int I8_THREADS = 192;
+constexpr int I8_THREADS = 320;                  // producer, MMA issuer, 8 epilogue warps
 constexpr int I8_TMEM_COLS = 512;
 constexpr size_t I8_SMEM_BYTES = (size_t)I8_STAGES * I8_STAGE_BYTES + 1024 + 4 * I8_BN * sizeof(double) +
                                  (2 * I8_STAGES + 1) * 8 + 64;
@@ -229,8 +230,9 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       umma_commit(accum_bar);                // accumulators complete
     }
   } else {
-    // ---------------- epilogue warps 2..5 -----------------------------------------------------------------
+    // ---------------- epilogue warps 2..9: two warps per TMEM lane quarter, 32 columns each ---------------
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;        // which 32 of the 64 candidate columns
     const int row = q * 32 + lane;
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -238,11 +240,12 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const double rs = (tmem_base == 0u) ? g.rowscale[(int64_t)rb * I8_BM + row] * g.colscale
                                         : __longlong_as_double(0x7ff8000000000000ll);
     const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
-    for (int c0 = 0; c0 < I8_BN; c0 += 8) {
+    for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 8) {
       int r[I8_S][8];
 #pragma unroll
       for (int d = 0; d < I8_S; d++) tmem_ld8(lane_addr + (unsigned)(d * I8_BN + c0), r[d]);
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      double sq[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         // v = sum_d G_d 2^(-7(d+2)), smallest weight first
@@ -253,16 +256,37 @@ score_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         v = fma((double)r[1][j], 0x1p-21, v);
         v = fma((double)r[0][j], 0x1p-14, v);
         v *= rs;
-        double sq = v * v;
-        sq += __shfl_xor_sync(0xffffffffu, sq, 16);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        if (lane == 0) colsum[q * I8_BN + c0 + j] = sq;
+        sq[j] = v * v;
       }
+      // Sum each of the 8 columns over the warp's 32 rows with a halving butterfly: every exchange step
+      // keeps half of the columns per lane, so 4 + 2 + 1 + 1 + 1 shuffles replace 8 x 5.  The summation
+      // tree is fixed, so results are reproducible run to run.
+      const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+      double w4[4], w2[2], w1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double send = h16 ? sq[j] : sq[j + 4];
+        const double keep = h16 ? sq[j + 4] : sq[j];
+        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const double send = h8 ? w4[j] : w4[j + 2];
+        const double keep = h8 ? w4[j + 2] : w4[j];
+        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const double send = h4 ? w2[0] : w2[1];
+        const double keep = h4 ? w2[1] : w2[0];
+        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+      w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+      // lanes with (lane & 3) == 0 now hold one column each: 4*[bit4] + 2*[bit3] + [bit2]
+      if ((lane & 3) == 0)
+        colsum[q * I8_BN + c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = w1;
     }
-    asm volatile("bar.sync 1, 128;\n" ::: "memory");     // the four epilogue warps
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");     // the eight epilogue warps
     const int et = tid - 64;
     if (et < I8_BN)
       g.partial[(int64_t)rb * g.ld_partial + (int64_t)cb * I8_BN + et] =

@@ -148,7 +148,7 @@ class GP(object):
 
   def _new_device_posterior(self, n_max):
     from .device import DevicePosterior
-    return DevicePosterior(n_max, device=self._device)
+    return DevicePosterior(n_max, device=getattr(self, '_device', None))
 
   def _build_on_device(self, X_mat, y_centred, flags):
     if self.handle_non_psd_kernels not in ('guaranteed_psd', 'try_before_project', 'project_first'):
@@ -185,8 +185,10 @@ class GP(object):
     self._mean_const = _constant_mean_value(self.mean_func, X_mat.shape[1])
 
   def _state(self, name):
+    if not hasattr(self, '_cache'):
+      self._cache = {}
     if name not in self._cache:
-      if self._post is None:
+      if getattr(self, '_post', None) is None:
         raise RuntimeError('Posterior has not been built.')
       L, a, K = self._post.get_state(want_L=(name == 'L'), want_alpha=(name == 'alpha'),
                                      want_K=(name == 'K'))
@@ -198,29 +200,38 @@ class GP(object):
   # gp.K_trtr_wo_noise by gp_core.py:203: lazily copied back as NumPy arrays.
   @property
   def L(self):
-    return None if (self._post is None and 'L' not in self._cache) else self._state('L')
+    return None if (getattr(self, '_post', None) is None and
+                    'L' not in getattr(self, '_cache', {})) else self._state('L')
 
   @L.setter
   def L(self, value):
     if value is not None:
+      if not hasattr(self, '_cache'):
+        self._cache = {}
       self._cache['L'] = value
 
   @property
   def alpha(self):
-    return None if (self._post is None and 'alpha' not in self._cache) else self._state('alpha')
+    return None if (getattr(self, '_post', None) is None and
+                    'alpha' not in getattr(self, '_cache', {})) else self._state('alpha')
 
   @alpha.setter
   def alpha(self, value):
     if value is not None:
+      if not hasattr(self, '_cache'):
+        self._cache = {}
       self._cache['alpha'] = value
 
   @property
   def K_trtr_wo_noise(self):
-    return None if (self._post is None and 'K' not in self._cache) else self._state('K')
+    return None if (getattr(self, '_post', None) is None and
+                    'K' not in getattr(self, '_cache', {})) else self._state('K')
 
   @K_trtr_wo_noise.setter
   def K_trtr_wo_noise(self, value):
     if value is not None:
+      if not hasattr(self, '_cache'):
+        self._cache = {}
       self._cache['K'] = value
 
   def compute_log_marginal_likelihood(self):

@@ -617,3 +617,50 @@ def test_auto_mode_guard_and_overflow(B):
   bs, bi, _ = post2.score_argmax(acq, ties)
   assert post2.query('last_used_i8') == 1.0 and post2.query('last_shortlist') == -1.0
   assert bi == 0
+
+
+def test_auto_mode_with_group_test_kernel_and_mf(B):
+  """ The int8 pass also serves Add-UCB's per-group descriptor (dfb_set_test_kernel) and the MF product
+      kernel: default mode == fp64 mode, bit for bit, at N >= 1024. """
+  from dragonfly_b200 import synth_data
+  rs = np.random.RandomState(11)
+  n, d = 1100, 10
+  X = rs.random_sample((n, d)); Y = synth_data.tiled(synth_data.park1, 4, X)
+  groups = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+  sub = [B.kernel.MaternKernel(4, 2.5, 1.0, 0.5), B.kernel.SEKernel(4, 1.0, 0.5), B.kernel.MaternKernel(2, 1.5, 1.0, 0.4)]
+  kern = B.kernel.AdditiveKernel(float(Y.var()) / 3, sub, groups)
+  pts = {}
+  for impl in (0, 2):
+    B.device.DEFAULT_OPTIONS['score_impl'] = impl
+    try:
+      gp = B.gp_core.GP(X, Y, kern, const_mean(float(np.median(Y))), 0.01 * float(Y.var()))
+      np.random.seed(17)
+      pts[impl] = B.acq.asy.add_ucb(gp, anc(B, 'add_ucb', 9000, n, d, float(Y.max())))
+      used = gp._post.query('last_used_i8')
+      assert used == (1.0 if impl == 2 else 0.0)
+    finally:
+      B.device.DEFAULT_OPTIONS.pop('score_impl', None)
+  assert (pts[0] == pts[2]).all()
+
+
+def test_thompson_blocks_at_scale(B):
+  """ Several 4096-candidate blocks x 64 draws on an N = 1100 posterior: finite, right shape, and the
+      first block equals a stand-alone draw with the same normals (blocks are independent). """
+  from dragonfly_b200 import synth_data
+  rs = np.random.RandomState(12)
+  X = rs.random_sample((1100, 6)); Y = synth_data.hartmann6(X)
+  gp = B.gp_core.GP(X, Y, B.kernel.MaternKernel(6, 2.5, float(Y.var()), 0.3), const_mean(float(np.median(Y))),
+                    0.01 * float(Y.var()))
+  C = rs.random_sample((9000, 6))
+  np.random.seed(3)
+  S = gp.draw_samples(64, C)
+  assert S.shape == (64, 9000) and np.isfinite(S).all()
+  np.random.seed(3)
+  U = np.random.normal(size=(9000, 64))
+  info, smp, _ = gp._post.ts_draws(C[:4096], np.ascontiguousarray(U[:4096].T), mean_const=gp._mean_const)
+  assert info == 0
+  close(S[:, :4096], smp.cpu().numpy(), atol=1e-9)
+  mu, sd = gp.eval(C[:4096], 'std')
+  # the draws scatter around the posterior mean with the posterior standard deviation
+  zscore = (S[:, :4096] - mu) / sd
+  assert abs(zscore.mean()) < 0.05 and 0.9 < zscore.std() < 1.1
