@@ -232,10 +232,10 @@ kstar_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coo
 
 // ---- fast path of kstar_kernel for the plain SE / Matern kernels (1 term, 1 factor, d <= 8) ------------
 // Same arithmetic, same operation order; what changes is the bookkeeping: kind, p and d are compile
-// time, the candidate coordinates live in registers and each warp carries KF_R independent candidate
-// rows through the exp/sqrt dependency chains.  (The generic kernel spends ~220 of its ~270
+// time, the candidate coordinates live in registers and each lane carries 4 x KF_R independent entries
+// (4 consecutive training points x KF_R candidate rows) through the exp/sqrt dependency chains.  (The generic kernel spends ~220 of its ~270
 // instructions per entry interpreting the descriptor: profiles/r01_kstar_ncu_summary.txt.)
-constexpr int KF_R = 4;
+constexpr int KF_R = 2;
 constexpr int KF_WARPS = 4;
 constexpr int KF_CANDS = KF_R * KF_WARPS;
 
@@ -331,49 +331,85 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
   double mu_acc[KF_R];
 #pragma unroll
   for (int r = 0; r < KF_R; r++) mu_acc[r] = 0.0;
-  for (int64_t j = lane; j < n_write; j += 32) {
-    double kv[KF_R];
+  // each lane owns 4 consecutive training points per step (128 per warp step): 16-byte loads of the
+  // SoA coordinates, 16-byte stores of the fp64 rows or one packed 32-bit store per digit plane, and
+  // 4 x KF_R independent exp/sqrt chains in flight
+  for (int64_t j0 = 4 * lane; j0 < n_write; j0 += 128) {
+    double kv[KF_R][4];
+    double aj[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int r = 0; r < KF_R; r++) kv[r] = 0.0;
-    double aj = 0.0;
-    if (j < n_valid) {
-      double xt[D];
+    for (int r = 0; r < KF_R; r++)
 #pragma unroll
-      for (int q = 0; q < D; q++) xt[q] = xsT[(int64_t)q * npad_tr + j];
-      const double nt2 = nrmT[j];
-      if (alpha != nullptr) aj = alpha[j];
+      for (int e = 0; e < 4; e++) kv[r][e] = 0.0;
+    if (j0 < n_valid) {
+      double xt[D][4];
 #pragma unroll
-      for (int r = 0; r < KF_R; r++) {
-        double dot = 0.0;
+      for (int q = 0; q < D; q++) {
+        const double2 lo = *reinterpret_cast<const double2*>(xsT + (int64_t)q * npad_tr + j0);
+        const double2 hi = *reinterpret_cast<const double2*>(xsT + (int64_t)q * npad_tr + j0 + 2);
+        xt[q][0] = lo.x; xt[q][1] = lo.y; xt[q][2] = hi.x; xt[q][3] = hi.y;
+      }
+      double nt2[4];
+      {
+        const double2 lo = *reinterpret_cast<const double2*>(nrmT + j0);
+        const double2 hi = *reinterpret_cast<const double2*>(nrmT + j0 + 2);
+        nt2[0] = lo.x; nt2[1] = lo.y; nt2[2] = hi.x; nt2[3] = hi.y;
+      }
+      if (alpha != nullptr) {
+        const double2 lo = *reinterpret_cast<const double2*>(alpha + j0);
+        const double2 hi = *reinterpret_cast<const double2*>(alpha + j0 + 2);
+        aj[0] = lo.x; aj[1] = lo.y; aj[2] = hi.x; aj[3] = hi.y;
+      }
 #pragma unroll
-        for (int q = 0; q < D; q++) dot = fma(xc[r][q], xt[q], dot);
-        double d2 = __dadd_rn(__dadd_rn(nt2, nc[r]), -2.0 * dot);
-        d2 = fmax(d2, 0.0);
-        const double prod = __dmul_rn(pre, base_value_fast<KIND, P>(f, d2));
-        kv[r] = __dmul_rn(post, __dadd_rn(0.0, prod));
+      for (int e = 0; e < 4; e++) {
+        const bool valid = (j0 + e) < n_valid;
+        if (!valid) aj[e] = 0.0;
+#pragma unroll
+        for (int r = 0; r < KF_R; r++) {
+          double dot = 0.0;
+#pragma unroll
+          for (int q = 0; q < D; q++) dot = fma(xc[r][q], xt[q][e], dot);
+          double d2 = __dadd_rn(__dadd_rn(nt2[e], nc[r]), -2.0 * dot);
+          d2 = fmax(d2, 0.0);
+          const double prod = __dmul_rn(pre, base_value_fast<KIND, P>(f, d2));
+          kv[r][e] = valid ? __dmul_rn(post, __dadd_rn(0.0, prod)) : 0.0;
+        }
       }
     }
 #pragma unroll
     for (int r = 0; r < KF_R; r++) {
       const int64_t cand = cand0 + r;
       if (cand < m_rows) {
-        const double v = (cand < m) ? kv[r] : 0.0;
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (cand < m) ? kv[r][e] : 0.0;
         if (I8OUT) {
-          // exact digit expansion of v * 2^-F (see slice_i8_kernel); one byte per digit plane
-          double x = v * i8o.inv_colscale;
-          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j >> 6) * 128 + (j & 63);
+          // exact digit expansion of v * 2^-F (0 <= v * 2^-F < 1/2, so every digit fits int8 without
+          // clamping; see slice_i8_kernel); four columns packed per 32-bit store
+          double x[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) x[e] = v[e] * i8o.inv_colscale;
+          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 >> 6) * 128 + (j0 & 63);
 #pragma unroll
           for (int sd = 0; sd < I8_S; sd++) {
-            const double y = x * 128.0;
-            double a = rint(y);
-            x = y - a;
-            a = fmin(fmax(a, -127.0), 127.0);
-            dst[(int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * 64] = (uint8_t)(int8_t)(int)a;
+            uint32_t pack = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const double y = x[e] * 128.0;
+              const double a = rint(y);
+              x[e] = y - a;
+              pack |= ((uint32_t)((int)a) & 0xffu) << (8 * e);
+            }
+            *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * 64) = pack;
           }
         } else {
-          Ks[cand * ldk + j] = v;
+          double2 lo, hi;
+          lo.x = v[0]; lo.y = v[1]; hi.x = v[2]; hi.y = v[3];
+          *reinterpret_cast<double2*>(Ks + cand * ldk + j0) = lo;
+          *reinterpret_cast<double2*>(Ks + cand * ldk + j0 + 2) = hi;
         }
-        mu_acc[r] = fma(v, aj, mu_acc[r]);
+#pragma unroll
+        for (int e = 0; e < 4; e++) mu_acc[r] = fma(v[e], aj[e], mu_acc[r]);
       }
     }
   }
@@ -997,7 +1033,8 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
   *emitted_i8 = 0;
   if (m_rows <= 0) return 0;
   if (!(h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
-        desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2)))
+        desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2) &&
+        n_write % 4 == 0 && npad_tr % 4 == 0))
     return 0;
   KstarI8Out o;
   o.planes = reinterpret_cast<uint8_t*>(planes); o.plane_bytes = plane_bytes; o.row_bytes = row_bytes;
@@ -1028,7 +1065,9 @@ int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_
   if (m_rows <= 0) return 0;
   // fast path: plain SE / Matern(p <= 2) on <= 8 coordinates
   if (h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
-      desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2)) {
+      desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2) &&
+      n_write % 4 == 0 && npad_tr % 4 == 0 && ldk % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(Ks) & 15) == 0 && (alpha == nullptr || (reinterpret_cast<uintptr_t>(alpha) & 15) == 0)) {
     const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
     const int d = desc.factors[0].n_dims;
     bool ok = false;
