@@ -443,53 +443,90 @@ __global__ void init_tall_kernel(double* T, int64_t n, int64_t npad, double diag
 // L_kk^-T while the lower triangle holds L_kk.  A non-positive (or NaN) pivot reports
 // info = global index + 1, the LAPACK dpotrf convention behind np.linalg.LinAlgError
 // (general_utils.py:176-180).
-constexpr int DIAG_LD = TILE + 1;
+// Register-resident version: thread (ty, tx) of a 16 x 16 grid owns the 8 x 8 block-cyclic elements
+// (ty + 16a, tx + 16b); per column only the scaled column (128 values) goes through shared memory.
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* T, int64_t ld, int step,
                                                          double* Dinv, int* info) {
-  extern __shared__ __align__(16) double S[];   // [128][129] + dL[128] + dW[128]
+  __shared__ double colbuf[TILE];
+  __shared__ double dLs[TILE];
+  __shared__ double piv_sh;
   if (*info != 0) return;
-  double* dL = S + TILE * DIAG_LD;
-  double* dW = dL + TILE;
   double* blk = T + (int64_t)step * TILE * ld + (int64_t)step * TILE;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    const int i = idx >> 7, c = idx & 127;
-    S[i * DIAG_LD + c] = (c <= i) ? blk[(int64_t)i * ld + c] : 0.0;
-  }
-  __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double e[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      e[a][b] = (c <= i) ? blk[(int64_t)i * ld + c] : 0.0;
+    }
   for (int j = 0; j < TILE; j++) {
-    const double piv = S[j * DIAG_LD + j];
+    const int jb = j >> 4, jt = j & 15;
+    if (ty == jt && tx == jt) {
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+        if (a == jb) piv_sh = e[a][a];
+    }
+    __syncthreads();
+    const double piv = piv_sh;
     if (!(piv > 0.0)) {                 // uniform across the block
       if (tid == 0) atomicCAS(info, 0, step * TILE + j + 1);
       return;
     }
     const double dj = sqrt(piv);
     const double rj = 1.0 / dj;
-    __syncthreads();                    // everyone has read the pivot before column j changes
-    if (tid < TILE) {
-      if (tid == j) { dL[j] = dj; dW[j] = rj; S[j * DIAG_LD + j] = rj; }
-      else S[tid * DIAG_LD + j] = S[tid * DIAG_LD + j] / dj;
+    if (tx == jt) {                     // owners of column j scale it and publish it
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        if (b == jb) {
+#pragma unroll
+          for (int a = 0; a < 8; a++) {
+            const int i = ty + 16 * a;
+            const double nv = (i == j) ? rj : e[a][b] / dj;
+            e[a][b] = nv;
+            colbuf[i] = nv;
+          }
+        }
+      }
+      if (ty == jt) dLs[j] = dj;
     }
     __syncthreads();
-    // S[i][c] -= m_i * S[c][j] for c > j and (i <= j  [inverse rows]  or  c <= i  [Cholesky rows]);
-    // m_i = S[i][j] (for i == j this slot temporarily holds 1/d_j).
-    for (int i = ty; i < TILE; i += 16) {
-      const double mi = S[i * DIAG_LD + j];
-      const int c_hi = (i <= j) ? (TILE - 1) : i;
-      for (int c = j + 1 + tx; c <= c_hi; c += 16)
-        S[i * DIAG_LD + c] = fma(-mi, S[c * DIAG_LD + j], S[i * DIAG_LD + c]);
+    // e(i,c) -= m_i * col_c for c > j and (i <= j [inverse rows] or c <= i [Cholesky rows]);
+    // m_i = colbuf[i] (1/d_j for i == j), col_c = colbuf[c]
+    double mrow[8], mcol[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) mrow[a] = colbuf[ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 8; b++) mcol[b] = colbuf[tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int i = ty + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        const int c = tx + 16 * b;
+        if (c > j && (i <= j || c <= i)) e[a][b] = fma(-mrow[a], mcol[b], e[a][b]);
+      }
     }
-    __syncthreads();
   }
-  for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    const int i = idx >> 7, c = idx & 127;
-    double lv, wv;
-    if (c < i) { lv = S[i * DIAG_LD + c]; wv = S[c * DIAG_LD + i]; }
-    else if (c == i) { lv = dL[i]; wv = dW[i]; }
-    else { lv = 0.0; wv = 0.0; }
-    blk[(int64_t)i * ld + c] = lv;
-    Dinv[i * TILE + c] = wv;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int i = ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int c = tx + 16 * b;
+      if (c < i) {
+        blk[(int64_t)i * ld + c] = e[a][b];                 // L
+      } else if (c == i) {
+        blk[(int64_t)i * ld + c] = dLs[i];
+        Dinv[i * TILE + c] = e[a][b];                        // 1 / L_ii
+      } else {
+        blk[(int64_t)i * ld + c] = 0.0;
+        Dinv[i * TILE + c] = 0.0;                            // L^-1 is lower triangular
+        Dinv[c * TILE + i] = e[a][b];                        // (L^-T)[i][c] = (L^-1)[c][i]
+      }
+    }
   }
 }
 
@@ -1106,13 +1143,8 @@ int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double d
 
 static bool g_diag_attr = false;
 int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info) {
-  const size_t smem = sizeof(double) * (TILE * DIAG_LD + 2 * TILE);
-  if (!g_diag_attr) {
-    DFB_CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    g_diag_attr = true;
-  }
-  chol_diag_kernel<<<1, 256, smem, h->stream>>>(T, ld, step, Dinv, info);
+  (void)g_diag_attr;
+  chol_diag_kernel<<<1, 256, 0, h->stream>>>(T, ld, step, Dinv, info);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
