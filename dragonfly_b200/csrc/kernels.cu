@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* T, int64_t ld, i
 #pragma unroll
           for (int a = 0; a < 8; a++) {
             const int i = ty + 16 * a;
-            const double nv = (i == j) ? rj : e[a][b] / dj;
+            const double nv = (i == j) ? rj : e[a][b] * rj;   // dpotf2 scales by the reciprocal too
             e[a][b] = nv;
             colbuf[i] = nv;
           }
