@@ -493,19 +493,29 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* T, int64_t ld, i
     }
     __syncthreads();
     // e(i,c) -= m_i * col_c for c > j and (i <= j [inverse rows] or c <= i [Cholesky rows]);
-    // m_i = colbuf[i] (1/d_j for i == j), col_c = colbuf[c]
-    double mrow[8], mcol[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) mrow[a] = colbuf[ty + 16 * a];
-#pragma unroll
-    for (int b = 0; b < 8; b++) mcol[b] = colbuf[tx + 16 * b];
+    // m_i = colbuf[i] (1/d_j for i == j), col_c = colbuf[c].  Branch-free: an element is statically
+    // lower (c <= i: active iff c > j) or upper (c > i: active iff i <= j and c > j), so masking the
+    // column factor by (c > j) and, for upper elements, the row factor by (i <= j) leaves 64 plain FMAs.
+    double mrow[8], mrow_inv[8], mcol[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
       const int i = ty + 16 * a;
+      mrow[a] = colbuf[i];
+      mrow_inv[a] = (i <= j) ? mrow[a] : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int c = tx + 16 * b;
+      mcol[b] = (c > j) ? colbuf[c] : 0.0;
+    }
+    const bool diag_lower = (tx <= ty);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const double mdiag = diag_lower ? mrow[a] : mrow_inv[a];
 #pragma unroll
       for (int b = 0; b < 8; b++) {
-        const int c = tx + 16 * b;
-        if (c > j && (i <= j || c <= i)) e[a][b] = fma(-mrow[a], mcol[b], e[a][b]);
+        const double mr = (b < a) ? mrow[a] : ((b == a) ? mdiag : mrow_inv[a]);
+        e[a][b] = fma(-mr, mcol[b], e[a][b]);
       }
     }
   }
