@@ -246,8 +246,15 @@ static int prepare_i8(dfb_handle* h) {
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
   // pair-interleaved digit planes: 3 planes of rows x (2 * npad) bytes
   DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, 2 * npad * npad, 2 * npad));
-  DFB_TRY(make_tensor_map_3d_u8(&h->tmWi8, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 128, 128));
-  DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 128, 64));
+  if (h->i8_impl == 1) {
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmW2, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmW3, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 3));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK2, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 128, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK3, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 128, 3));
+  } else {
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmWi8, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 128, 128, 3));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 128, 64, 3));
+  }
   h->i8_ready = true;
   return 0;
 }
@@ -344,8 +351,12 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
         if (!fused_digits)
           DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
                                   2 * h->chunk * npad, 2 * npad));
-        DFB_TRY(launch_score_i8_args(h, h->tmWi8, h->tmKi8, nb, (int)(m_rows / 64), (int)npad, h->partial, Mc,
-                                     h->rowscale, colscale));
+        if (h->i8_impl == 1)
+          DFB_TRY(launch_score_i8x2_args(h, h->tmW2, h->tmW3, h->tmK2, h->tmK3, nb, (int)(m_rows / TILE), (int)npad,
+                                         h->partial, Mc, h->rowscale, colscale));
+        else
+          DFB_TRY(launch_score_i8_args(h, h->tmWi8, h->tmKi8, nb, (int)(m_rows / 64), (int)npad, h->partial, Mc,
+                                       h->rowscale, colscale));
       } else if (h->gemm_impl == 1 && h->tma_ready) {
         ScoreTmaArgs ta;
         ta.n_rb = g.n_rb; ta.n_cb = g.n_cb; ta.K = g.K; ta.partial = g.partial; ta.ld_partial = g.ld_partial;
@@ -398,10 +409,11 @@ int dfb_create(dfb_handle** out, int device) {
   }
   if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return -1; }
   DFB_CUDA_OK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  DFB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) {
-    set_error("device %d is sm_%d%d; libdfb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  int cc_major = 0, cc_minor = 0;     // attribute queries: cudaGetDeviceProperties costs milliseconds per call
+  DFB_CUDA_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  DFB_CUDA_OK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (cc_major < 10) {
+    set_error("device %d is sm_%d%d; libdfb200 is built for sm_100a (B200) only", device, cc_major, cc_minor);
     return -2;
   }
   dfb_handle* h = new (std::nothrow) dfb_handle();
@@ -815,6 +827,12 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
+  if (strcmp(name, "i8_impl") == 0) {
+    if (value != 0 && value != 1) { set_error("i8_impl must be 0 (N=64, one pass) or 1 (N=128, two passes)"); return -1; }
+    h->i8_impl = (int)value;
+    if (h->i8_ready) { DFB_CUDA_OK(cudaSetDevice(h->device)); DFB_TRY(prepare_i8(h)); }   // re-slice W in the new layout
+    return 0;
+  }
   if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }
   if (strcmp(name, "i8_cb_group") == 0 && value >= 1) { h->i8_cb_group = (int)value; return 0; }
   if (strcmp(name, "score_impl") == 0) {

@@ -134,6 +134,8 @@ struct dfb_handle {
   double* rowscale = nullptr; // npad  2^E_i
   double* rowinv = nullptr;   // npad  2^-E_i
   CUtensorMap tmWi8, tmKi8;
+  int i8_impl = 1;            // 0 = one pass, N = 64 MMAs (gemm_i8.cuh); 1 = two passes, N = 128 (gemm_i8x2.cuh)
+  CUtensorMap tmW2, tmW3, tmK2, tmK3;   // 2- and 3-plane boxes of the digit planes (i8_impl 1)
 
   // model state
   dfb_kernel_desc desc_tr;

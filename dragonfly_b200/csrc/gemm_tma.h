@@ -19,7 +19,11 @@ int launch_score_tma(dfb_handle* h, const CUtensorMap& tmW, const CUtensorMap& t
 
 struct ScoreI8Args;
 int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t planes,
-                          int64_t row_ld_bytes, int64_t plane_stride_bytes, int box_cols, int box_rows);
+                          int64_t row_ld_bytes, int64_t plane_stride_bytes, int box_cols, int box_rows,
+                          int box_planes);
+int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtensorMap& tmA3,
+                           const CUtensorMap& tmB2, const CUtensorMap& tmB3, int n_rb, int n_cb, int K,
+                           double* partial, int64_t ld_partial, const double* rowscale, double colscale);
 int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
                         double* rowscale, double* rowinv);
 int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,

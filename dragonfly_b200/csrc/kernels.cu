@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "gemm_tma.cuh"
 #include "gemm_i8.cuh"
+#include "gemm_i8x2.cuh"
 
 namespace dfb {
 
@@ -266,6 +267,7 @@ struct KstarI8Out {
   int64_t plane_bytes;    // 2 * chunk * npad
   int64_t row_bytes;      // 2 * npad
   double inv_colscale;    // 2^-F
+  int kb;                 // k-values per interleave block (64 or 32)
 };
 
 template <int KIND, int P, int D, bool I8OUT>
@@ -389,7 +391,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
           double x[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) x[e] = v[e] * i8o.inv_colscale;
-          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 >> 6) * 128 + (j0 & 63);
+          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 / i8o.kb) * (2 * i8o.kb) + (j0 % i8o.kb);
 #pragma unroll
           for (int sd = 0; sd < I8_S; sd++) {
             uint32_t pack = 0;
@@ -400,7 +402,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
               x[e] = y - a;
               pack |= ((uint32_t)((int)a) & 0xffu) << (8 * e);
             }
-            *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * 64) = pack;
+            *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) = pack;
           }
         } else {
           double2 lo, hi;
@@ -849,7 +851,7 @@ __global__ void row_exponent_kernel(const double* __restrict__ M, int64_t ld, in
 //   (s/2) * plane_bytes + row * 2*cols + (k/64) * 128 + (s%2) * 64 + (k%64).
 __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int64_t cols4,
                                 const double* __restrict__ rowinv, double inv_const,
-                                uint32_t* __restrict__ out, int64_t plane_words) {
+                                uint32_t* __restrict__ out, int64_t plane_words, int kb) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols4) return;
   const int64_t row = idx / cols4, c4 = idx - row * cols4;
@@ -858,7 +860,8 @@ __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_
   double x[4] = {in.x * inv, in.y * inv, in.z * inv, in.w * inv};
   const int64_t k = 4 * c4;
   const int64_t row_words = 2 * cols4;                       // 2 * cols bytes
-  const int64_t base = row * row_words + (k >> 6) * 32 + ((k & 63) >> 2);
+  // kb = k-values per interleave block (64: gemm_i8.cuh, 32: gemm_i8x2.cuh)
+  const int64_t base = row * row_words + (k / kb) * (kb >> 1) + ((k % kb) >> 2);
 #pragma unroll
   for (int s = 0; s < I8_S; s++) {
     uint32_t pack = 0;
@@ -870,7 +873,7 @@ __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_
       a = fmin(fmax(a, -127.0), 127.0);
       pack |= ((uint32_t)((int)a) & 0xffu) << (8 * q);
     }
-    out[(int64_t)(s >> 1) * plane_words + base + (s & 1) * 16] = pack;
+    out[(int64_t)(s >> 1) * plane_words + base + (s & 1) * (kb >> 2)] = pack;
   }
 }
 
@@ -937,7 +940,8 @@ int make_tensor_map_2d_f64(CUtensorMap* out, const double* base, int64_t rows, i
 }
 
 int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t planes,
-                          int64_t row_ld_bytes, int64_t plane_stride_bytes, int box_cols, int box_rows) {
+                          int64_t row_ld_bytes, int64_t plane_stride_bytes, int box_cols, int box_rows,
+                          int box_planes) {
   static EncodeTiledFn encode = nullptr;
   if (encode == nullptr) {
     void* fn = nullptr;
@@ -951,10 +955,11 @@ int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int6
   }
   const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
   const cuuint64_t gstride[2] = {(cuuint64_t)row_ld_bytes, (cuuint64_t)plane_stride_bytes};
-  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)planes};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (3d u8) failed with CUresult %d", (int)r);
@@ -992,7 +997,32 @@ int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMa
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = h->i8_cb_group;
+  g.dbg = 0;
   return launch_score_i8(h, tmA, tmB, g);
+}
+
+static bool g_i8x2_attr = false;
+int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtensorMap& tmA3,
+                           const CUtensorMap& tmB2, const CUtensorMap& tmB3, int n_rb, int n_cb, int K,
+                           double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
+  ScoreI8Args g;
+  g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
+  g.rowscale = rowscale; g.colscale = colscale;
+  static const int dbg = getenv("DFB200_I8_DBG") ? atoi(getenv("DFB200_I8_DBG")) : 0;
+  g.dbg = dbg;
+  g.cb_group = h->i8_cb_group > n_cb ? n_cb : h->i8_cb_group;
+  const int n_groups = (n_cb + g.cb_group - 1) / g.cb_group;
+  const int n_blocks = n_rb * g.cb_group * n_groups;
+  if (n_blocks <= 0) return 0;
+  if (!g_i8x2_attr) {
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)X2_SMEM_BYTES));
+    g_i8x2_attr = true;
+  }
+  score_i8x2_kernel<<<n_blocks, X2_THREADS, X2_SMEM_BYTES, h->stream>>>(tmA2, tmA3, tmB2, tmB3, g);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
@@ -1009,7 +1039,8 @@ int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, in
   const int64_t total = rows * (cols / 4);
   if (total <= 0) return 0;
   slice_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
-      M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4);
+      M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4,
+      h->i8_impl == 1 ? 32 : 64);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1086,6 +1117,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
   KstarI8Out o;
   o.planes = reinterpret_cast<uint8_t*>(planes); o.plane_bytes = plane_bytes; o.row_bytes = row_bytes;
   o.inv_colscale = inv_colscale;
+  o.kb = (h->i8_impl == 1) ? 32 : 64;
   const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
   const int d = desc.factors[0].n_dims;
   bool ok = false;

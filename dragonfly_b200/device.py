@@ -32,6 +32,32 @@ def _dev_f64(arr, device):
 # DMMA contraction everywhere.  See dfb_set_option in include/dfb200.h.
 DEFAULT_OPTIONS = {}
 
+# A BO loop builds a fresh GP (hence a fresh handle) every iteration; the ~1.3 GB workspace of an N = 5000
+# posterior is recycled through this small per-(device, size) pool rather than through cudaMalloc /
+# cudaFree, whose cost (tens of ms, variable) would otherwise sit inside every build_posterior.
+_WORKSPACE_POOL = {}
+_WORKSPACE_POOL_DEPTH = 2
+
+
+def _take_workspace(key, dev):
+  free = _WORKSPACE_POOL.get(key)
+  if free:
+    return free.pop()
+  return torch.empty(key[1] + 256, dtype=torch.uint8, device=dev)
+
+
+def _give_workspace(key, ws):
+  if ws is None:
+    return
+  free = _WORKSPACE_POOL.setdefault(key, [])
+  if len(free) < _WORKSPACE_POOL_DEPTH:
+    free.append(ws)
+
+
+def release_workspaces():
+  """ Drops the pooled workspaces (returns the memory to torch's allocator). """
+  _WORKSPACE_POOL.clear()
+
 
 class DevicePosterior(object):
   """ One handle + workspace.  Immutable once built (GP objects replace, never mutate, it), so
@@ -45,7 +71,8 @@ class DevicePosterior(object):
     _lib.check(self.lib.dfb_create(C.byref(hp), self.device.index), 'dfb_create')
     self.h = hp
     nbytes = self.lib.dfb_workspace_bytes(self.n_max, 0, int(chunk))
-    self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+    self._pool_key = (self.device.index, int(nbytes))
+    self.workspace = _take_workspace(self._pool_key, self.device)
     ptr = (self.workspace.data_ptr() + 255) // 256 * 256
     with torch.cuda.device(self.device):
       stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -65,6 +92,8 @@ class DevicePosterior(object):
         torch.cuda.synchronize(self.device)
         self.lib.dfb_destroy(self.h)
         self.h = None
+        _give_workspace(self._pool_key, self.workspace)
+        self.workspace = None
     except Exception:  # pylint: disable=broad-except
       pass
 

@@ -507,11 +507,12 @@ def test_tma_kernel_matches_cp_async_kernel(B):
 
 
 # ---- the int8-slice tcgen05 contraction (score_impl 1 / auto) ------------------------------------------------
-def _post_pair(B, kern, X, Y, mean_const, noise_var, chunk=0):
+def _post_pair(B, kern, X, Y, mean_const, noise_var, chunk=0, i8_impl=0):
   posts = []
   for impl in (0, 1):
     post = B.device.DevicePosterior(len(X), chunk=chunk)
     post.set_option('score_impl', impl)
+    post.set_option('i8_impl', i8_impl)
     post.set_kernel(B.kernel.build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
     post.set_train(X, np.asarray(Y) - mean_const)
     info, _ = post.build(noise_var)
@@ -535,8 +536,9 @@ def _i8_kernels(B):
   }
 
 
+@pytest.mark.parametrize('i8_impl', [0, 1])
 @pytest.mark.parametrize('name', ['se', 'matern05', 'matern15', 'matern25', 'additive', 'mf_product'])
-def test_i8_sigma2_within_contract(B, name):
+def test_i8_sigma2_within_contract(B, name, i8_impl):
   """ Digit-sliced tensor-core contraction vs fp64 DMMA on the same posterior: mu identical (it never
       leaves fp64), |d sigma^2| far inside the 1e-8 contract and inside the library's own a-priori
       bound, for every kernel family, over several row blocks and ragged chunks. """
@@ -545,7 +547,7 @@ def test_i8_sigma2_within_contract(B, name):
   X = rs.random_sample((1100, 6)); Y = synth_data.hartmann6(X)
   C = rs.random_sample((5000, 6))
   kern = _i8_kernels(B)[name]
-  fp, i8 = _post_pair(B, kern, X, Y, float(np.median(Y)), 0.01 * 0.7, chunk=2048)
+  fp, i8 = _post_pair(B, kern, X, Y, float(np.median(Y)), 0.01 * 0.7, chunk=2048, i8_impl=i8_impl)
   assert i8.query('i8_ready') == 1.0
   mu0, sd0 = fp.eval(C, mean_const=1.0)
   mu1, sd1 = i8.eval(C, mean_const=1.0)
@@ -554,6 +556,11 @@ def test_i8_sigma2_within_contract(B, name):
   err = np.abs(sd0 ** 2 - sd1 ** 2).max()
   assert err <= 1e-9, err
   assert err <= i8.query('i8_sigma2_bound')
+  # both tilings of the digit products compute the same exact integers: identical to the last bit
+  if i8_impl == 1:
+    _, ref = _post_pair(B, kern, X, Y, float(np.median(Y)), 0.01 * 0.7, chunk=2048, i8_impl=0)
+    _, sd_ref = ref.eval(C, mean_const=1.0)
+    close(sd1 ** 2, sd_ref ** 2, atol=1e-13)
 
 
 def test_i8_against_reference_golden(B):

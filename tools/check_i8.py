@@ -16,6 +16,7 @@ def run(n_train, n_cand, chunk=0):
     post.set_option('score_impl', impl)
     post.set_option('i8_ts', int(os.environ.get('I8_TS', '0')))
     post.set_option('i8_fuse', int(os.environ.get('I8_FUSE', '1')))
+    post.set_option('i8_impl', int(os.environ.get('I8_IMPL', '0')))
     post.set_kernel(desc)
     post.set_train(w['X'], w['Y'] - w['mean_const'])
     info, lml = post.build(w['noise_var'])
