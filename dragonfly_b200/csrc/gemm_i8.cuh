@@ -56,7 +56,6 @@ struct ScoreI8Args {
   int64_t ld_partial;
   const double* rowscale;   // 2^E_i per row of W
   double colscale;          // 2^F
-  int dbg;                  // experiments only (DFB200_I8_DBG): 1 = no TMA traffic, 2 = no MMAs
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,

@@ -997,7 +997,6 @@ int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMa
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = h->i8_cb_group;
-  g.dbg = 0;
   return launch_score_i8(h, tmA, tmB, g);
 }
 
@@ -1008,12 +1007,13 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
   ScoreI8Args g;
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
-  static const int dbg = getenv("DFB200_I8_DBG") ? atoi(getenv("DFB200_I8_DBG")) : 0;
-  g.dbg = dbg;
-  g.cb_group = h->i8_cb_group > n_cb ? n_cb : h->i8_cb_group;
-  const int n_groups = (n_cb + g.cb_group - 1) / g.cb_group;
-  const int n_blocks = n_rb * g.cb_group * n_groups;
-  if (n_blocks <= 0) return 0;
+  g.cb_group = 0;                                   // unused: the persistent kernel deals tiles itself
+  const int n_tiles = n_rb * n_cb;
+  if (n_tiles <= 0) return 0;
+  static int n_sm[64] = {0};                        // one CTA per SM (201 KB of shared memory each)
+  if (n_sm[h->device & 63] == 0)
+    DFB_CUDA_OK(cudaDeviceGetAttribute(&n_sm[h->device & 63], cudaDevAttrMultiProcessorCount, h->device));
+  const int n_blocks = n_tiles < n_sm[h->device & 63] ? n_tiles : n_sm[h->device & 63];
   if (!g_i8x2_attr) {
     DFB_CUDA_OK(cudaFuncSetAttribute(score_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)X2_SMEM_BYTES));
