@@ -293,6 +293,7 @@ def run_ours(args):
   used_i8 = bool(gp._post.query('last_used_i8'))
   shortlist = int(gp._post.query('last_shortlist'))
   i8_bound = gp._post.query('i8_sigma2_bound')
+  i8_impl = int(gp._post.query('i8_impl'))
   del gp
   # the same step with the int8 path disabled: pure fp64 DMMA contraction, for reference
   device.DEFAULT_OPTIONS['score_impl'] = 0
@@ -323,34 +324,42 @@ def run_ours(args):
     tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
     if os.path.exists(tpath):
       try:
-        traffic = json.load(open(tpath)).get('dram_bytes_per_launch_i8' if used_i8 else 'dram_bytes_per_launch')
+        traffic = json.load(open(tpath)).get(('dram_bytes_per_launch_i8x2' if i8_impl == 1 else 'dram_bytes_per_launch_i8')
+                                             if used_i8 else 'dram_bytes_per_launch')
       except Exception:  # pylint: disable=broad-except
         traffic = None
     share = {kname: prof[kname][0] / max(sum(p[0] for p in prof.values()), 1e-9) for kname in prof}
     if used_i8:
-      # dominant kernel: score_i8_kernel (+ its digit-slicing pre-pass, timed together).  Algorithmic
-      # work: 21 int8 digit products per fp64 multiply-add of the triangular contraction.
+      # dominant kernel: the tcgen05 int8 contraction (the digit planes of K_* are emitted by the K_*
+      # kernel, those of W once per build).  Algorithmic work: 21 int8 digit products per fp64
+      # multiply-add of the triangular contraction.
       ops_per_cand = 21.0 * flops_per_cand
       achieved = gemm_cands * ops_per_cand / (gemm_ms * 1e-3) * 1e-12
       # int8 tensor peak: MEASURED_PEAKS.json has no int8 figure, so the denominator is the measured
       # tcgen05.mma kind::i8 issue rate of tools/ubench_i8.cu on this pool's B200
-      # (profiles/r01_ubench_tcgen05_i8.txt): 4577 TOP/s for N >= 128; 2777 TOP/s for the N = 64 shape
-      # that six TMEM accumulators force on this kernel.
+      # (profiles/r01_ubench_tcgen05_i8.txt): 4577 TOP/s for N >= 128 (2777 TOP/s for N = 64).
       peak, peak_n64 = 4577.2, 2777.1
+      if i8_impl == 1:
+        kname = ('score_i8x2_kernel (persistent, one CTA per SM; tcgen05.mma kind::i8 M128 N128 K32 / UTCIMMA, four '
+                 'int32 accumulators = all 512 TMEM columns, two passes per 128x128 tile, 4-stage TMA ring): '
+                 'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2')
+      else:
+        kname = ('score_i8_kernel (tcgen05.mma kind::i8 M128 N64 K32, six TMEM accumulators, TMA ring): '
+                 'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2')
       roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TOP/s (int8)',
-        'frac': achieved / peak, 'frac_of_shape_limited_peak': achieved / peak_n64, 'traffic': traffic,
-        'kernel': 'score_i8_kernel (tcgen05.mma kind::i8 / UTCIMMA, TMEM accumulators, TMA ring), digit planes '
-                  'emitted by the K_* kernel: V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2',
+        'frac': achieved / peak, 'traffic': traffic, 'kernel': kname,
         'ops_per_candidate': ops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
         'launches_timed': int(gemm_launches),
-        'peak_source': 'measured tcgen05 kind::i8 issue rate, M128 N256 K32, tools/ubench_i8.cu on this pool '
+        'peak_source': 'measured tcgen05 kind::i8 issue rate, M128 N128/N256 K32, tools/ubench_i8.cu on this pool '
                        '(profiles/r01_ubench_tcgen05_i8.txt); MEASURED_PEAKS.json bf16 burst = %s TF/s for '
                        'comparison' % peaks.get('bf16_tflops', 'n/a'),
         'fp64_equivalent_tflops': fp64_equiv,
         'fp64_equivalent_vs_cublas_dgemm': fp64_equiv / dgemm_peak if dgemm_peak > 0 else None,
         'cublas_dgemm_tflops_live': dgemm_peak, 'share_of_scoring': share,
         'i8_sigma2_error_bound': i8_bound, 'argmax_shortlist_rescored_fp64': shortlist}
+      if i8_impl == 0:
+        roofline['frac_of_shape_limited_peak'] = achieved / peak_n64
     else:
       roofline = {
         'bound': 'tensor', 'achieved': fp64_equiv, 'peak': dgemm_peak, 'unit': 'TFLOP/s',

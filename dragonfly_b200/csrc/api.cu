@@ -805,6 +805,7 @@ int dfb_query(dfb_handle* h, const char* name, double* out) {
   if (strcmp(name, "last_used_i8") == 0) { *out = (double)h->last_used_i8; return 0; }
   if (strcmp(name, "last_shortlist") == 0) { *out = (double)h->last_shortlist; return 0; }
   if (strcmp(name, "i8_ready") == 0) { *out = h->i8_ready ? 1.0 : 0.0; return 0; }
+  if (strcmp(name, "i8_impl") == 0) { *out = (double)h->i8_impl; return 0; }
   set_error("unknown query '%s'", name);
   return -1;
 }

@@ -2,6 +2,7 @@
 // the diagonal-block Cholesky/inverse, small vector kernels and the acquisition + arg-max.
 // sm_100a only.  Reference paths are relative to the reference tree (dragonfly-opt 0.1.7).
 #include "kernels.cuh"
+#include "exp_nonpos.h"
 #include "gemm_tma.cuh"
 #include "gemm_i8.cuh"
 #include "gemm_i8x2.cuh"
@@ -14,7 +15,7 @@ namespace dfb {
 __device__ __forceinline__ double base_kernel_value(const dfb_factor_desc& f, double d2) {
   if (f.kind == DFB_BASE_SE) {
     // scale * np.exp(-dist_sq / 2)                                        kernel.py:176
-    return __dmul_rn(f.scale, exp(__dmul_rn(d2, -0.5)));
+    return __dmul_rn(f.scale, dfb_exp_nonpos(__dmul_rn(d2, -0.5)));
   }
   // Matern: dist = sqrt(D2); kernel.py:259-270, 292-299
   const double dist = sqrt(d2);
@@ -30,7 +31,7 @@ __device__ __forceinline__ double base_kernel_value(const dfb_factor_desc& f, do
     else pw = pow(mm, (double)e);
     u = __dadd_rn(u, __dmul_rn(f.coeffs[i], pw));
   }
-  const double w = __dmul_rn(f.gamma_ratio, exp(__dmul_rn(-f.s2, dist)));
+  const double w = __dmul_rn(f.gamma_ratio, dfb_exp_nonpos(__dmul_rn(-f.s2, dist)));
   u = __dmul_rn(u, w);
   return __dmul_rn(f.scale, u);
 }
@@ -242,8 +243,8 @@ constexpr int KF_CANDS = KF_R * KF_WARPS;
 
 template <int KIND, int P>
 __device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, double d2) {
-  if (KIND == DFB_BASE_SE) return __dmul_rn(f.scale, exp(__dmul_rn(d2, -0.5)));
-  const double dist = sqrt(d2);
+  if (KIND == DFB_BASE_SE) return __dmul_rn(f.scale, dfb_exp_nonpos(__dmul_rn(d2, -0.5)));
+  const double dist = dfb_sqrt_nonneg(d2);
   const double mm = __dmul_rn(f.s8, dist);
   double u;
   if (P == 0) {
@@ -256,7 +257,7 @@ __device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, doub
     u = __dadd_rn(u, __dmul_rn(f.coeffs[1], mm));
     u = __dadd_rn(u, __dmul_rn(f.coeffs[2], 1.0));
   }
-  const double w = __dmul_rn(f.gamma_ratio, exp(__dmul_rn(-f.s2, dist)));
+  const double w = __dmul_rn(f.gamma_ratio, dfb_exp_nonpos(__dmul_rn(-f.s2, dist)));
   return __dmul_rn(f.scale, __dmul_rn(u, w));
 }
 
@@ -388,22 +389,39 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
         if (I8OUT) {
           // exact digit expansion of v * 2^-F (0 <= v * 2^-F < 1/2, so every digit fits int8 without
           // clamping; see slice_i8_kernel); four columns packed per 32-bit store
-          double x[4];
+          // x = hi 2^-21 + lo 2^-42 with hi = rint(x 2^21), lo = rint((x 2^21 - hi) 2^21), both read off the
+          // low mantissa word of (value + 1.5 * 2^52); each 21-bit half then splits into three balanced
+          // 7-bit digits with 32-bit integer shifts.
+          const double MAGIC = 6755399441055744.0;
+          int hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) x[e] = v[e] * i8o.inv_colscale;
+          for (int e = 0; e < 4; e++) {
+            const double x = v[e] * i8o.inv_colscale;
+            const double t1 = fma(x, 0x1p21, MAGIC);
+            hi[e] = __double2loint(t1);
+            const double rem = fma(x, 0x1p21, -(t1 - MAGIC));       // exact, |rem| <= 1/2
+            lo[e] = __double2loint(fma(rem, 0x1p21, MAGIC));
+          }
           uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 / i8o.kb) * (2 * i8o.kb) + (j0 % i8o.kb);
+          uint32_t pack[I8_S];
 #pragma unroll
-          for (int sd = 0; sd < I8_S; sd++) {
-            uint32_t pack = 0;
+          for (int hsel = 0; hsel < 2; hsel++) {
+            int a1[4], a2[4], a3[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              const double y = x[e] * 128.0;
-              const double a = rint(y);
-              x[e] = y - a;
-              pack |= ((uint32_t)((int)a) & 0xffu) << (8 * e);
+              const int w = hsel ? lo[e] : hi[e];
+              a1[e] = (w + 8192) >> 14;
+              const int r1 = w - (a1[e] << 14);
+              a2[e] = (r1 + 64) >> 7;
+              a3[e] = r1 - (a2[e] << 7);
             }
-            *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) = pack;
+            pack[3 * hsel + 0] = __byte_perm(__byte_perm(a1[0], a1[1], 0x0040), __byte_perm(a1[2], a1[3], 0x0040), 0x5410);
+            pack[3 * hsel + 1] = __byte_perm(__byte_perm(a2[0], a2[1], 0x0040), __byte_perm(a2[2], a2[3], 0x0040), 0x5410);
+            pack[3 * hsel + 2] = __byte_perm(__byte_perm(a3[0], a3[1], 0x0040), __byte_perm(a3[2], a3[3], 0x0040), 0x5410);
           }
+#pragma unroll
+          for (int sd = 0; sd < I8_S; sd++)
+            *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) = pack[sd];
         } else {
           double2 lo, hi;
           lo.x = v[0]; lo.y = v[1]; hi.x = v[2]; hi.y = v[3];

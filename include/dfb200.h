@@ -212,15 +212,16 @@ int64_t dfb_launch_count(dfb_handle* h);
  *                     in fp64 the shortlist of candidates that could be the arg-max, so the returned index
  *                     and score are the fp64 ones.  The int8 path is skipped when its a-priori error bound
  *                     (query "i8_sigma2_bound") exceeds 1e-9 max(1, k(x,x)) or n < 1024.
- *  "i8_impl"    : which tcgen05 kernel the int8 path uses: 1 (default) = two passes of M128 N128 K32 MMAs over
- *                 a 128 x 128 tile (gemm_i8x2.cuh), 0 = one pass of N = 64 MMAs over a 128 x 64 tile
+ *  "i8_impl"    : which tcgen05 kernel the int8 path uses: 1 (default) = persistent kernel, two passes of M128
+ *                 N128 K32 MMAs over each 128 x 128 tile (gemm_i8x2.cuh), 0 = one pass of N = 64 MMAs over a 128 x 64 tile
  *                 (gemm_i8.cuh).  Same digit products, same error bound; switching re-slices W (the digit
  *                 planes' interleave granularity differs).
  *  "i8_fuse"    : 1 (default) = the K_* kernel emits the int8 digit planes directly, 0 = via an fp64 K_* buffer.
  *  "i8_ts"      : i8_impl 0 only: 1 = stage W's digits in tensor memory (tcgen05.cp), default 0.
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
-/* Diagnostics: "i8_sigma2_bound", "i8_ready", "last_used_i8", "last_shortlist" (-1 = overflow -> fp64 pass). */
+/* Diagnostics: "i8_sigma2_bound", "i8_ready", "i8_impl", "last_used_i8", "last_shortlist" (-1 = overflow ->
+ * fp64 pass). */
 int dfb_query(dfb_handle* h, const char* name, double* out);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
