@@ -239,7 +239,11 @@ kstar_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_train_coo
 // instructions per entry interpreting the descriptor: profiles/r01_kstar_ncu_summary.txt.)
 constexpr int KF_R = 2;
 constexpr int KF_WARPS = 4;
-constexpr int KF_CANDS = KF_R * KF_WARPS;
+// Two warps share a candidate pair, each over half of the training points: 2.76 waves of half-length
+// warp tasks per 6528-candidate chunk instead of 1.38 waves of full-length ones (the second wave of
+// which left 60 % of the machine idle); the two halves of mu are added in shared memory, in fixed order.
+constexpr int KF_SPLIT = 2;
+constexpr int KF_CANDS = KF_R * KF_WARPS / KF_SPLIT;
 
 template <int KIND, int P>
 __device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, double d2) {
@@ -297,8 +301,13 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
   const dfb_factor_desc f = fsh;
   const double pre = scal_sh[0], post = scal_sh[1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t cand0 = (int64_t)blockIdx.x * KF_CANDS + warp * KF_R;
-  if (cand0 >= m_rows) return;
+  const int part = warp % KF_SPLIT;
+  const int64_t cand0 = (int64_t)blockIdx.x * KF_CANDS + (warp / KF_SPLIT) * KF_R;
+  const bool active = cand0 < m_rows;
+  const int64_t span = ((n_write + 128 * KF_SPLIT - 1) / (128 * KF_SPLIT)) * 128;
+  const int64_t j_lo = active ? part * span : n_write;
+  const int64_t j_hi = (j_lo + span < n_write) ? j_lo + span : n_write;
+  __shared__ double mu_sh[KF_WARPS][KF_R];
 
   double xc[KF_R][D], nc[KF_R];
 #pragma unroll
@@ -315,7 +324,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
     }
     nc[r] = s;
   }
-  if (kss_out != nullptr && lane == 0) {
+  if (kss_out != nullptr && lane == 0 && part == 0 && active) {
 #pragma unroll
     for (int r = 0; r < KF_R; r++) {
       const int64_t cand = cand0 + r;
@@ -337,7 +346,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
   // each lane owns 4 consecutive training points per step (128 per warp step): 16-byte loads of the
   // SoA coordinates, 16-byte stores of the fp64 rows or one packed 32-bit store per digit plane, and
   // 4 x KF_R independent exp/sqrt chains in flight
-  for (int64_t j0 = 4 * lane; j0 < n_write; j0 += 128) {
+  for (int64_t j0 = j_lo + 4 * lane; j0 < j_hi; j0 += 128) {
     double kv[KF_R][4];
     double aj[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -438,8 +447,18 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
     for (int r = 0; r < KF_R; r++) {
       double s = mu_acc[r];
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const int64_t cand = cand0 + r;
-      if (lane == 0 && cand < m) mu[cand] = mean_const + s;
+      if (lane == 0) mu_sh[warp][r] = s;
+    }
+    __syncthreads();
+    if (part == 0 && lane == 0 && active) {
+#pragma unroll
+      for (int r = 0; r < KF_R; r++) {
+        double s = mu_sh[warp][r];
+#pragma unroll
+        for (int q = 1; q < KF_SPLIT; q++) s += mu_sh[warp + q][r];
+        const int64_t cand = cand0 + r;
+        if (cand < m) mu[cand] = mean_const + s;
+      }
     }
   }
 }
