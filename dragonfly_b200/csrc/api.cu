@@ -246,7 +246,9 @@ static int prepare_i8(dfb_handle* h) {
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
   // pair-interleaved digit planes: 3 planes of rows x (2 * npad) bytes
   DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, 2 * npad * npad, 2 * npad));
-  if (h->i8_impl == 1) {
+  if (h->i8_impl >= 1) {
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK2h, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK3h, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 3));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW2, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW3, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 3));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK2, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 128, 1));
@@ -351,7 +353,10 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
         if (!fused_digits)
           DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
                                   2 * h->chunk * npad, 2 * npad));
-        if (h->i8_impl == 1)
+        if (h->i8_impl == 2)
+          DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmK2h, h->tmK3h, nb, (int)(m_rows / TILE), (int)npad,
+                                         h->partial, Mc, h->rowscale, colscale));
+        else if (h->i8_impl == 1)
           DFB_TRY(launch_score_i8x2_args(h, h->tmW2, h->tmW3, h->tmK2, h->tmK3, nb, (int)(m_rows / TILE), (int)npad,
                                          h->partial, Mc, h->rowscale, colscale));
         else
@@ -829,7 +834,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {
-    if (value != 0 && value != 1) { set_error("i8_impl must be 0 (N=64, one pass) or 1 (N=128, two passes)"); return -1; }
+    if (value < 0 || value > 2) { set_error("i8_impl must be 0 (N=64, one pass), 1 (N=128, two passes) or 2 (CTA pairs)"); return -1; }
     h->i8_impl = (int)value;
     if (h->i8_ready) { DFB_CUDA_OK(cudaSetDevice(h->device)); DFB_TRY(prepare_i8(h)); }   // re-slice W in the new layout
     return 0;

@@ -56,6 +56,7 @@ struct ScoreI8Args {
   int64_t ld_partial;
   const double* rowscale;   // 2^E_i per row of W
   double colscale;          // 2^F
+  unsigned long long* timing;   // diagnostics (DFB200_I8_TIMING): per-CTA clocks the MMA thread spent waiting; else NULL
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,

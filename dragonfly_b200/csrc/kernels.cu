@@ -6,6 +6,7 @@
 #include "gemm_tma.cuh"
 #include "gemm_i8.cuh"
 #include "gemm_i8x2.cuh"
+#include "gemm_i8c2.cuh"
 
 namespace dfb {
 
@@ -1034,6 +1035,7 @@ int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMa
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = h->i8_cb_group;
+  g.timing = nullptr;
   return launch_score_i8(h, tmA, tmB, g);
 }
 
@@ -1045,6 +1047,7 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = 0;                                   // unused: the persistent kernel deals tiles itself
+  g.timing = nullptr;
   const int n_tiles = n_rb * n_cb;
   if (n_tiles <= 0) return 0;
   static int n_sm[64] = {0};                        // one CTA per SM (201 KB of shared memory each)
@@ -1059,6 +1062,52 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
   score_i8x2_kernel<<<n_blocks, X2_THREADS, X2_SMEM_BYTES, h->stream>>>(tmA2, tmA3, tmB2, tmB3, g);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static bool g_i8c2_attr = false;
+int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3,
+                           const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, int n_rb, int n_cb, int K,
+                           double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
+  ScoreI8Args g;
+  g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
+  g.rowscale = rowscale; g.colscale = colscale;
+  g.cb_group = 0;
+  const int n_tiles = ((n_rb + 1) / 2) * n_cb;      // row-block pairs x candidate tiles
+  if (n_tiles <= 0) return 0;
+  static int n_sm[64] = {0};
+  if (n_sm[h->device & 63] == 0)
+    DFB_CUDA_OK(cudaDeviceGetAttribute(&n_sm[h->device & 63], cudaDevAttrMultiProcessorCount, h->device));
+  const int max_clusters = n_sm[h->device & 63] / 2;                 // one CTA per SM, two SMs per cluster
+  const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+  if (!g_i8c2_attr) {
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)C2_SMEM_BYTES));
+    g_i8c2_attr = true;
+  }
+  // DFB200_I8_TIMING=1: where the MMA-issuing thread waits (diagnostics; synchronises after every launch)
+  static const bool timing = getenv("DFB200_I8_TIMING") != nullptr;
+  static unsigned long long* tbuf = nullptr;
+  g.timing = nullptr;
+  if (timing) {
+    if (tbuf == nullptr) DFB_CUDA_OK(cudaMalloc(&tbuf, sizeof(unsigned long long) * 4 * 128));
+    g.timing = tbuf;
+  }
+  score_i8c2_kernel<<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  if (timing) {
+    static int printed = 0;
+    unsigned long long host[4 * 128];
+    DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    DFB_CUDA_OK(cudaMemcpy(host, tbuf, sizeof(unsigned long long) * 4 * n_clusters, cudaMemcpyDeviceToHost));
+    double a[4] = {0, 0, 0, 0};
+    for (int c = 0; c < n_clusters; c++) for (int q = 0; q < 4; q++) a[q] += (double)host[4 * c + q] / n_clusters;
+    if (printed++ < 6)
+      fprintf(stderr, "[i8c2 timing] clusters %d  MMA thread clocks: total %.0f  wait full %.0f (%.1f%%)  drain %.0f (%.1f%%)  "
+              "epilogue %.0f (%.1f%%)\n", n_clusters, a[3], a[0], 100 * a[0] / a[3], a[1], 100 * a[1] / a[3], a[2],
+              100 * a[2] / a[3]);
+  }
   return 0;
 }
 
@@ -1077,7 +1126,7 @@ int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, in
   if (total <= 0) return 0;
   slice_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
       M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4,
-      h->i8_impl == 1 ? 32 : 64);
+      h->i8_impl >= 1 ? 32 : 64);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1154,7 +1203,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
   KstarI8Out o;
   o.planes = reinterpret_cast<uint8_t*>(planes); o.plane_bytes = plane_bytes; o.row_bytes = row_bytes;
   o.inv_colscale = inv_colscale;
-  o.kb = (h->i8_impl == 1) ? 32 : 64;
+  o.kb = (h->i8_impl >= 1) ? 32 : 64;
   const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
   const int d = desc.factors[0].n_dims;
   bool ok = false;

@@ -507,12 +507,13 @@ def test_tma_kernel_matches_cp_async_kernel(B):
 
 
 # ---- the int8-slice tcgen05 contraction (score_impl 1 / auto) ------------------------------------------------
-def _post_pair(B, kern, X, Y, mean_const, noise_var, chunk=0, i8_impl=0):
+def _post_pair(B, kern, X, Y, mean_const, noise_var, chunk=0, i8_impl=None):
   posts = []
   for impl in (0, 1):
     post = B.device.DevicePosterior(len(X), chunk=chunk)
     post.set_option('score_impl', impl)
-    post.set_option('i8_impl', i8_impl)
+    if i8_impl is not None:      # None: the library default (CTA-pair kernel)
+      post.set_option('i8_impl', i8_impl)
     post.set_kernel(B.kernel.build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
     post.set_train(X, np.asarray(Y) - mean_const)
     info, _ = post.build(noise_var)
@@ -536,7 +537,7 @@ def _i8_kernels(B):
   }
 
 
-@pytest.mark.parametrize('i8_impl', [0, 1])
+@pytest.mark.parametrize('i8_impl', [0, 1, 2])
 @pytest.mark.parametrize('name', ['se', 'matern05', 'matern15', 'matern25', 'additive', 'mf_product'])
 def test_i8_sigma2_within_contract(B, name, i8_impl):
   """ Digit-sliced tensor-core contraction vs fp64 DMMA on the same posterior: mu identical (it never
@@ -557,7 +558,7 @@ def test_i8_sigma2_within_contract(B, name, i8_impl):
   assert err <= 1e-9, err
   assert err <= i8.query('i8_sigma2_bound')
   # both tilings of the digit products compute the same exact integers: identical to the last bit
-  if i8_impl == 1:
+  if i8_impl >= 1:
     _, ref = _post_pair(B, kern, X, Y, float(np.median(Y)), 0.01 * 0.7, chunk=2048, i8_impl=0)
     _, sd_ref = ref.eval(C, mean_const=1.0)
     close(sd1 ** 2, sd_ref ** 2, atol=1e-13)
