@@ -237,6 +237,29 @@ static int prof_end(dfb_handle* h, int cls, double units) {
   return 0;
 }
 
+// A-priori estimate of the int8-slice path's absolute sigma^2 error for the active kernel.  The error of
+// one entry of v = L^-1 k_* is a sum over k of digit-truncation and dropped-product terms of size
+// 2^-q * rowscale_i * colscale with effectively random signs (q = 43 for six radix-128 digits, 40 for five
+// radix-256 digits), so it grows like sqrt(n); d(sigma^2) = 2 sum_i v_i dv_i <= 2 sqrt(k(x,x)) max_i |dv_i|
+// in the worst alignment.  Measured maxima (tools/check_i8.py, N = 100 .. 5000, 13056 candidates) sit at
+// 0.55x (radix 128) and 0.87x (radix 256) of rowscale_max * sqrt(n) * colscale * 2^-q * sqrt(k(x,x)); the
+// constant 8 leaves a >= 9x margin over those.
+static double i8_colscale(const dfb_kernel_desc& desc) {
+  int e = 0;
+  frexp(desc.kss * (1.0 + 1e-9), &e);
+  return ldexp(1.0, e + 1);
+}
+static double i8_sigma2_bound(const dfb_handle* h, const dfb_kernel_desc& desc) {
+  return 8.0 * h->i8_rowscale_max * sqrt((double)h->n) * i8_colscale(desc) *
+         ldexp(1.0, h->i8_radix256 ? -40 : -43) * sqrt(desc.kss);
+}
+static const double I8_BOUND_LIMIT = 5e-9;     // half of the 1e-8 sigma^2 contract, times max(1, k(x,x))
+static bool i8_usable(const dfb_handle* h, const dfb_kernel_desc& desc) {
+  if (!h->i8_ready || !(desc.kss > 0.0)) return false;
+  const double b = i8_sigma2_bound(h, desc);
+  return b <= I8_BOUND_LIMIT * (desc.kss > 1.0 ? desc.kss : 1.0);
+}
+
 // Digit planes of W = L^-1 for the tcgen05 path + the tensor maps of both operands.
 static int prepare_i8(dfb_handle* h) {
   const int64_t npad = h->npad;
@@ -244,6 +267,17 @@ static int prepare_i8(dfb_handle* h) {
   DFB_TRY(launch_vec_max(h, h->rowscale, h->n, h->red + 4));
   DFB_CUDA_OK(cudaMemcpyAsync(&h->i8_rowscale_max, h->red + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  // Digit scheme of the CTA-pair kernel: five radix-256 digits (15 products) when the a-priori bound of
+  // that coarser expansion passes for the training kernel, else six radix-128 digits (21 products).  The
+  // radix-256 groups also need int32 headroom: 5 K 2^14 < 2^31.
+  h->i8_radix256 = 0;
+  if (h->i8_impl == 2 && h->i8_radix_opt != 0 && npad <= 24576) {
+    h->i8_radix256 = 1;
+    const dfb_kernel_desc& dtr = h->desc_tr;
+    if (h->i8_radix_opt < 0 && dtr.kss > 0.0 &&
+        i8_sigma2_bound(h, dtr) > I8_BOUND_LIMIT * (dtr.kss > 1.0 ? dtr.kss : 1.0))
+      h->i8_radix256 = 0;
+  }
   // pair-interleaved digit planes: 3 planes of rows x (2 * npad) bytes
   DFB_TRY(launch_slice_i8(h, h->W, npad, npad, npad, h->rowinv, 0.0, h->Wi8, 2 * npad * npad, 2 * npad));
   if (h->i8_impl >= 1) {
@@ -266,23 +300,6 @@ struct ChunkOut {
 };
 
 // Scores m candidates chunk by chunk: K_* rows + mu -> |L^-1 k_*|^2 -> sd / acquisition / arg-max.
-// A-priori bound on the int8-slice path's absolute sigma^2 error for the active kernel: digits carry
-// 42 bits below the row / column scales 2^E_i, 2^F; the constant is calibrated on the measured
-// worst cases (tools/check_i8.py, tests/test_gpu_parity.py::test_i8_*) with a >= 8x safety factor.
-static double i8_colscale(const dfb_kernel_desc& desc) {
-  int e = 0;
-  frexp(desc.kss * (1.0 + 1e-9), &e);
-  return ldexp(1.0, e + 1);
-}
-static double i8_sigma2_bound(const dfb_handle* h, const dfb_kernel_desc& desc) {
-  return 64.0 * h->i8_rowscale_max * i8_colscale(desc) * ldexp(1.0, -43) * sqrt(desc.kss);
-}
-static bool i8_usable(const dfb_handle* h, const dfb_kernel_desc& desc) {
-  if (!h->i8_ready || !(desc.kss > 0.0)) return false;
-  const double b = i8_sigma2_bound(h, desc);
-  return b <= 1e-9 * (desc.kss > 1.0 ? desc.kss : 1.0);
-}
-
 struct ChunkMode {
   bool want_std, do_argmax;
   bool use_i8;                 // int8-slice tcgen05 contraction instead of fp64 DMMA
@@ -640,15 +657,22 @@ int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, i
   if (fast) {
     // Pass 1: int8-slice scoring of everything, collecting the shortlist of candidates that could be
     // the exact arg-max.  Natural score scale: UCB |mu| + beta sigma ~ (1 + beta) sqrt(kss); EI/TTEI
-    // <= sigma ~ sqrt(kss); PI <= 1.  The fast path's score error is <= sens * B2 / (2 sigma) with
-    // sigma >= sd_min, far below margin = 1e-6 * scale for every acquisition (DESIGN.md, int8 path).
+    // <= sigma ~ sqrt(kss); PI <= 1.  The shortlist margin is the larger of 1e-6 of that scale and the
+    // a-priori score error of the int8 pass (below).
     const double sk = sqrt(desc.kss);
     double scale = sk;
     if (acq->kind == DFB_ACQ_UCB) scale = (1.0 + fabs(acq->beta)) * sk + fabs(mean_const);
     else if (acq->kind == DFB_ACQ_PI) scale = 1.0;
     md.collect = true;
-    md.margin = 1e-6 * scale;
     md.sd_min = sqrt(1e-3 * desc.kss);
+    // every candidate with sigma >= sd_min has |score_int8 - score_fp64| <= sens * B2 / (2 sd_min), where
+    // sens bounds |d score / d sigma|: UCB |beta|; EI, TTEI <= 1 (phi(z) <= 0.4); PI |z phi(z)| / sigma
+    // <= 0.25 / sd_min.  Both the leader and a challenger can be off by that much, hence the factor 2.
+    double sens = 1.0;
+    if (acq->kind == DFB_ACQ_UCB) sens = fabs(acq->beta);
+    else if (acq->kind == DFB_ACQ_PI) sens = 0.25 / md.sd_min;
+    const double rigorous = 2.0 * sens * i8_sigma2_bound(h, desc) / (2.0 * md.sd_min);
+    md.margin = 1e-6 * scale > rigorous ? 1e-6 * scale : rigorous;
     DFB_CUDA_OK(cudaMemsetAsync(h->list_count, 0, sizeof(int) * 4, h->stream));
     DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, md));
     int count = 0;
@@ -811,6 +835,7 @@ int dfb_query(dfb_handle* h, const char* name, double* out) {
   if (strcmp(name, "last_shortlist") == 0) { *out = (double)h->last_shortlist; return 0; }
   if (strcmp(name, "i8_ready") == 0) { *out = h->i8_ready ? 1.0 : 0.0; return 0; }
   if (strcmp(name, "i8_impl") == 0) { *out = (double)h->i8_impl; return 0; }
+  if (strcmp(name, "i8_radix256") == 0) { *out = (double)h->i8_radix256; return 0; }
   set_error("unknown query '%s'", name);
   return -1;
 }
@@ -837,6 +862,12 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
     if (value < 0 || value > 2) { set_error("i8_impl must be 0 (N=64, one pass), 1 (N=128, two passes) or 2 (CTA pairs)"); return -1; }
     h->i8_impl = (int)value;
     if (h->i8_ready) { DFB_CUDA_OK(cudaSetDevice(h->device)); DFB_TRY(prepare_i8(h)); }   // re-slice W in the new layout
+    return 0;
+  }
+  if (strcmp(name, "i8_radix") == 0) {
+    if (value < -1 || value > 1) { set_error("i8_radix must be -1 (auto), 0 (radix 128) or 1 (radix 256)"); return -1; }
+    h->i8_radix_opt = (int)value;
+    if (h->i8_ready) { DFB_CUDA_OK(cudaSetDevice(h->device)); DFB_TRY(prepare_i8(h)); }
     return 0;
   }
   if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }

@@ -136,6 +136,8 @@ struct dfb_handle {
   CUtensorMap tmWi8, tmKi8;
   int i8_impl = 2;            // 0 = one pass, N = 64 MMAs (gemm_i8.cuh); 1 = two passes, N = 128 (gemm_i8x2.cuh);
                               // 2 = as 1 with CTA-pair M256 MMAs (gemm_i8c2.cuh)
+  int i8_radix_opt = -1;      // digit scheme of the pair kernel: -1 auto (radix 256 when its bound allows), 0 = 128, 1 = 256
+  int i8_radix256 = 0;        // scheme in use for the current posterior (set by prepare_i8)
   CUtensorMap tmK2h, tmK3h;             // 64-row boxes of the K_* digit planes (i8_impl 2: half tiles per CTA)
   CUtensorMap tmW2, tmW3, tmK2, tmK3;   // 2- and 3-plane boxes of the digit planes (i8_impl 1)
 

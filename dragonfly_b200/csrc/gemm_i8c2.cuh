@@ -15,6 +15,16 @@
 // transaction bytes of both land on the LEADER's full barrier (cta_group::2 TMA form).  The leader's
 // single MMA thread issues for the pair and commits to both CTAs' barriers (multicast commit); the
 // epilogue warps of both CTAs report "columns drained" on the leader's barriers with remote arrives.
+// Digits: with R256 the kernel uses FIVE radix-256 digits per operand (top digit 7 bits, four balanced bytes:
+// digits_radix256 in kernels.cu) instead of six radix-128 digits: x ~ sum_s a_s 2^-(8s-1).  The products
+// a_s b_t with s + t <= 6 are kept (15 MMAs per K = 32 block instead of 21; the dropped s + t = 7 terms
+// are ~2^-40 of the operands' scale, the same order as the digit truncation), grouped by d = s + t with
+// weight 2^-(8d-2).  Pass A accumulates groups 3..6 (14 products, all digits) in the four accumulators,
+// pass B group 2 (the single leading product) in accumulator 0.  int32 headroom: 5 K 2^14 < 2^31 needs
+// K <= 26214 (api.cu refuses the path beyond npad = 24576).  The tensor pipe -- and at the 1 kW power cap
+// the whole step -- scales with the MMA count, so this is a straight 29 % cut of the dominant cost for
+// an error that stays ~30x inside the 1e-8 contract at N = 5000.  R256 = false keeps the six radix-128 digits
+// and 21 products of gemm_i8x2.cuh (12x more accurate): api.cu picks per posterior from the a-priori bound.
 // The k-range is the triangular range of the lower row block of the pair (the upper one's digits are
 // zero there).  A phantom row block (odd n_rb) reads zeros through TMA's out-of-bounds fill.
 #pragma once
@@ -26,6 +36,7 @@
 namespace dfb {
 
 constexpr int C2_STAGES = 6;
+constexpr int C2_DIGITS = 5;                           // radix-256 digits per operand
 constexpr int C2_A_SUB = X2_BM * 2 * X2_BK;             // 8192 B: 128 rows x 64 B
 constexpr int C2_B_SUB = (X2_BN / 2) * 2 * X2_BK;       // 4096 B:  64 rows x 64 B
 constexpr int C2_STAGE_BYTES = 3 * C2_A_SUB + 3 * C2_B_SUB;          // 36864 per CTA
@@ -106,6 +117,7 @@ __device__ __forceinline__ bool c2_tile(const ScoreI8Args& g, int j, int& rp, in
   return true;
 }
 
+template <bool R256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
 score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA3,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB3,
@@ -213,33 +225,64 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           const unsigned a_lo = ((a0 & 0x3FFFFu) >> 4) | 0x10000u;
           const unsigned b_lo = (((a0 + 3 * C2_A_SUB) & 0x3FFFFu) >> 4) | 0x10000u;
           const bool first = (it == 0) || (it == nk);
-          if (!pb) {
+          if constexpr (R256) {
+            if (!pb) {
+              // groups 3..6 -> accumulators 0..3; sub-tile index = digit-pair plane
 #pragma unroll
-            for (int d = 4; d <= 7; d++) {
-              const unsigned acc = (unsigned)((d - 4) * X2_BN);
-              bool lead = true;
+              for (int d = 3; d <= 6; d++) {
+                const unsigned acc = (unsigned)((d - 3) * X2_BN);
+                bool lead = true;
 #pragma unroll
-              for (int sa = 1; sa <= I8_S; sa++) {
-                const int tb = d - sa;
-                if (tb < 1 || tb > I8_S) continue;
-                const unsigned aoff = ((sa - 1) >> 1) * C2_A_SUB + ((sa - 1) & 1) * X2_BK;
-                const unsigned boff = ((tb - 1) >> 1) * C2_B_SUB + ((tb - 1) & 1) * X2_BK;
-                if (el) c2_umma(acc, DESC_HI | (uint64_t)(a_lo + (aoff >> 4)), DESC_HI | (uint64_t)(b_lo + (boff >> 4)),
-                        (first && lead) ? 0u : 1u);
-                lead = false;
+                for (int sa = 1; sa <= C2_DIGITS; sa++) {
+                  const int tb = d - sa;
+                  if (tb < 1 || tb > C2_DIGITS) continue;
+                  const unsigned aoff = ((sa - 1) >> 1) * C2_A_SUB + ((sa - 1) & 1) * X2_BK;
+                  const unsigned boff = ((tb - 1) >> 1) * C2_B_SUB + ((tb - 1) & 1) * X2_BK;
+                  if (el)
+                    c2_umma(acc, DESC_HI | (uint64_t)(a_lo + (aoff >> 4)), DESC_HI | (uint64_t)(b_lo + (boff >> 4)),
+                            (first && lead) ? 0u : 1u);
+                  lead = false;
+                }
+              }
+            } else {
+              // group 2 = the leading product (1, 1) -> accumulator 0; sub-tile index = K = 32 block
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                const uint64_t a1 = DESC_HI | (uint64_t)(a_lo + ((unsigned)(u * C2_A_SUB) >> 4));
+                const uint64_t b1 = DESC_HI | (uint64_t)(b_lo + ((unsigned)(u * C2_B_SUB) >> 4));
+                if (el) c2_umma(0u, a1, b1, (first && u == 0) ? 0u : 1u);
               }
             }
           } else {
+            // six radix-128 digits: groups 4..7 -> accumulators 0..3 in pass A, groups 2, 3 -> 0..1 in pass B
+            if (!pb) {
 #pragma unroll
-            for (int u = 0; u < 3; u++) {
-              const unsigned au = (unsigned)(u * C2_A_SUB), bu = (unsigned)(u * C2_B_SUB);
-              const uint64_t a1 = DESC_HI | (uint64_t)(a_lo + (au >> 4));
-              const uint64_t a2 = DESC_HI | (uint64_t)(a_lo + ((au + X2_BK) >> 4));
-              const uint64_t b1 = DESC_HI | (uint64_t)(b_lo + (bu >> 4));
-              const uint64_t b2 = DESC_HI | (uint64_t)(b_lo + ((bu + X2_BK) >> 4));
-              if (el) c2_umma(0u, a1, b1, (first && u == 0) ? 0u : 1u);
-              if (el) c2_umma((unsigned)X2_BN, a1, b2, (first && u == 0) ? 0u : 1u);
-              if (el) c2_umma((unsigned)X2_BN, a2, b1, 1u);
+              for (int d = 4; d <= 7; d++) {
+                const unsigned acc = (unsigned)((d - 4) * X2_BN);
+                bool lead = true;
+#pragma unroll
+                for (int sa = 1; sa <= I8_S; sa++) {
+                  const int tb = d - sa;
+                  if (tb < 1 || tb > I8_S) continue;
+                  const unsigned aoff = ((sa - 1) >> 1) * C2_A_SUB + ((sa - 1) & 1) * X2_BK;
+                  const unsigned boff = ((tb - 1) >> 1) * C2_B_SUB + ((tb - 1) & 1) * X2_BK;
+                  if (el) c2_umma(acc, DESC_HI | (uint64_t)(a_lo + (aoff >> 4)), DESC_HI | (uint64_t)(b_lo + (boff >> 4)),
+                          (first && lead) ? 0u : 1u);
+                  lead = false;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 3; u++) {
+                const unsigned au = (unsigned)(u * C2_A_SUB), bu = (unsigned)(u * C2_B_SUB);
+                const uint64_t a1 = DESC_HI | (uint64_t)(a_lo + (au >> 4));
+                const uint64_t a2 = DESC_HI | (uint64_t)(a_lo + ((au + X2_BK) >> 4));
+                const uint64_t b1 = DESC_HI | (uint64_t)(b_lo + (bu >> 4));
+                const uint64_t b2 = DESC_HI | (uint64_t)(b_lo + ((bu + X2_BK) >> 4));
+                if (el) c2_umma(0u, a1, b1, (first && u == 0) ? 0u : 1u);
+                if (el) c2_umma((unsigned)X2_BN, a1, b2, (first && u == 0) ? 0u : 1u);
+                if (el) c2_umma((unsigned)X2_BN, a2, b1, 1u);
+              }
             }
           }
           if (el) c2_commit(&empty_bar[s]);
@@ -289,7 +332,9 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           tmem_ld8(lane_addr + (unsigned)(3 * X2_BN + half * 64), rc[cur ^ 1]);
         }
 #pragma unroll
-        for (int j2 = 0; j2 < 8; j2++) v1[c0 + j2] = fma((double)ra[cur][j2], 0x1p-28, (double)rc[cur][j2] * 0x1p-35);
+        for (int j2 = 0; j2 < 8; j2++)
+          v1[c0 + j2] = R256 ? fma((double)ra[cur][j2], 0x1p-22, (double)rc[cur][j2] * 0x1p-30)
+                             : fma((double)ra[cur][j2], 0x1p-28, (double)rc[cur][j2] * 0x1p-35);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       if (lane == 0) c2_arrive_leader(drain_bar);
@@ -303,19 +348,21 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
 #pragma unroll
         for (int j2 = 0; j2 < 8; j2++)
-          v1[c0 + j2] += fma((double)ra[cur][j2], 0x1p-42, (double)rc[cur][j2] * 0x1p-49);
+          v1[c0 + j2] += R256 ? fma((double)ra[cur][j2], 0x1p-38, (double)rc[cur][j2] * 0x1p-46)
+                              : fma((double)ra[cur][j2], 0x1p-42, (double)rc[cur][j2] * 0x1p-49);
       }
       mbar_wait(acc2_bar, tpar);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      tmem_ld8(lane_addr + (unsigned)(0 * X2_BN + half * 64), ra[0]);
-      tmem_ld8(lane_addr + (unsigned)(1 * X2_BN + half * 64), rc[0]);
+      // radix 256: group 2 sits in accumulator 0 alone; radix 128: groups 2, 3 in accumulators 0, 1
+      tmem_ld8(lane_addr + (unsigned)(half * 64), ra[0]);
+      if (!R256) tmem_ld8(lane_addr + (unsigned)(X2_BN + half * 64), rc[0]);
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 8) {
         const int cur = (c0 >> 3) & 1;
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         if (c0 + 8 < 64) {
-          tmem_ld8(lane_addr + (unsigned)(0 * X2_BN + half * 64 + c0 + 8), ra[cur ^ 1]);
-          tmem_ld8(lane_addr + (unsigned)(1 * X2_BN + half * 64 + c0 + 8), rc[cur ^ 1]);
+          tmem_ld8(lane_addr + (unsigned)(half * 64 + c0 + 8), ra[cur ^ 1]);
+          if (!R256) tmem_ld8(lane_addr + (unsigned)(X2_BN + half * 64 + c0 + 8), rc[cur ^ 1]);
         } else {
           // last tensor-memory read of this tile has landed: the issuer may start the next tile's pass A
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -324,7 +371,8 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         double sq[8];
 #pragma unroll
         for (int j2 = 0; j2 < 8; j2++) {
-          double v = v1[c0 + j2] + fma((double)ra[cur][j2], 0x1p-14, (double)rc[cur][j2] * 0x1p-21);
+          double v = R256 ? fma((double)ra[cur][j2], 0x1p-14, v1[c0 + j2])
+                          : v1[c0 + j2] + fma((double)ra[cur][j2], 0x1p-14, (double)rc[cur][j2] * 0x1p-21);
           v *= rs;
           sq[j2] = v * v;
         }

@@ -268,12 +268,36 @@ __device__ __forceinline__ double base_value_fast(const dfb_factor_desc& f, doub
 
 // I8OUT: instead of the fp64 K_* rows, emit their six signed 7-bit digit planes (pair-interleaved layout
 // of gemm_i8.cuh) for the tcgen05 contraction -- the fp64 matrix is then never written.
+// Radix-256 digits for the CTA-pair kernel (gemm_i8c2.cuh): x (|x| <= 1/2) ~ a0 2^-7 + a1 2^-15 + a2 2^-23 +
+// a3 2^-31 + a4 2^-39, a0 in [-64, 64], a1..a4 balanced bytes in [-128, 127]; |x - sum| <= 2^-40.
+// hi = rint(x 2^15) and lo = rint((x 2^15 - hi) 2^24) are read off the low mantissa word of
+// (value + 1.5 * 2^52); the bytes then peel off with sign extension, carries rippling upwards.
+__device__ __forceinline__ void digits_radix256(double x, int (&a)[5]) {
+  const double MAGIC = 6755399441055744.0;
+  const double t1 = fma(x, 0x1p15, MAGIC);
+  int hi = __double2loint(t1);
+  const double rem = fma(x, 0x1p15, -(t1 - MAGIC));          // exact, |rem| <= 1/2
+  const int lo = __double2loint(fma(rem, 0x1p24, MAGIC));
+  a[4] = (int)(signed char)lo;
+  int r = (lo - a[4]) >> 8;
+  a[3] = (int)(signed char)r;
+  r = (r - a[3]) >> 8;
+  a[2] = (int)(signed char)r;
+  hi += (r - a[2]) >> 8;
+  a[1] = (int)(signed char)hi;
+  a[0] = (hi - a[1]) >> 8;
+}
+__device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
 struct KstarI8Out {
   uint8_t* planes;        // Ki8
   int64_t plane_bytes;    // 2 * chunk * npad
   int64_t row_bytes;      // 2 * npad
   double inv_colscale;    // 2^-F
   int kb;                 // k-values per interleave block (64 or 32)
+  int radix256;           // 1: five radix-256 digits (digits_radix256), 0: six radix-128 digits
 };
 
 template <int KIND, int P, int D, bool I8OUT>
@@ -402,6 +426,16 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
           // x = hi 2^-21 + lo 2^-42 with hi = rint(x 2^21), lo = rint((x 2^21 - hi) 2^21), both read off the
           // low mantissa word of (value + 1.5 * 2^52); each 21-bit half then splits into three balanced
           // 7-bit digits with 32-bit integer shifts.
+          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 / i8o.kb) * (2 * i8o.kb) + (j0 % i8o.kb);
+          if (i8o.radix256) {
+            int dg[4][5];
+#pragma unroll
+            for (int e = 0; e < 4; e++) digits_radix256(v[e] * i8o.inv_colscale, dg[e]);
+#pragma unroll
+            for (int sd = 0; sd < 5; sd++)
+              *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) =
+                  pack4_i8(dg[0][sd], dg[1][sd], dg[2][sd], dg[3][sd]);
+          } else {
           const double MAGIC = 6755399441055744.0;
           int hi[4], lo[4];
 #pragma unroll
@@ -412,7 +446,6 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
             const double rem = fma(x, 0x1p21, -(t1 - MAGIC));       // exact, |rem| <= 1/2
             lo[e] = __double2loint(fma(rem, 0x1p21, MAGIC));
           }
-          uint8_t* dst = i8o.planes + cand * i8o.row_bytes + (j0 / i8o.kb) * (2 * i8o.kb) + (j0 % i8o.kb);
           uint32_t pack[I8_S];
 #pragma unroll
           for (int hsel = 0; hsel < 2; hsel++) {
@@ -432,6 +465,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
 #pragma unroll
           for (int sd = 0; sd < I8_S; sd++)
             *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) = pack[sd];
+          }
         } else {
           double2 lo, hi;
           lo.x = v[0]; lo.y = v[1]; hi.x = v[2]; hi.y = v[3];
@@ -889,7 +923,7 @@ __global__ void row_exponent_kernel(const double* __restrict__ M, int64_t ld, in
 //   (s/2) * plane_bytes + row * 2*cols + (k/64) * 128 + (s%2) * 64 + (k%64).
 __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_t rows, int64_t cols4,
                                 const double* __restrict__ rowinv, double inv_const,
-                                uint32_t* __restrict__ out, int64_t plane_words, int kb) {
+                                uint32_t* __restrict__ out, int64_t plane_words, int kb, int radix256) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols4) return;
   const int64_t row = idx / cols4, c4 = idx - row * cols4;
@@ -900,6 +934,15 @@ __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_
   const int64_t row_words = 2 * cols4;                       // 2 * cols bytes
   // kb = k-values per interleave block (64: gemm_i8.cuh, 32: gemm_i8x2.cuh)
   const int64_t base = row * row_words + (k / kb) * (kb >> 1) + ((k % kb) >> 2);
+  if (radix256) {
+    int dg[4][5];
+#pragma unroll
+    for (int q = 0; q < 4; q++) digits_radix256(x[q], dg[q]);
+#pragma unroll
+    for (int s = 0; s < 5; s++)
+      out[(int64_t)(s >> 1) * plane_words + base + (s & 1) * (kb >> 2)] = pack4_i8(dg[0][s], dg[1][s], dg[2][s], dg[3][s]);
+    return;
+  }
 #pragma unroll
   for (int s = 0; s < I8_S; s++) {
     uint32_t pack = 0;
@@ -1081,7 +1124,9 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
   const int max_clusters = n_sm[h->device & 63] / 2;                 // one CTA per SM, two SMs per cluster
   const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
   if (!g_i8c2_attr) {
-    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)C2_SMEM_BYTES));
+    DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C2_SMEM_BYTES));
     g_i8c2_attr = true;
   }
@@ -1093,7 +1138,10 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
     if (tbuf == nullptr) DFB_CUDA_OK(cudaMalloc(&tbuf, sizeof(unsigned long long) * 4 * 128));
     g.timing = tbuf;
   }
-  score_i8c2_kernel<<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
+  if (h->i8_radix256)
+    score_i8c2_kernel<true><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
+  else
+    score_i8c2_kernel<false><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   if (timing) {
@@ -1126,7 +1174,7 @@ int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, in
   if (total <= 0) return 0;
   slice_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
       M, ld, rows, cols / 4, rowinv, inv_const, reinterpret_cast<uint32_t*>(out), plane_bytes / 4,
-      h->i8_impl >= 1 ? 32 : 64);
+      h->i8_impl >= 1 ? 32 : 64, h->i8_radix256);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1204,6 +1252,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
   o.planes = reinterpret_cast<uint8_t*>(planes); o.plane_bytes = plane_bytes; o.row_bytes = row_bytes;
   o.inv_colscale = inv_colscale;
   o.kb = (h->i8_impl >= 1) ? 32 : 64;
+  o.radix256 = h->i8_radix256;
   const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
   const int d = desc.factors[0].n_dims;
   bool ok = false;

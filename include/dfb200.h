@@ -207,21 +207,28 @@ int64_t dfb_launch_count(dfb_handle* h);
  *  "score_impl" : how |L^-1 k_*|^2 is contracted (env DFB200_SCORE=fp64|i8|auto; default auto):
  *                 0 = fp64 DMMA everywhere;
  *                 1 = int8-slice tcgen05 path (exact digit expansion of both fp64 operands, int32
- *                     accumulation in tensor memory, error-bounded: |d sigma^2| <~ 1e-10 k(x,x)) everywhere;
+ *                     accumulation in tensor memory; measured |d sigma^2| <= 4e-10 at N = 5000, a-priori
+ *                     estimate: query "i8_sigma2_bound") everywhere;
  *                 2 = auto: dfb_eval stays fp64; dfb_score_argmax scores with the int8 path, then re-scores
  *                     in fp64 the shortlist of candidates that could be the arg-max, so the returned index
  *                     and score are the fp64 ones.  The int8 path is skipped when its a-priori error bound
- *                     (query "i8_sigma2_bound") exceeds 1e-9 max(1, k(x,x)) or n < 1024.
- *  "i8_impl"    : which tcgen05 kernel the int8 path uses: 1 (default) = persistent kernel, two passes of M128
- *                 N128 K32 MMAs over each 128 x 128 tile (gemm_i8x2.cuh), 0 = one pass of N = 64 MMAs over a 128 x 64 tile
- *                 (gemm_i8.cuh).  Same digit products, same error bound; switching re-slices W (the digit
- *                 planes' interleave granularity differs).
+ *                     (query "i8_sigma2_bound") exceeds 5e-9 max(1, k(x,x)) -- half the 1e-8 contract --
+ *                     or n < 1024.
+ *  "i8_impl"    : which tcgen05 kernel the int8 path uses (switching re-slices W: layouts differ):
+ *                 2 (default) = persistent CTA-pair kernel: tcgen05.mma.cta_group::2 M256 N128 K32, two passes
+ *                     per 256 x 128 tile (gemm_i8c2.cuh);
+ *                 1 = the same two passes from single CTAs, M128 N128 K32 (gemm_i8x2.cuh);
+ *                 0 = one pass of M128 N64 K32 MMAs over 128 x 64 tiles, one CTA per tile (gemm_i8.cuh).
+ *  "i8_radix"   : digit scheme of the CTA-pair kernel: 1 = five radix-256 digits, 15 products (measured
+ *                 |d sigma^2| 3.6e-10 at N = 5000); 0 = six radix-128 digits, 21 products (3e-11), the scheme
+ *                 of i8_impl 0 and 1; -1 (default) = radix 256 whenever its a-priori bound is below
+ *                 5e-9 max(1, k(x,x)) for the training kernel, else radix 128.
  *  "i8_fuse"    : 1 (default) = the K_* kernel emits the int8 digit planes directly, 0 = via an fp64 K_* buffer.
  *  "i8_ts"      : i8_impl 0 only: 1 = stage W's digits in tensor memory (tcgen05.cp), default 0.
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
-/* Diagnostics: "i8_sigma2_bound", "i8_ready", "i8_impl", "last_used_i8", "last_shortlist" (-1 = overflow ->
- * fp64 pass). */
+/* Diagnostics: "i8_sigma2_bound", "i8_ready", "i8_impl", "i8_radix256", "last_used_i8", "last_shortlist"
+ * (-1 = overflow -> fp64 pass). */
 int dfb_query(dfb_handle* h, const char* name, double* out);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
