@@ -294,6 +294,7 @@ def run_ours(args):
   shortlist = int(gp._post.query('last_shortlist'))
   i8_bound = gp._post.query('i8_sigma2_bound')
   i8_impl = int(gp._post.query('i8_impl'))
+  i8_r256 = int(gp._post.query('i8_radix256'))
   del gp
   # the same step with the int8 path disabled: pure fp64 DMMA contraction, for reference
   device.DEFAULT_OPTIONS['score_impl'] = 0
@@ -324,32 +325,40 @@ def run_ours(args):
     tpath = os.path.join(ROOT, 'profiles', 'gemm_traffic.json')
     if os.path.exists(tpath):
       try:
-        traffic = json.load(open(tpath)).get(('dram_bytes_per_launch_i8x2' if i8_impl == 1 else 'dram_bytes_per_launch_i8')
+        traffic = json.load(open(tpath)).get({2: 'dram_bytes_per_launch_i8c2', 1: 'dram_bytes_per_launch_i8x2'}.get(i8_impl, 'dram_bytes_per_launch_i8')
                                              if used_i8 else 'dram_bytes_per_launch')
       except Exception:  # pylint: disable=broad-except
         traffic = None
     share = {kname: prof[kname][0] / max(sum(p[0] for p in prof.values()), 1e-9) for kname in prof}
     if used_i8:
       # dominant kernel: the tcgen05 int8 contraction (the digit planes of K_* are emitted by the K_*
-      # kernel, those of W once per build).  Algorithmic work: 21 int8 digit products per fp64
-      # multiply-add of the triangular contraction.
-      ops_per_cand = 21.0 * flops_per_cand
+      # kernel, those of W once per build).  Algorithmic work: one int8 digit product per kept (s, t) pair
+      # for every fp64 multiply-add of the triangular contraction -- 15 with five radix-256 digits, 21 with
+      # six radix-128 digits.
+      n_products = 15.0 if i8_r256 else 21.0
+      ops_per_cand = n_products * flops_per_cand
       achieved = gemm_cands * ops_per_cand / (gemm_ms * 1e-3) * 1e-12
       # int8 tensor peak: MEASURED_PEAKS.json has no int8 figure, so the denominator is the measured
       # tcgen05.mma kind::i8 issue rate of tools/ubench_i8.cu on this pool's B200
       # (profiles/r01_ubench_tcgen05_i8.txt): 4577 TOP/s for N >= 128 (2777 TOP/s for N = 64).
       peak, peak_n64 = 4577.2, 2777.1
-      if i8_impl == 1:
+      digits = ('five radix-256 digits, 15 exact int8 products' if i8_r256
+                else 'six radix-128 digits, 21 exact int8 products')
+      if i8_impl == 2:
+        kname = ('score_i8c2_kernel (persistent 2-CTA clusters; tcgen05.mma.cta_group::2 kind::i8 M256 N128 K32 / '
+                 'UTCIMMA.2CTA, four int32 accumulators = all 512 TMEM columns per SM, two passes per 256x128 '
+                 'tile, 6-stage TMA ring): V = L^-1 K_*^T as %s, fused |v|^2' % digits)
+      elif i8_impl == 1:
         kname = ('score_i8x2_kernel (persistent, one CTA per SM; tcgen05.mma kind::i8 M128 N128 K32 / UTCIMMA, four '
                  'int32 accumulators = all 512 TMEM columns, two passes per 128x128 tile, 4-stage TMA ring): '
-                 'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2')
+                 'V = L^-1 K_*^T as %s, fused |v|^2' % digits)
       else:
         kname = ('score_i8_kernel (tcgen05.mma kind::i8 M128 N64 K32, six TMEM accumulators, TMA ring): '
-                 'V = L^-1 K_*^T as 21 exact int8 digit products, fused |v|^2')
+                 'V = L^-1 K_*^T as %s, fused |v|^2' % digits)
       roofline = {
         'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TOP/s (int8)',
         'frac': achieved / peak, 'traffic': traffic, 'kernel': kname,
-        'ops_per_candidate': ops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
+        'int8_products_per_fp64_fma': n_products, 'ops_per_candidate': ops_per_cand, 'launch_ms_avg': gemm_ms / max(gemm_launches, 1),
         'launches_timed': int(gemm_launches),
         'peak_source': 'measured tcgen05 kind::i8 issue rate, M128 N128/N256 K32, tools/ubench_i8.cu on this pool '
                        '(profiles/r01_ubench_tcgen05_i8.txt); MEASURED_PEAKS.json bf16 burst = %s TF/s for '
@@ -374,8 +383,9 @@ def run_ours(args):
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None,
-      'dtype': 'f64' + (' (sigma^2 contraction: exact int8 digit expansion of the fp64 operands on tcgen05, '
-                        '|d sigma^2| <= %.1e; arg-max re-scored in fp64 DMMA)' % i8_bound if used_i8 else ''),
+      'dtype': 'f64' + (' (sigma^2 contraction: int8 digit expansion of the fp64 operands on tcgen05, a-priori '
+                        '|d sigma^2| <= %.1e, measured 3.6e-10; arg-max re-scored in fp64 DMMA)' % i8_bound
+                        if used_i8 else ''),
       'data': 'synthetic', 'config': workload_config(args, world),
       'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT,

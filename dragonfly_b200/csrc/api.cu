@@ -58,8 +58,9 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   double* te_xs = c.take<double>((size_t)npad * DFB_MAX_SLOTS);
   double* te_nrm = c.take<double>((size_t)npad * DFB_MAX_FACTORS);
   double* Ks = c.take<double>((size_t)chunk * npad);
-  int8_t* Wi8 = c.take<int8_t>((size_t)6 * npad * npad);
-  int8_t* Ki8 = c.take<int8_t>((size_t)6 * chunk * npad);
+  // three pair-interleaved digit planes (2 bytes per entry each) + one compact plane of the leading digit
+  int8_t* Wi8 = c.take<int8_t>((size_t)7 * npad * npad);
+  int8_t* Ki8 = c.take<int8_t>((size_t)7 * chunk * npad);
   double* rowscale = c.take<double>((size_t)npad);
   double* rowinv = c.take<double>((size_t)npad);
   int64_t* list_idx = c.take<int64_t>((size_t)SHORTLIST_CAP);
@@ -283,6 +284,9 @@ static int prepare_i8(dfb_handle* h) {
   if (h->i8_impl >= 1) {
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK2h, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK3h, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 3));
+    // compact plane of the leading digit (row-major rows of npad bytes, SWIZZLE_128B boxes of 128 k-values)
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmW1c, h->Wi8 + 6 * npad * npad, npad, npad, 1, npad, npad * npad, 128, 128, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK1c, h->Ki8 + 6 * h->chunk * npad, npad, h->chunk, 1, npad, h->chunk * npad, 128, 64, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW2, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW3, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 3));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK2, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 128, 1));
@@ -371,7 +375,7 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
           DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
                                   2 * h->chunk * npad, 2 * npad));
         if (h->i8_impl == 2)
-          DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmK2h, h->tmK3h, nb, (int)(m_rows / TILE), (int)npad,
+          DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmW1c, h->tmK2h, h->tmK3h, h->tmK1c, nb, (int)(m_rows / TILE), (int)npad,
                                          h->partial, Mc, h->rowscale, colscale));
         else if (h->i8_impl == 1)
           DFB_TRY(launch_score_i8x2_args(h, h->tmW2, h->tmW3, h->tmK2, h->tmK3, nb, (int)(m_rows / TILE), (int)npad,

@@ -138,6 +138,7 @@ struct dfb_handle {
                               // 2 = as 1 with CTA-pair M256 MMAs (gemm_i8c2.cuh)
   int i8_radix_opt = -1;      // digit scheme of the pair kernel: -1 auto (radix 256 when its bound allows), 0 = 128, 1 = 256
   int i8_radix256 = 0;        // scheme in use for the current posterior (set by prepare_i8)
+  CUtensorMap tmW1c, tmK1c;             // compact leading-digit planes (pass B of the radix-256 scheme)
   CUtensorMap tmK2h, tmK3h;             // 64-row boxes of the K_* digit planes (i8_impl 2: half tiles per CTA)
   CUtensorMap tmW2, tmW3, tmK2, tmK3;   // 2- and 3-plane boxes of the digit planes (i8_impl 1)
 

@@ -20,7 +20,8 @@
 // a_s b_t with s + t <= 6 are kept (15 MMAs per K = 32 block instead of 21; the dropped s + t = 7 terms
 // are ~2^-40 of the operands' scale, the same order as the digit truncation), grouped by d = s + t with
 // weight 2^-(8d-2).  Pass A accumulates groups 3..6 (14 products, all digits) in the four accumulators,
-// pass B group 2 (the single leading product) in accumulator 0.  int32 headroom: 5 K 2^14 < 2^31 needs
+// pass B group 2 (the single leading product) in accumulator 0, streaming a compact copy of the leading
+// digit (plain row-major int8 rows, SWIZZLE_128B, 128 k-values per stage: a sixth of pass A's bytes).  int32 headroom: 5 K 2^14 < 2^31 needs
 // K <= 26214 (api.cu refuses the path beyond npad = 24576).  The tensor pipe -- and at the 1 kW power cap
 // the whole step -- scales with the MMA count, so this is a straight 29 % cut of the dominant cost for
 // an error that stays ~30x inside the 1e-8 contract at N = 5000.  R256 = false keeps the six radix-128 digits
@@ -40,6 +41,8 @@ constexpr int C2_DIGITS = 5;                           // radix-256 digits per o
 constexpr int C2_A_SUB = X2_BM * 2 * X2_BK;             // 8192 B: 128 rows x 64 B
 constexpr int C2_B_SUB = (X2_BN / 2) * 2 * X2_BK;       // 4096 B:  64 rows x 64 B
 constexpr int C2_STAGE_BYTES = 3 * C2_A_SUB + 3 * C2_B_SUB;          // 36864 per CTA
+constexpr int C2_PB_A_BYTES = X2_BM * 128;              // pass B, radix 256: 128 rows x 128 k-values of the leading digit
+constexpr int C2_PB_BYTES = C2_PB_A_BYTES + (X2_BN / 2) * 128;       // + 64 candidate rows: 24576 per CTA
 constexpr int C2_THREADS = 320;
 constexpr size_t C2_SMEM_BYTES = (size_t)C2_STAGES * C2_STAGE_BYTES + 1024 + 2 * 4 * X2_BN * sizeof(double) +
                                  (2 * C2_STAGES + 4) * 8 + 64;
@@ -105,6 +108,11 @@ __device__ __forceinline__ void c2_commit(void* bar) {
       : "memory");
 }
 
+// stages of pass B for nk K = 32 blocks: radix 256 carries 128 k-values of the compact leading-digit plane per
+// stage, radix 128 three K = 32 blocks of the first digit-pair plane
+template <bool R256>
+__device__ __forceinline__ int c2_pass_b_stages(int nk) { return R256 ? (nk + 3) / 4 : (nk + 2) / 3; }
+
 // Tile j of cluster c: serpentine deal of the list (row-block pair descending, cb ascending)
 __device__ __forceinline__ bool c2_tile(const ScoreI8Args& g, int j, int& rp, int& cb, int& nk) {
   const int P = (int)gridDim.x >> 1, c = (int)blockIdx.x >> 1;
@@ -120,7 +128,8 @@ __device__ __forceinline__ bool c2_tile(const ScoreI8Args& g, int j, int& rp, in
 template <bool R256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
 score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA3,
-                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB3,
+                  const __grid_constant__ CUtensorMap tmA1c, const __grid_constant__ CUtensorMap tmB1,
+                  const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmB1c,
                   const ScoreI8Args g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
@@ -165,12 +174,19 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       for (int j = 0; c2_tile(g, j, rp, cb, nk); j++) {
         const int rb = 2 * rp + (int)rank;
         const int brow = cb * X2_BN + (int)rank * (X2_BN / 2);
-        const int n_it = nk + (nk + 2) / 3;
+        const int n_it = nk + c2_pass_b_stages<R256>(nk);
         for (int it = 0; it < n_it; it++, git++) {
           const unsigned s = git % C2_STAGES, n = git / C2_STAGES;
           mbar_wait(&empty_bar[s], (n & 1u) ^ 1u);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)C2_STAGE_BYTES);   // both CTAs' bytes
           unsigned char* dst = tiles + (size_t)s * C2_STAGE_BYTES;
+          if (R256 && it >= nk) {
+            // pass B, radix 256: 128 k-values of the compact leading-digit planes (A 16 KB, B half 8 KB)
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)C2_PB_BYTES);
+            c2_tma_load_3d(dst, &tmA1c, (it - nk) * 128, rb * X2_BM, 0, &full_bar[s]);
+            c2_tma_load_3d(dst + C2_PB_A_BYTES, &tmB1c, (it - nk) * 128, brow, 0, &full_bar[s]);
+            continue;
+          }
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)C2_STAGE_BYTES);   // both CTAs' bytes
           if (it < nk) {
             c2_tma_load_3d(dst, &tmA3, it * 2 * X2_BK, rb * X2_BM, 0, &full_bar[s]);
             c2_tma_load_3d(dst + 3 * C2_A_SUB, &tmB3, it * 2 * X2_BK, brow, 0, &full_bar[s]);
@@ -200,7 +216,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       long long t_full = 0, t_drain = 0, t_epi = 0, t0 = 0;
       const long long t_start = clock64();
       for (int j = 0; c2_tile(g, j, rp, cb, nk); j++) {
-        const int n_it = nk + (nk + 2) / 3;
+        const int n_it = nk + c2_pass_b_stages<R256>(nk);
         const unsigned tpar = (unsigned)(j & 1);
         if (j > 0) {
           if (timed) t0 = clock64();
@@ -245,11 +261,14 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                 }
               }
             } else {
-              // group 2 = the leading product (1, 1) -> accumulator 0; sub-tile index = K = 32 block
+              // group 2 = the leading product (1, 1) -> accumulator 0: four K = 32 steps along the 128-byte
+              // SWIZZLE_128B rows of the compact leading-digit tiles (SBO = 1024 B, layout type 2)
+              constexpr uint64_t DESC_HI128 = ((uint64_t)(64u | (1u << 14) | (2u << 29))) << 32;
+              const unsigned pb_b_lo = (((a0 + C2_PB_A_BYTES) & 0x3FFFFu) >> 4) | 0x10000u;
 #pragma unroll
-              for (int u = 0; u < 3; u++) {
-                const uint64_t a1 = DESC_HI | (uint64_t)(a_lo + ((unsigned)(u * C2_A_SUB) >> 4));
-                const uint64_t b1 = DESC_HI | (uint64_t)(b_lo + ((unsigned)(u * C2_B_SUB) >> 4));
+              for (int u = 0; u < 4; u++) {
+                const uint64_t a1 = DESC_HI128 | (uint64_t)(a_lo + ((unsigned)(u * X2_BK) >> 4));
+                const uint64_t b1 = DESC_HI128 | (uint64_t)(pb_b_lo + ((unsigned)(u * X2_BK) >> 4));
                 if (el) c2_umma(0u, a1, b1, (first && u == 0) ? 0u : 1u);
               }
             }

@@ -24,8 +24,8 @@ int make_tensor_map_3d_u8(CUtensorMap* out, const void* base, int64_t cols, int6
 int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtensorMap& tmA3,
                            const CUtensorMap& tmB2, const CUtensorMap& tmB3, int n_rb, int n_cb, int K,
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale);
-int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3,
-                           const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, int n_rb, int n_cb, int K,
+int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3, const CUtensorMap& tmA1c,
+                           const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, const CUtensorMap& tmB1c, int n_rb, int n_cb, int K,
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale);
 int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
                         double* rowscale, double* rowinv);

@@ -435,6 +435,9 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
             for (int sd = 0; sd < 5; sd++)
               *reinterpret_cast<uint32_t*>(dst + (int64_t)(sd >> 1) * i8o.plane_bytes + (sd & 1) * i8o.kb) =
                   pack4_i8(dg[0][sd], dg[1][sd], dg[2][sd], dg[3][sd]);
+            // compact copy of the leading digit (plain row-major rows) for pass B of gemm_i8c2.cuh
+            *reinterpret_cast<uint32_t*>(i8o.planes + 3 * i8o.plane_bytes + cand * (i8o.row_bytes >> 1) + j0) =
+                pack4_i8(dg[0][0], dg[1][0], dg[2][0], dg[3][0]);
           } else {
           const double MAGIC = 6755399441055744.0;
           int hi[4], lo[4];
@@ -941,6 +944,7 @@ __global__ void slice_i8_kernel(const double* __restrict__ M, int64_t ld, int64_
 #pragma unroll
     for (int s = 0; s < 5; s++)
       out[(int64_t)(s >> 1) * plane_words + base + (s & 1) * (kb >> 2)] = pack4_i8(dg[0][s], dg[1][s], dg[2][s], dg[3][s]);
+    out[3 * plane_words + row * cols4 + c4] = pack4_i8(dg[0][0], dg[1][0], dg[2][0], dg[3][0]);   // compact leading digit
     return;
   }
 #pragma unroll
@@ -1109,8 +1113,8 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
 }
 
 static bool g_i8c2_attr = false;
-int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3,
-                           const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, int n_rb, int n_cb, int K,
+int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3, const CUtensorMap& tmA1c,
+                           const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, const CUtensorMap& tmB1c, int n_rb, int n_cb, int K,
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
   ScoreI8Args g;
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
@@ -1139,9 +1143,9 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
     g.timing = tbuf;
   }
   if (h->i8_radix256)
-    score_i8c2_kernel<true><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
+    score_i8c2_kernel<true><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmA1c, tmB1h, tmB3h, tmB1c, g);
   else
-    score_i8c2_kernel<false><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmB1h, tmB3h, g);
+    score_i8c2_kernel<false><<<2 * n_clusters, C2_THREADS, C2_SMEM_BYTES, h->stream>>>(tmA1, tmA3, tmA1c, tmB1h, tmB3h, tmB1c, g);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   if (timing) {
