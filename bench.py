@@ -206,6 +206,21 @@ def measure_dgemm_peak(torch, dev):
   return 2.0 * n ** 3 / best * 1e-9
 
 
+def kstar_build_line(prof, n_train, peaks):
+  """ The standalone materialising K_* build (fp64 rows written to HBM) against the HBM roofline. """
+  ms, launches, cands = prof
+  npad = (n_train + 127) // 128 * 128
+  if ms <= 0:
+    return None
+  gbs = cands * npad * 8.0 / (ms * 1e-3) * 1e-9
+  hbm = float(peaks.get('hbm_gbs', 6564.2))
+  entries = cands * npad / (ms * 1e-3)
+  return {'kernel': 'kstar_fast_kernel<Matern, p=2, d=6> writing fp64 K_* rows', 'achieved_gbs': gbs,
+          'hbm_peak_gbs': hbm, 'frac_of_hbm': gbs / hbm, 'candidates_per_s': cands / (ms * 1e-3),
+          'entries_per_s': entries, 'launch_ms_avg': ms / max(launches, 1),
+          'bound': 'fp64 pipe / issue slots (sqrt + exp per entry), not HBM: see DESIGN.md 5.1'}
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -301,7 +316,40 @@ def run_ours(args):
   one_step(cands_dev)
   barrier()
   ms_fp64 = timed(cands_dev, 2)
+  # the materialising K_* build of the fp64 path (the north-star's "K_* build vs HBM" figure), timed per
+  # launch with the same event hooks: 8 * npad bytes written per candidate
+  gp = gp_core.GP(Xh, Yh, kern, mean, w['noise_var'], device=local)
+  gp._post.profile_enable(True)
+  for _ in range(2):
+    flush.fill_(1.0)
+    gp._fused_score(acq, cands_dev[:200000])
+  kstar64 = gp._post.profile_read(0)
+  gp._post.profile_enable(False)
+  del gp
   device.DEFAULT_OPTIONS.pop('score_impl')
+
+  # incremental posterior update (dfb_extend_posterior) against the full rebuild the reference does on every
+  # new observation: N-1 -> N points
+  upd = {}
+  if rank == 0:
+    gp = gp_core.GP(Xh[:-1], Yh[:-1], kern, mean, w['noise_var'], device=local)
+    post0 = gp._post
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    gp.add_data_multiple([Xh[-1]], [Yh[-1]])
+    torch.cuda.synchronize(dev)
+    upd['extend_1_point_ms'] = 1e3 * (time.perf_counter() - t0)
+    upd['in_place'] = bool(gp._post is post0)
+    lml_ext = gp.compute_log_marginal_likelihood()
+    del gp, post0
+    t0 = time.perf_counter()
+    gp = gp_core.GP(Xh, Yh, kern, mean, w['noise_var'], device=local)
+    torch.cuda.synchronize(dev)
+    upd['full_build_ms'] = 1e3 * (time.perf_counter() - t0)
+    upd['lml_rel_diff'] = abs(lml_ext - gp.compute_log_marginal_likelihood()) / abs(gp.compute_log_marginal_likelihood())
+    upd['note'] = ('GP.add_data_multiple of one observation at N-1 -> N: in-place extension of the factorisation '
+                   '(last row block of L / L^-1 only) vs GP(...) from scratch, host wall-clock incl. uploads')
+    del gp
 
   t = torch.tensor([ms_dev, ms_e2e, ms_fp64], dtype=torch.float64, device=dev)
   if world > 1:
@@ -395,6 +443,8 @@ def run_ours(args):
       'roofline': roofline,
       'fp64_dmma_only': {'value': M * world * 2 / (ms_fp64 * 1e-3), 'unit': UNIT,
                          'note': 'same step with DFB200_SCORE=fp64 (no int8 path), 2 timed steps'},
+      'kstar_build_fp64': kstar_build_line(kstar64, N, peaks),
+      'posterior_update': upd,
     }
     if not args.no_cpu_baseline:
       wc = synth_data.make_workload('headline_hartmann6_matern_ei', n_train=args.n_train,

@@ -19,6 +19,7 @@ DFB_BASE_SE, DFB_BASE_MATERN = 0, 1
 DFB_DEVICE, DFB_HOST = 0, 1
 DFB_ACQ_MEAN, DFB_ACQ_UCB, DFB_ACQ_EI, DFB_ACQ_PI, DFB_ACQ_TTEI = 0, 1, 2, 3, 4
 DFB_BUILD_FULL, DFB_BUILD_LML_ONLY, DFB_BUILD_NO_ALPHA = 0, 1, 2
+DFB_EXTEND_SAVE = 16
 
 
 class FactorDesc(C.Structure):
@@ -61,6 +62,8 @@ PROTOTYPES = {
   'dfb_set_test_kernel': (C.c_int, [_P, C.POINTER(KernelDesc)]),
   'dfb_set_train': (C.c_int, [_P, _P, _I64, _I32, _P]),
   'dfb_build_posterior': (C.c_int, [_P, _D, _D, _I32, C.POINTER(_D)]),
+  'dfb_extend_posterior': (C.c_int, [_P, _P, _I64, _P, _I32, C.POINTER(_D)]),
+  'dfb_restore_posterior': (C.c_int, [_P]),
   'dfb_get_max_diag': (C.c_int, [_P, C.POINTER(_D)]),
   'dfb_get_state': (C.c_int, [_P, _P, _P, _P]),
   'dfb_set_alpha': (C.c_int, [_P, _P, _I64]),

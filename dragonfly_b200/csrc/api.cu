@@ -81,7 +81,11 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   dfb_kernel_desc* d0 = c.take<dfb_kernel_desc>(1);
   dfb_kernel_desc* d1 = c.take<dfb_kernel_desc>(1);
   dfb_kernel_desc* d2 = c.take<dfb_kernel_desc>(1);
+  // dfb_extend_posterior's snapshot of what it overwrites: the last row block of L, the last block
+  // column of L^-T, that block of the y row, alpha
+  double* ext_save = c.take<double>((size_t)(2 * TILE + 1) * npad + TILE);
   if (h != nullptr && base != nullptr) {
+    h->ext_save = ext_save;
     h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
     h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
     h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->list_idx = list_idx; h->list_X = list_X; h->list_count = list_count; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
@@ -296,6 +300,93 @@ static int prepare_i8(dfb_handle* h) {
     DFB_TRY(make_tensor_map_3d_u8(&h->tmKi8, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 128, 64, 3));
   }
   h->i8_ready = true;
+  return 0;
+}
+
+
+// ---- incremental posterior update ------------------------------------------------------
+// Appending q training points changes only the LAST row block of L (as long as n + q stays inside the same
+// padded size): Cholesky row i depends on rows <= i alone.  Rather than re-running the N^3/3 right-looking
+// factorisation, the pre-step state of the last block column of the tall matrix [A ; I ; y^T] is rebuilt by
+// left-looking products against the finished factor and the last factorisation step is replayed:
+//     P    = A[last, :m0] L00^-T = A[last, :m0] W00^T          top, row block nb-1, columns < m0
+//     S    = A[last, last] - P P^T                             top, diagonal block
+//     Wt_c = -(L00^-T) P^T                                     L^-T rows < m0, last block column
+//     y_c  = y[last] - v[:m0] P^T                              y row, last block
+// then chol_diag + the panel solve of step nb-1 turn (S, I, Wt_c, y_c) into (L_dd, L_dd^-T, L^-T's last
+// block column, v[last]).  Cost 4 N^2 * 128 flops + one 128 x 128 Cholesky instead of 2 N^3 / 3.
+static int replay_last_block(dfb_handle* h, int32_t flags, double* lml_out_host) {
+  const int64_t n = h->n, npad = h->npad;
+  const int nb = (int)(npad / TILE), step = nb - 1;
+  const int64_t m0 = (int64_t)step * TILE;
+  double* top_row = h->T + m0 * npad;                      // row block nb-1 of the top
+  double* mid = h->T + npad * npad;                        // L^-T
+  double* yrow = h->T + 2 * npad * npad;                   // y row block (row 0 holds the data)
+  h->have_post = h->have_w = false;
+  h->tr_prepped = h->te_prepped = false;
+  DFB_TRY(ensure_train_scaled(h));
+  DFB_CUDA_OK(cudaMemsetAsync(h->info, 0, sizeof(int) * 4, h->stream));
+  // A[last, :] = K(X[last], X) + (noise + jitter) I, identity on the padding rows -> Ks scratch (128 x npad)
+  DFB_TRY(launch_kstar(h, h->d_desc_tr, h->desc_tr, 1, h->tr.xs, h->tr.nrm, npad, nullptr, h->X + m0 * h->d,
+                       n - m0, h->d, TILE, h->Ks, npad, n, npad, 0.0, nullptr, nullptr));
+  DFB_TRY(launch_set_diag(h, h->Ks + m0, npad, 0, n - m0, h->noise_plus_jitter, 1));
+  DFB_TRY(launch_set_diag(h, h->Ks + m0, npad, n - m0, TILE, 1.0, 0));
+  GemmArgs g;
+  if (step > 0) {
+    // P[a][i] = sum_{k <= i} A[a][k] W[i][k]
+    memset(&g, 0, sizeof(g));
+    g.A = h->Ks; g.lda = npad; g.B = h->W; g.ldb = npad; g.D = top_row; g.ldd = npad; g.alpha = 1.0;
+    g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = step; g.K = (int)m0; g.tri = 2;
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
+    // Wt_c[j][a] = -sum_k Wt[j][k] P[a][k]
+    memset(&g, 0, sizeof(g));
+    g.A = mid; g.lda = npad; g.B = top_row; g.ldb = npad; g.D = mid + m0; g.ldd = npad; g.alpha = -1.0;
+    g.mode = MODE_GENERIC; g.n_rb = step; g.n_cb = 1; g.K = (int)m0;
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
+  }
+  // S = A[last, last] - P P^T  (K = 0 degenerates to a copy)
+  memset(&g, 0, sizeof(g));
+  g.A = top_row; g.lda = npad; g.B = top_row; g.ldb = npad; g.C = h->Ks + m0; g.ldc = npad;
+  g.D = top_row + m0; g.ldd = npad; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = 1; g.K = (int)m0;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
+  // identity in the diagonal block of L^-T
+  DFB_CUDA_OK(cudaMemset2DAsync(mid + m0 * npad + m0, sizeof(double) * npad, 0, sizeof(double) * TILE, TILE, h->stream));
+  DFB_TRY(launch_set_diag(h, mid, npad, m0, npad, 1.0, 0));
+  // y_c = y[last] - v[:m0] P^T (rows 1..127 of the y block are zero and stay zero)
+  DFB_TRY(launch_copy_pad(h, h->yc + m0, n - m0, yrow + m0, TILE));
+  memset(&g, 0, sizeof(g));
+  g.A = yrow; g.lda = npad; g.B = top_row; g.ldb = npad; g.C = yrow + m0; g.ldc = npad;
+  g.D = yrow + m0; g.ldd = npad; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = 1; g.K = (int)m0;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
+  // replay of factorisation step nb-1
+  DFB_TRY(launch_chol_diag(h, h->T, npad, step, h->Dinv, h->info));
+  memset(&g, 0, sizeof(g));
+  g.A = h->T; g.lda = npad; g.B = h->Dinv; g.ldb = TILE; g.D = h->T; g.ldd = npad;
+  g.alpha = 1.0; g.mode = MODE_PANEL; g.K = TILE; g.step = step; g.nb = nb; g.info = h->info;
+  DFB_TRY(launch_gemm(h, g, EPI_STORE, 2 * nb + 1 - (step + 1)));
+  const double* Wt = mid;
+  const double* v = yrow;
+  DFB_TRY(launch_transpose(h, Wt, h->W, npad));
+  if (flags == DFB_BUILD_FULL) DFB_TRY(launch_alpha(h, Wt, v, h->alpha, n, npad));
+  DFB_TRY(launch_lml_reduce(h, h->T, h->yc, flags == DFB_BUILD_FULL ? h->alpha : nullptr, v, n, npad, h->red));
+  double red[3];
+  int info = 0;
+  DFB_CUDA_OK(cudaMemcpyAsync(red, h->red, sizeof(red), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(&info, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (info != 0) {
+    set_error("extended matrix is not positive definite: non-positive pivot at index %d", info - 1);
+    return info;
+  }
+  h->have_post = true;
+  h->have_w = true;
+  h->i8_ready = false;
+  if (h->score_impl == 1 || (h->score_impl == 2 && h->n >= 1024)) DFB_TRY(prepare_i8(h));
+  // the fp64 TMA maps of W and Ks describe (address, npad) only: still valid
+  if (lml_out_host != nullptr) {
+    const double quad = (flags == DFB_BUILD_FULL) ? red[1] : red[2];
+    *lml_out_host = -0.5 * quad - red[0] - 0.5 * (double)n * log(2.0 * M_PI);
+  }
   return 0;
 }
 
@@ -588,6 +679,74 @@ int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t 
     const double quad = (flags == DFB_BUILD_FULL) ? red[1] : red[2];
     *lml_out_host = -0.5 * quad - red[0] - 0.5 * (double)n * log(2.0 * M_PI);
   }
+  return 0;
+}
+
+int dfb_restore_posterior(dfb_handle* h);
+
+int dfb_extend_posterior(dfb_handle* h, const double* X_new_dev, int64_t q, const double* y_centred_new_dev,
+                         int32_t flags, double* lml_out_host) {
+  DFB_TRY(need(h, true, true, true, true, true));
+  const int32_t build_flags = flags & ~DFB_EXTEND_SAVE;
+  if (build_flags != DFB_BUILD_FULL && build_flags != DFB_BUILD_NO_ALPHA) { set_error("dfb_extend_posterior: flags must be DFB_BUILD_FULL or DFB_BUILD_NO_ALPHA (| DFB_EXTEND_SAVE)"); return -1; }
+  if (q < 1 || X_new_dev == nullptr || y_centred_new_dev == nullptr) { set_error("bad extend arguments (q = %lld)", (long long)q); return -1; }
+  if (h->n + q > h->npad) {
+    set_error("dfb_extend_posterior: %lld + %lld points do not fit the padded size %lld of this posterior: rebuild",
+              (long long)h->n, (long long)q, (long long)h->npad);
+    return -1;
+  }
+  if (h->ext_saved) { set_error("dfb_extend_posterior: a saved extension is active, call dfb_restore_posterior first"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  const int64_t n0 = h->n, npad = h->npad;
+  const int64_t m0 = npad - TILE;
+  if (flags & DFB_EXTEND_SAVE) {
+    double* s = h->ext_save;
+    DFB_CUDA_OK(cudaMemcpyAsync(s, h->T + m0 * npad, sizeof(double) * TILE * npad, cudaMemcpyDeviceToDevice, h->stream));
+    DFB_CUDA_OK(cudaMemcpy2DAsync(s + TILE * npad, sizeof(double) * TILE, h->T + npad * npad + m0, sizeof(double) * npad,
+                                  sizeof(double) * TILE, (size_t)npad, cudaMemcpyDeviceToDevice, h->stream));
+    DFB_CUDA_OK(cudaMemcpyAsync(s + 2 * TILE * npad, h->T + 2 * npad * npad + m0, sizeof(double) * TILE,
+                                cudaMemcpyDeviceToDevice, h->stream));
+    DFB_CUDA_OK(cudaMemcpyAsync(s + 2 * TILE * npad + TILE, h->alpha, sizeof(double) * npad, cudaMemcpyDeviceToDevice, h->stream));
+    h->ext_saved_n = n0;
+  }
+  DFB_CUDA_OK(cudaMemcpyAsync(h->X + n0 * h->d, X_new_dev, sizeof(double) * q * h->d, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(h->yc + n0, y_centred_new_dev, sizeof(double) * q, cudaMemcpyDeviceToDevice, h->stream));
+  h->n = n0 + q;
+  if (h->n_max < h->n) h->n_max = h->n;
+  const int r = replay_last_block(h, build_flags, lml_out_host);
+  if (flags & DFB_EXTEND_SAVE) {
+    h->ext_saved = true;
+    if (r > 0) {                       // not positive definite: put the un-extended posterior back
+      char msg[512];
+      snprintf(msg, sizeof(msg), "%s", g_err);
+      DFB_TRY(dfb_restore_posterior(h));
+      set_error("%s", msg);
+    }
+  }
+  return r;
+}
+
+int dfb_restore_posterior(dfb_handle* h) {
+  DFB_TRY(need(h, true, true, true, false, false));
+  if (!h->ext_saved) { set_error("dfb_restore_posterior: nothing saved"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  const int64_t npad = h->npad, m0 = npad - TILE, n0 = h->ext_saved_n;
+  const double* s = h->ext_save;
+  DFB_CUDA_OK(cudaMemcpyAsync(h->T + m0 * npad, s, sizeof(double) * TILE * npad, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_CUDA_OK(cudaMemcpy2DAsync(h->T + npad * npad + m0, sizeof(double) * npad, s + TILE * npad, sizeof(double) * TILE,
+                                sizeof(double) * TILE, (size_t)npad, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(h->T + 2 * npad * npad + m0, s + 2 * TILE * npad, sizeof(double) * TILE,
+                              cudaMemcpyDeviceToDevice, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(h->alpha, s + 2 * TILE * npad + TILE, sizeof(double) * npad, cudaMemcpyDeviceToDevice, h->stream));
+  DFB_TRY(launch_fill(h, h->yc + n0, npad - n0, 0.0));           // zero the appended targets
+  h->n = n0;
+  h->ext_saved = false;
+  h->tr_prepped = h->te_prepped = false;
+  DFB_TRY(launch_transpose(h, h->T + npad * npad, h->W, npad));
+  h->have_post = h->have_w = true;
+  h->i8_ready = false;
+  if (h->score_impl == 1 || (h->score_impl == 2 && h->n >= 1024)) DFB_TRY(prepare_i8(h));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -152,5 +152,9 @@ struct dfb_handle {
   int64_t n = 0, npad = 0;
   int32_t d = 0;
   double noise_plus_jitter = 0.0;
+  // dfb_extend_posterior / dfb_restore_posterior
+  double* ext_save = nullptr;   // (2*TILE + 1) * npad + TILE doubles
+  bool ext_saved = false;
+  int64_t ext_saved_n = 0;
   double max_diag = 0.0;
 };

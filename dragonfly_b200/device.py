@@ -123,6 +123,32 @@ class DevicePosterior(object):
     self.lml = lml.value if info == 0 else None
     return info, self.lml
 
+  def capacity(self):
+    """ Training points this posterior can hold without a rebuild: its padded size (a multiple of 128). """
+    return (self.n + 127) // 128 * 128
+
+  def extend(self, X_new, y_centred_new, flags=_lib.DFB_BUILD_FULL, save=False):
+    """ dfb_extend_posterior: appends training points to the built posterior in O(N^2) work.
+        Returns (info, lml); info > 0 = the extended matrix is not positive definite (with save=True
+        the un-extended posterior is back in place, otherwise it must be rebuilt). """
+    Xd = _dev_f64(X_new, self.device)
+    yd = _dev_f64(y_centred_new, self.device)
+    q = int(Xd.shape[0])
+    assert int(Xd.shape[1]) == self.dim and int(yd.shape[0]) == q
+    lml = C.c_double(0.0)
+    info = _lib.check(self.lib.dfb_extend_posterior(
+        self.h, C.c_void_p(Xd.data_ptr()), q, C.c_void_p(yd.data_ptr()),
+        int(flags) | (_lib.DFB_EXTEND_SAVE if save else 0), C.byref(lml)), 'dfb_extend_posterior')
+    if info == 0:
+      self.n += q
+      self.lml = lml.value
+    return info, (lml.value if info == 0 else None)
+
+  def restore(self, n_before):
+    """ dfb_restore_posterior: undoes an extend(..., save=True) bit for bit. """
+    _lib.check(self.lib.dfb_restore_posterior(self.h), 'dfb_restore_posterior')
+    self.n = int(n_before)
+
   def max_diag(self):
     out = C.c_double(0.0)
     _lib.check(self.lib.dfb_get_max_diag(self.h, C.byref(out)), 'dfb_get_max_diag')

@@ -10,6 +10,7 @@ jitter ladder of stable_cholesky (general_utils.py:166-204), which re-submits th
 10^p * max(diag) added until the device reports success.
 """
 import sys
+from contextlib import contextmanager
 from warnings import warn
 
 import numpy as np
@@ -131,14 +132,61 @@ class GP(object):
   def add_data_single(self, x_new, y_new, *args, **kwargs):
     self.add_data_multiple([x_new], [y_new], *args, **kwargs)
 
+  # The reference re-factorises from scratch on every new observation (gp_core.py:139-146).  Here the
+  # built posterior is extended in place (dfb_extend_posterior: only the last row block of L changes,
+  # O(N^2) instead of O(N^3)) whenever that is exactly the same mathematical object; set to False to
+  # force the reference's full rebuild.
+  incremental_updates = True
+
   def add_data_multiple(self, X_new, Y_new, build_posterior=True):
-    """ gp_core.py:139-146 (full rebuild on every new observation, like the reference). """
+    """ gp_core.py:139-146 """
     _check_feature_label_lengths_and_format(X_new, Y_new)
+    X_new, Y_new = list(X_new), list(Y_new)
     self.X.extend(X_new)
     self.Y.extend(Y_new)
     self.num_tr_data = len(self.Y)
     if build_posterior:
-      self.build_posterior()
+      if not self._extend_posterior(len(Y_new)):
+        self.build_posterior()
+
+  def _posterior_token(self):
+    return (id(self.kernel), id(self.mean_func), float(self.noise_var), self.handle_non_psd_kernels)
+
+  def _rows_as_train_matrix(self, rows):
+    """ `rows` (a list in the format of self.X) as rows of the matrix the kernel sees. """
+    saved_X = self.X
+    try:
+      self.X = list(rows)
+      return self._train_matrix()
+    finally:
+      self.X = saved_X
+
+  def _can_extend_in_place(self, q):
+    post = getattr(self, '_post', None)
+    return (self.incremental_updates and post is not None and q >= 1 and
+            getattr(self, 'jitter_power', None) is None and
+            getattr(self, '_post_token', None) == self._posterior_token() and
+            post.n + q <= post.capacity())
+
+  def _extend_posterior(self, q):
+    """ The last q entries of self.X / self.Y are new: extend the device posterior in place.
+        Returns False when a full build_posterior() is needed instead (posterior shared with a copy
+        of this GP, a jitter ladder in play, kernel / noise / mean changed since the build, padded
+        size exceeded, or the extended matrix not positive definite at jitter 0). """
+    post = getattr(self, '_post', None)
+    if (not self._can_extend_in_place(q) or getattr(self, '_post_shared', False) or
+        post.n + q != self.num_tr_data):
+      return False
+    y_new = (np.asarray(self.Y[-q:], dtype=np.float64) -
+             np.asarray(self.mean_func(self.X[-q:]), dtype=np.float64))
+    info, lml = post.extend(self._rows_as_train_matrix(self.X[-q:]), y_new, _lib.DFB_BUILD_FULL)
+    if info != 0:
+      self._post = None        # the factorisation was overwritten: rebuild (with the jitter ladder)
+      return False
+    self._cache = {}
+    self._y_centred = np.concatenate((self._y_centred, y_new))
+    self._lml = lml
+    return True
 
   # -- posterior ------------------------------------------------------------------------------------
   def _train_matrix(self):
@@ -182,6 +230,8 @@ class GP(object):
     self._y_centred = y_centred
     self._post, self._lml, self.jitter_power = self._build_on_device(X_mat, y_centred,
                                                                      _lib.DFB_BUILD_FULL)
+    self._post_token = self._posterior_token()
+    self._post_shared = False
     self._mean_const = _constant_mean_value(self.mean_func, X_mat.shape[1])
 
   def _state(self, name):
@@ -297,16 +347,42 @@ class GP(object):
     post.set_alpha(self.alpha)
     return post
 
+  @contextmanager
+  def _hallucinated(self, X_halluc):
+    """ The device posterior with the pending points appended (variance from the augmented GP, mean
+        from the un-augmented one: gp_core.py:200-217).  When the q points fit the padded size, the
+        built posterior is extended in place (dfb_extend_posterior | DFB_EXTEND_SAVE, alpha
+        zero-extended) and restored bit for bit on exit; otherwise -- or if the extended matrix needs
+        the jitter ladder -- a fresh (N + q)-point posterior is built like the reference does. """
+    q = len(X_halluc)
+    post = getattr(self, '_post', None)
+    if q == 0:
+      yield post
+      return
+    if self._can_extend_in_place(q) and not getattr(post, '_ext_active', False):
+      n0 = post.n
+      info, _ = post.extend(self._rows_as_train_matrix(X_halluc), np.zeros(q), _lib.DFB_BUILD_NO_ALPHA,
+                            save=True)
+      if info == 0:
+        post._ext_active = True
+        try:
+          yield post        # alpha was left untouched: its tail beyond n0 is zero
+        finally:
+          post.restore(n0)
+          post._ext_active = False
+        return
+    yield self._augmented_posterior(X_halluc)
+
   def eval_with_hallucinated_observations(self, X_test, X_halluc, uncert_form='none'):
     """ gp_core.py:192-220 """
     if uncert_form not in ('none', 'std', 'covar'):
       raise ValueError('uncert_form should be none, covar or std.')
     if uncert_form == 'none' or len(X_halluc) == 0:
       return self.eval(X_test, uncert_form)
-    post = self._augmented_posterior(X_halluc)
-    if uncert_form == 'covar':
-      return self._eval_covar_on(post, X_test)
-    return self._eval_on(post, X_test, True)
+    with self._hallucinated(X_halluc) as post:
+      if uncert_form == 'covar':
+        return self._eval_covar_on(post, X_test)
+      return self._eval_on(post, X_test, True)
 
   # -- fused acquisition scoring (the body of gpb_acquisitions' objectives + np.argmax) -----------
   def _device_posterior(self, halluc=None):
@@ -317,18 +393,18 @@ class GP(object):
   def _fused_score(self, acq, pts, halluc=None, test_desc=None, mean_const=None,
                    want_scores=False):
     """ One dfb_score_argmax call: returns (best_score, best_index, scores or None). """
-    post = self._device_posterior(halluc)
     mc = self._mean_const if mean_const is None else mean_const
     if mc is None:
       raise NotImplementedError('Fused acquisition scoring needs a constant mean function '
                                 '(what GPFitter.build_gp produces, gp_core.py:527-530).')
-    if test_desc is not None:
-      post.set_test_kernel(test_desc)
-    try:
-      return post.score_argmax(acq, self._test_matrix(pts), mean_const=mc, want_scores=want_scores)
-    finally:
+    with self._hallucinated([] if halluc is None else halluc) as post:
       if test_desc is not None:
-        post.set_test_kernel(None)
+        post.set_test_kernel(test_desc)
+      try:
+        return post.score_argmax(acq, self._test_matrix(pts), mean_const=mc, want_scores=want_scores)
+      finally:
+        if test_desc is not None:
+          post.set_test_kernel(None)
 
   def _group_test_descriptor(self, add_kernel, kernel_j, group_j, train_dim):
     """ K_*j = scale * k_j(X*_j, X[:, g_j]) (gpb_acquisitions.py:166-170): candidates have d_j
@@ -382,7 +458,8 @@ class GP(object):
     """ gp_core.py:256-261 """
     if len(X_halluc) == 0:
       return self.draw_samples(num_samples, X_test)
-    return self._draw_samples_on(self._augmented_posterior(X_halluc), num_samples, X_test)
+    with self._hallucinated(X_halluc) as post:
+      return self._draw_samples_on(post, num_samples, X_test)
 
   def __str__(self):
     return '%s, noise-var=%0.3f (n=%d)' % (self._child_str(), self.noise_var, len(self.Y))
@@ -390,7 +467,17 @@ class GP(object):
   def _child_str(self):
     return 'B200-GP %s' % (str(self.kernel))
 
-  # copies share the (immutable) device posterior
+  # Copies share the device posterior; a shared posterior is never extended for good (add_data on
+  # either copy rebuilds into a fresh one), only temporarily for hallucinations (restored on exit).
+  def __copy__(self):
+    cls = self.__class__
+    new = cls.__new__(cls)
+    new.__dict__.update(self.__dict__)
+    if getattr(self, '_post', None) is not None:
+      self._post_shared = True
+      new._post_shared = True
+    return new
+
   def __deepcopy__(self, memo):
     import copy as _copy
     cls = self.__class__
@@ -399,6 +486,11 @@ class GP(object):
     for k, v in self.__dict__.items():
       if k == '_post':
         new.__dict__[k] = v
+      elif k == '_post_token':
+        new.__dict__[k] = None     # ids of the deep-copied kernel / mean differ: first add_data rebuilds
       else:
         new.__dict__[k] = _copy.deepcopy(v, memo)
+    if getattr(self, '_post', None) is not None:
+      self._post_shared = True
+      new._post_shared = True
     return new

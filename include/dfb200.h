@@ -149,6 +149,20 @@ int dfb_set_train(dfb_handle* h, const double* X_dev, int64_t n, int32_t d,
  * positive definite (np.linalg.LinAlgError in stable_cholesky, general_utils.py:176-192).  */
 int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t flags,
                         double* lml_out_host);
+/* GP.add_data_multiple (gp_core.py:139-146) and the (N + q)-point factorisation of
+ * eval_with_hallucinated_observations (gp_core.py:200-206) WITHOUT the reference's full rebuild: appends q
+ * training points (X_new: q x d, y_centred_new: q) to a built posterior and re-derives only the last row block
+ * of L, the last block column of L^-T / rows of W = L^-1, alpha and the LML (Cholesky row i depends on rows
+ * <= i only).  Uses the kernel, noise_var and jitter of the last dfb_build_posterior.  Requires n + q to stay
+ * within the posterior's padded size (multiple of 128), else returns < 0 and the caller rebuilds.
+ * flags: DFB_BUILD_FULL or DFB_BUILD_NO_ALPHA, optionally | DFB_EXTEND_SAVE to snapshot what is overwritten so
+ * that dfb_restore_posterior() puts the un-extended posterior back bit for bit (hallucinations are temporary).
+ * Returns info > 0 if the extended matrix is not positive definite (with DFB_EXTEND_SAVE the old posterior is
+ * restored first; without it the posterior is invalid and must be rebuilt).  */
+#define DFB_EXTEND_SAVE 16
+int dfb_extend_posterior(dfb_handle* h, const double* X_new_dev, int64_t q, const double* y_centred_new_dev,
+                         int32_t flags, double* lml_out_host);
+int dfb_restore_posterior(dfb_handle* h);
 /* max(diag K) of the last build -- the jitter ladder's scale (general_utils.py:183-189). */
 int dfb_get_max_diag(dfb_handle* h, double* out_host);
 /* Copies of gp.L (n x n lower), gp.alpha (n), gp.K_trtr_wo_noise (n x n); any may be NULL.
