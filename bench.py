@@ -56,6 +56,16 @@ def dist_env():
 # ---------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference algorithm)
 # ---------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+  """ torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to run on all the host
+      cores, so lift the BLAS / OpenMP pools back to the core count (threadpoolctl works after import). """
+  try:
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=os.cpu_count())
+  except Exception:  # pylint: disable=broad-except
+    pass
+
+
 def cpu_threads():
   try:
     from threadpoolctl import threadpool_info
@@ -88,6 +98,7 @@ def run_reference(args):
   if rank != 0:
     return
   from dragonfly_b200 import synth_data
+  use_all_host_threads()
   w = synth_data.make_workload('headline_hartmann6_matern_ei', n_train=args.n_train,
                                n_cand=args.cpu_sample)
   O, gp, build_s = build_oracle_gp(w)
@@ -230,6 +241,11 @@ def run_ours(args):
   assert torch.cuda.is_available(), 'bench.py needs a CUDA device: there is no CPU fallback'
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
+  # stdout carries exactly one JSON line: native libraries that write to fd 1 (NCCL prints its version banner
+  # there) are pointed at stderr for the duration; the line itself goes to the saved descriptor.
+  sys.stdout.flush()
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
   M = args.cands_per_gpu
@@ -447,6 +463,7 @@ def run_ours(args):
       'posterior_update': upd,
     }
     if not args.no_cpu_baseline:
+      use_all_host_threads()
       wc = synth_data.make_workload('headline_hartmann6_matern_ei', n_train=args.n_train,
                                     n_cand=args.cpu_sample)
       O, ogp, build_s = build_oracle_gp(wc)
@@ -456,7 +473,9 @@ def run_ours(args):
         'sample': '%d candidates in chunks of %d through the faithful gp.eval(chunk, "std") '
                   'restatement + EI + arg-max (%.1f s); posterior build %.2f s excluded' % (
                       args.cpu_sample, CPU_CHUNK, dt, build_s)}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
+  os.close(json_fd)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -20,6 +20,8 @@ DFB_DEVICE, DFB_HOST = 0, 1
 DFB_ACQ_MEAN, DFB_ACQ_UCB, DFB_ACQ_EI, DFB_ACQ_PI, DFB_ACQ_TTEI = 0, 1, 2, 3, 4
 DFB_BUILD_FULL, DFB_BUILD_LML_ONLY, DFB_BUILD_NO_ALPHA = 0, 1, 2
 DFB_EXTEND_SAVE = 16
+DFB_MOO_MAX_OBJ = 8
+DFB_MOO_LIN_UCB, DFB_MOO_TCH_UCB, DFB_MOO_LIN_VAL, DFB_MOO_TCH_VAL = 0, 1, 2, 3
 
 
 class FactorDesc(C.Structure):
@@ -43,6 +45,11 @@ class KernelDesc(C.Structure):
 class AcqDesc(C.Structure):
   _fields_ = [('kind', C.c_int32), ('reserved', C.c_int32), ('beta', C.c_double),
               ('best', C.c_double), ('ref_mean', C.c_double), ('ref_std', C.c_double)]
+
+
+class MooDesc(C.Structure):
+  _fields_ = [('kind', C.c_int32), ('n_obj', C.c_int32), ('beta', C.c_double),
+              ('weight', C.c_double * DFB_MOO_MAX_OBJ), ('ref', C.c_double * DFB_MOO_MAX_OBJ)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against include/dfb200.h
@@ -71,6 +78,8 @@ PROTOTYPES = {
   'dfb_eval_covar': (C.c_int, [_P, _P, _I64, _I32, _D, _P, _P]),
   'dfb_score_argmax': (C.c_int, [_P, C.POINTER(AcqDesc), _P, _I64, _I32, _I32, _D, _P,
                                  C.POINTER(_D), C.POINTER(_I64)]),
+  'dfb_moo_score_argmax': (C.c_int, [_P, C.POINTER(MooDesc), C.POINTER(_P), C.POINTER(_P), _I64, _P,
+                                     C.POINTER(_D), C.POINTER(_I64)]),
   'dfb_kernel_matrix': (C.c_int, [_P, C.POINTER(KernelDesc), _P, _I64, _I32, _P, _I64, _I32, _P]),
   'dfb_ts_workspace_bytes': (C.c_size_t, [_I64, _I64]),
   'dfb_set_ts_workspace': (C.c_int, [_P, _P, C.c_size_t, _I64]),

@@ -864,6 +864,29 @@ int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, i
   return 0;
 }
 
+int dfb_moo_score_argmax(dfb_handle* h, const dfb_moo_desc* desc, const double* const* a_dev,
+                         const double* const* b_dev, int64_t m, double* scores_dev,
+                         double* best_score_host, int64_t* best_index_host) {
+  DFB_TRY(need(h, true, false, false, false, false));
+  if (desc == nullptr || a_dev == nullptr || m < 1) { set_error("bad moo arguments (m = %lld)", (long long)m); return -1; }
+  if (desc->kind < DFB_MOO_LIN_UCB || desc->kind > DFB_MOO_TCH_VAL) { set_error("unknown scalarisation kind %d", desc->kind); return -1; }
+  if (desc->n_obj < 1 || desc->n_obj > DFB_MOO_MAX_OBJ) { set_error("n_obj = %d outside [1, %d]", desc->n_obj, DFB_MOO_MAX_OBJ); return -1; }
+  const bool ucb = desc->kind == DFB_MOO_LIN_UCB || desc->kind == DFB_MOO_TCH_UCB;
+  for (int k = 0; k < desc->n_obj; k++)
+    if (a_dev[k] == nullptr || (ucb && (b_dev == nullptr || b_dev[k] == nullptr))) { set_error("objective %d: NULL vector", k); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  DFB_TRY(launch_reset_best(h));
+  DFB_TRY(launch_moo(h, *desc, a_dev, ucb ? b_dev : nullptr, m, scores_dev));
+  double bs = 0.0;
+  int64_t bi = -1;
+  DFB_CUDA_OK(cudaMemcpyAsync(&bs, h->best_score, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaMemcpyAsync(&bi, h->best_index, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (best_score_host) *best_score_host = bs;
+  if (best_index_host) *best_index_host = bi;
+  return 0;
+}
+
 int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,
                       int32_t d1, const double* X2_dev, int64_t n2, int32_t d2, double* K_dev) {
   DFB_TRY(need(h, true, false, false, false, false));

@@ -824,6 +824,69 @@ argmax_merge_kernel(const double* __restrict__ blk_score, const int64_t* __restr
   }
 }
 
+// ---- multi-objective scalarisations + arg-max        dragonfly/opt/multiobjective_gpb_acquisitions.py ----
+// One thread per candidate combines the objectives' (mu, sd) -- or posterior samples -- in the reference's
+// own operation order (no FMA contraction), then the same block arg-max as acq_kernel.
+struct MooArgs {
+  dfb_moo_desc d;
+  const double* a[DFB_MOO_MAX_OBJ];    // mu_k, or the sampled values v_k
+  const double* b[DFB_MOO_MAX_OBJ];    // sd_k (UCB kinds)
+};
+__device__ __forceinline__ double np_minimum(double x, double y) {   // np.minimum: NaN propagates
+  if (isnan(x)) return x;
+  if (isnan(y)) return y;
+  return x < y ? x : y;
+}
+__global__ void __launch_bounds__(256)
+moo_kernel(const MooArgs g, int64_t m, int64_t idx_base, double* __restrict__ score_out, double* blk_score,
+           int64_t* blk_index) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double score = 0.0;
+  int64_t index = -1;
+  if (i < m) {
+    const int K = g.d.n_obj;
+    if (g.d.kind == DFB_MOO_LIN_UCB) {              // :79-91
+      double mu_tot = 0.0, s2_tot = 0.0;
+      for (int k = 0; k < K; k++) {
+        const double w = g.d.weight[k], sd = g.b[k][i];
+        mu_tot = __dadd_rn(mu_tot, __dmul_rn(g.a[k][i], w));
+        s2_tot = __dadd_rn(s2_tot, __dmul_rn(__dmul_rn(sd, sd), __dmul_rn(w, w)));
+      }
+      score = __dadd_rn(mu_tot, __dmul_rn(g.d.beta, sqrt(s2_tot)));
+    } else if (g.d.kind == DFB_MOO_TCH_UCB) {       // :94-107 (takes the square root of the std, as written there)
+      score = __longlong_as_double(0x7ff0000000000000ll);
+      for (int k = 0; k < K; k++) {
+        const double ucb = __dadd_rn(__dadd_rn(g.a[k][i], __dmul_rn(g.d.beta, sqrt(g.b[k][i]))), -g.d.ref[k]);
+        score = np_minimum(score, ucb / g.d.weight[k]);
+      }
+    } else if (g.d.kind == DFB_MOO_LIN_VAL) {       // :31-39
+      for (int k = 0; k < K; k++) score = __dadd_rn(score, __dmul_rn(g.a[k][i], g.d.weight[k]));
+    } else {                                        // DFB_MOO_TCH_VAL :56-65
+      score = __longlong_as_double(0x7ff0000000000000ll);
+      for (int k = 0; k < K; k++)
+        score = np_minimum(score, __dadd_rn(g.a[k][i], -g.d.ref[k]) / g.d.weight[k]);
+    }
+    if (score_out != nullptr) score_out[i] = score;
+    index = idx_base + i;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double so = __shfl_xor_sync(0xffffffffu, score, o);
+    const int64_t io = __shfl_xor_sync(0xffffffffu, index, o);
+    if (better(so, io, score, index)) { score = so; index = io; }
+  }
+  __shared__ double ss[8];
+  __shared__ int64_t si[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ss[warp] = score; si[warp] = index; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(ss[w], si[w], score, index)) { score = ss[w]; index = si[w]; }
+    blk_score[blockIdx.x] = score;
+    blk_index[blockIdx.x] = index;
+  }
+}
+
 __global__ void reset_best_kernel(double* best_score, int64_t* best_index) {
   *best_score = 0.0;
   *best_index = -1;
@@ -1393,6 +1456,30 @@ int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const d
   if (do_argmax) {
     argmax_merge_kernel<<<1, 256, 0, h->stream>>>(h->blk_score, h->blk_index, (int)blocks,
                                                   h->best_score, h->best_index);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// scores m candidates in slices of the handle's chunk (the block arg-max scratch is sized for one chunk)
+int launch_moo(dfb_handle* h, const dfb_moo_desc& d, const double* const* a, const double* const* b, int64_t m,
+               double* scores) {
+  for (int64_t c0 = 0; c0 < m; c0 += h->chunk) {
+    const int64_t mc = (m - c0 < h->chunk) ? (m - c0) : h->chunk;
+    MooArgs g;
+    memset(&g, 0, sizeof(g));
+    g.d = d;
+    for (int k = 0; k < d.n_obj; k++) {
+      g.a[k] = a[k] + c0;
+      g.b[k] = (b != nullptr && b[k] != nullptr) ? b[k] + c0 : nullptr;
+    }
+    const unsigned blocks = (unsigned)((mc + 255) / 256);
+    moo_kernel<<<blocks, 256, 0, h->stream>>>(g, mc, c0, scores ? scores + c0 : nullptr, h->blk_score, h->blk_index);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+    argmax_merge_kernel<<<1, 256, 0, h->stream>>>(h->blk_score, h->blk_index, (int)blocks, h->best_score,
+                                                  h->best_index);
     h->launches++;
     DFB_CUDA_OK(cudaGetLastError());
   }

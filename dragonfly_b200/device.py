@@ -256,6 +256,30 @@ class DevicePosterior(object):
                       'dfb_ts_draws')
     return info, out, mx.value
 
+  def moo_score_argmax(self, kind, a_list, b_list, weights, refs=None, beta=0.0, want_scores=False):
+    """ dfb_moo_score_argmax: scalarise n_obj objectives' device vectors and take the arg-max.
+        a_list / b_list: CUDA fp64 tensors (mu_k or sampled values; sd_k or None).
+        Returns (best_score, best_index, scores tensor or None). """
+    K = len(a_list)
+    d = _lib.MooDesc()
+    d.kind, d.n_obj, d.beta = int(kind), K, float(beta)
+    for k in range(K):
+      d.weight[k] = float(weights[k])
+      d.ref[k] = float(refs[k]) if refs is not None else 0.0
+    a_t = [_dev_f64(a, self.device) for a in a_list]
+    b_t = [_dev_f64(b, self.device) for b in b_list] if b_list is not None else None
+    m = int(a_t[0].shape[0])
+    assert all(int(t.shape[0]) == m for t in a_t) and (b_t is None or all(int(t.shape[0]) == m for t in b_t))
+    PtrArr = C.c_void_p * K
+    a_ptrs = PtrArr(*[t.data_ptr() for t in a_t])
+    b_ptrs = PtrArr(*[t.data_ptr() for t in b_t]) if b_t is not None else None
+    sc = torch.empty((m,), dtype=torch.float64, device=self.device) if want_scores else None
+    bs, bi = C.c_double(0.0), C.c_int64(-1)
+    _lib.check(self.lib.dfb_moo_score_argmax(
+        self.h, C.byref(d), a_ptrs, b_ptrs, m, C.c_void_p(sc.data_ptr()) if want_scores else None,
+        C.byref(bs), C.byref(bi)), 'dfb_moo_score_argmax')
+    return bs.value, bi.value, sc
+
   def launch_count(self):
     return int(self.lib.dfb_launch_count(self.h))
 

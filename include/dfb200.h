@@ -113,6 +113,21 @@ typedef struct dfb_acq_desc {
   double  ref_std;     /* TTEI */
 } dfb_acq_desc;
 
+/* ---- multi-objective scalarisation --------- dragonfly/opt/multiobjective_gpb_acquisitions.py */
+#define DFB_MOO_MAX_OBJ 8
+#define DFB_MOO_LIN_UCB 0   /* sum_k w_k mu_k + beta sqrt(sum_k w_k^2 sd_k^2)                     :79-91  */
+#define DFB_MOO_TCH_UCB 1   /* min_k (mu_k + beta sqrt(sd_k) - ref_k) / w_k  (sqrt of the std, as written) :94-107 */
+#define DFB_MOO_LIN_VAL 2   /* sum_k w_k v_k,  v = one posterior sample per objective (lin_ts)   :19-41  */
+#define DFB_MOO_TCH_VAL 3   /* min_k (v_k - ref_k) / w_k                             (tch_ts)   :44-68  */
+
+typedef struct dfb_moo_desc {
+  int32_t kind;
+  int32_t n_obj;                       /* 1 .. DFB_MOO_MAX_OBJ */
+  double  beta;                        /* UCB kinds: beta_th = sqrt(0.2 d log(2 d t + 1)) (:73-75) */
+  double  weight[DFB_MOO_MAX_OBJ];     /* anc_data.obj_weights */
+  double  ref[DFB_MOO_MAX_OBJ];        /* anc_data.reference_point (Tchebychev kinds) */
+} dfb_moo_desc;
+
 /* ---- build flags ----------------------------------------------------------------------------- */
 #define DFB_BUILD_FULL      0   /* L, W = L^-1, alpha, LML  (GP.build_posterior, gp_core.py:155-163) */
 #define DFB_BUILD_LML_ONLY  1   /* L and LML only           (GPFitter._tuning_objective, :551-563)   */
@@ -196,6 +211,15 @@ int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, d
 int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, int64_t m,
                      int32_t dc, int32_t space, double mean_const, double* scores,
                      double* best_score_host, int64_t* best_index_host);
+
+/* The multi-objective acquisitions' scalarisation + random_maximise's arg-max (np.argmax order) over m
+ * candidates that n_obj GPs have already scored with dfb_eval on the device: a_dev[k] = mu_k (UCB kinds) or the
+ * sampled values v_k (VAL kinds), b_dev[k] = sd_k (UCB kinds; NULL otherwise).  a_dev / b_dev are HOST arrays of
+ * n_obj device pointers (each m doubles); scores_dev (m) may be NULL.  The handle supplies stream and scratch
+ * only (any handle with a workspace on the same device).  */
+int dfb_moo_score_argmax(dfb_handle* h, const dfb_moo_desc* desc, const double* const* a_dev,
+                         const double* const* b_dev, int64_t m, double* scores_dev,
+                         double* best_score_host, int64_t* best_index_host);
 
 /* Kernel.__call__(X1, X2) (kernel.py:72-83): the n1 x n2 Gram matrix, device pointers. */
 int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,

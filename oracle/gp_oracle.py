@@ -468,3 +468,47 @@ def rand_exp_sampling_probs(lmls):
   lmls = np.asarray(lmls, dtype=np.float64)
   w = np.exp(lmls - lmls.max())
   return w / w.sum()
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-objective scalarisations                dragonfly/opt/multiobjective_gpb_acquisitions.py
+# ---------------------------------------------------------------------------------------------
+def moo_ucb_beta_th(dim, time_step):
+  """ multiobjective_gpb_acquisitions.py:73-75 """
+  return np.sqrt(0.2 * dim * np.log(2 * dim * time_step + 1))
+
+
+def moo_lin_ucb(mus, sds, weights, beta_th):
+  """ :79-91 -- mu_tot + beta_th sqrt(sigma2_tot), accumulated objective by objective. """
+  mu_tot = 0.0
+  sigma2_tot = 0.0
+  for mu, sigma, weight in zip(mus, sds, weights):
+    mu_tot += mu * weight
+    sigma2_tot += sigma * sigma * weight**2
+  return mu_tot + beta_th * np.sqrt(sigma2_tot)
+
+
+def moo_tch_ucb(mus, sds, weights, refs, beta_th):
+  """ :94-107 -- the reference unpacks eval(..., 'std') into `mu, sigma2` and takes np.sqrt of it:
+      the square root of the STANDARD DEVIATION enters the UCB.  Restated as written. """
+  ret = np.asarray([np.inf for _ in range(len(mus[0]))])
+  for mu, sigma2, weight, ref in zip(mus, sds, weights, refs):
+    ucb = mu + beta_th * np.sqrt(sigma2) - ref
+    ret = np.minimum(ret, ucb / weight)
+  return ret
+
+
+def moo_lin_vals(samples, weights):
+  """ :31-39 (lin_ts): s = sum_k sample_k * w_k """
+  s = 0.0
+  for sample, weight in zip(samples, weights):
+    s += sample * weight
+  return s
+
+
+def moo_tch_vals(samples, weights, refs):
+  """ :56-65 (tch_ts): s = min_k (sample_k - ref_k) / w_k """
+  s = np.full((len(samples[0]), ), np.inf)
+  for sample, weight, ref in zip(samples, weights, refs):
+    s = np.minimum(s, (sample - ref) / weight)
+  return s

@@ -285,3 +285,24 @@ def test_extension_at_the_metric_n(B):
   # K alpha + noise alpha = y_c at the appended points
   mu_t, _ = gp.eval(X[n0:], 'none')
   close(mu_t - m0 + nv * gp.alpha[n0:], Y[n0:] - m0, atol=1e-9)
+
+
+def test_add_data_against_the_reference_golden(B):
+  """ tests/golden/incremental.npz: the UNMODIFIED reference after add_data_multiple + 2 x add_data_single
+      (it rebuilds three times); the device extends in place three times. """
+  from conftest import load_golden
+  g = load_golden('incremental')
+  n0 = int(g['n0'])
+  gp = B.gp_core.GP(g['X'][:n0], g['Y'][:n0], B.kernel.MaternKernel(6, 2.5, float(g['scale']), g['bws']),
+                    B.gp_core.ConstantMean(float(g['mean_const'])), float(g['noise_var']))
+  post = gp._post
+  gp.add_data_multiple(list(g['X'][n0:n0 + 4]), list(g['Y'][n0:n0 + 4]))
+  gp.add_data_single(g['X'][n0 + 4], g['Y'][n0 + 4])
+  gp.add_data_single(g['X'][n0 + 5], g['Y'][n0 + 5])
+  assert gp._post is post and gp.num_tr_data == n0 + 6
+  close(gp.L, g['L'], rtol=1e-8, atol=1e-10)
+  close(gp.alpha, g['alpha'], rtol=1e-7, atol=1e-8)
+  close(gp.compute_log_marginal_likelihood(), g['lml'], rtol=1e-10)
+  mu, sd = gp.eval(g['C'], 'std')
+  close(mu, g['mu'], atol=MU_TOL)
+  close(sd ** 2, g['sd'] ** 2, atol=VAR_TOL)

@@ -241,3 +241,70 @@ def test_lml_grid_and_sampling_weights():
   close(lmls, g['lmls'], rtol=1e-11)
   w = O.rand_exp_sampling_probs(lmls)
   assert abs(w.sum() - 1) < 1e-12 and w.argmax() == np.argmax(g['lmls'])
+
+
+# ---- multi-objective scalarisations and add_data ----------------------------------------
+def _moo_oracle_gps(g):
+  gp1 = O.OGP(g['X'], g['Y1'], O.OMaternKernel(6, 2.5, float(g['scale1']), g['bws1']),
+              const_mean(float(g['mean1'])), float(g['noise1']))
+  gp2 = O.OGP(g['X'], g['Y2'], O.OSEKernel(6, float(g['scale2']), g['bws2']),
+              const_mean(float(g['mean2'])), float(g['noise2']))
+  return [gp1, gp2]
+
+
+def test_moo_scalarisations_match_reference():
+  """ multiobjective_gpb_acquisitions.py:79-107 on the reference's own (mu, sigma). """
+  g = load_golden('moo')
+  gps = _moo_oracle_gps(g)
+  beta = O.moo_ucb_beta_th(6, int(g['t']))
+  assert beta == float(g['beta'])
+  mus, sds = zip(*[gp.eval(g['C'], 'std') for gp in gps])
+  lin = O.moo_lin_ucb(mus, sds, g['weights'], beta)
+  tch = O.moo_tch_ucb(mus, sds, g['weights'], g['refs'], beta)
+  close(lin, g['lin_ucb_scores'], rtol=1e-10, atol=1e-11)
+  close(tch, g['tch_ucb_scores'], rtol=1e-10, atol=1e-11)
+  assert O.np_argmax_first(lin) == int(np.argmax(g['lin_ucb_scores']))
+  assert O.np_argmax_first(tch) == int(np.argmax(g['tch_ucb_scores']))
+
+
+def test_moo_end_to_end_recommendations():
+  """ The reference's recommendations under np.random.seed(9): candidates from np.random.random, then (TS)
+      one np.random.normal draw per objective, scalarise, arg-max. """
+  g = load_golden('moo')
+  gps = _moo_oracle_gps(g)
+  beta = float(g['beta'])
+  bounds = [[0, 1]] * 6
+  for name in ['lin_ucb', 'tch_ucb']:
+    np.random.seed(9)
+    pts = O.map_to_bounds(np.random.random((1500, 6)), bounds)
+    mus, sds = zip(*[gp.eval(pts, 'std') for gp in gps])
+    sc = (O.moo_lin_ucb(mus, sds, g['weights'], beta) if name == 'lin_ucb'
+          else O.moo_tch_ucb(mus, sds, g['weights'], g['refs'], beta))
+    assert (pts[O.np_argmax_first(sc)] == g['e2e_%s_point' % name]).all()
+  for name, halluc in [('lin_ts', None), ('tch_ts', None), ('lin_ts_halluc', g['Xh'])]:
+    np.random.seed(9)
+    pts = O.map_to_bounds(np.random.random((300, 6)), bounds)
+    samples = []
+    for gp in gps:
+      U = np.random.normal(size=(300, 1))
+      samples.append(gp.draw_samples_with_normals(pts, U, None if halluc is None else list(halluc)).ravel())
+    sc = (O.moo_tch_vals(samples, g['weights'], g['refs']) if name == 'tch_ts'
+          else O.moo_lin_vals(samples, g['weights']))
+    assert (pts[O.np_argmax_first(sc)] == g['e2e_%s_point' % name]).all()
+
+
+def test_add_data_matches_reference():
+  """ gp_core.py:135-146: the reference after add_data_multiple + 2 x add_data_single. """
+  g = load_golden('incremental')
+  n0 = int(g['n0'])
+  gp = O.OGP(g['X'][:n0], g['Y'][:n0], O.OMaternKernel(6, 2.5, float(g['scale']), g['bws']),
+             const_mean(float(g['mean_const'])), float(g['noise_var']))
+  gp.add_data_multiple(list(g['X'][n0:n0 + 4]), list(g['Y'][n0:n0 + 4]))
+  gp.add_data_multiple([g['X'][n0 + 4]], [g['Y'][n0 + 4]])
+  gp.add_data_multiple([g['X'][n0 + 5]], [g['Y'][n0 + 5]])
+  close(gp.L, g['L'], rtol=1e-10, atol=1e-12)
+  close(gp.alpha, g['alpha'], rtol=1e-8, atol=1e-9)
+  close(gp.compute_log_marginal_likelihood(), g['lml'], rtol=1e-12)
+  mu, sd = gp.eval(g['C'], 'std')
+  close(mu, g['mu'], atol=1e-11)
+  close(sd ** 2, g['sd'] ** 2, atol=1e-11)
