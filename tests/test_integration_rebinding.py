@@ -37,6 +37,13 @@ for prop in ['L', 'alpha', 'K_trtr_wo_noise']:
 for ns in ('asy', 'syn', 'seq'):
   for acq in ('ucb', 'ei', 'pi', 'ttei', 'ts', 'add_ucb'):
     setattr(getattr(ref_acq, ns), acq, getattr(getattr(b200_acq, ns), acq))
+import dragonfly.opt.multiobjective_gpb_acquisitions as ref_moo
+from dragonfly_b200 import multiobjective_gpb_acquisitions as b200_moo
+for ns in ('asy', 'seq'):
+  for acq in ('lin_ucb', 'tch_ucb', 'lin_ts', 'tch_ts'):
+    assert hasattr(getattr(ref_moo, ns), acq)
+    setattr(getattr(ref_moo, ns), acq, getattr(getattr(b200_moo, ns), acq))
+assert ref_moo.asy.lin_ucb is b200_moo.mo_lin_asy_ucb and vars(ref_moo.syn) == vars(b200_moo.syn) == {}
 X = np.random.rand(6, 2); Y = np.random.rand(6)
 gp = ref_core.GP(X, Y, SEKernel(2, 1.0, [0.5, 0.5]), lambda x: np.zeros(len(x)), 0.1, build_posterior=False)
 assert gp.L is None and gp.alpha is None and gp.num_tr_data == 6

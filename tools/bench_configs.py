@@ -110,4 +110,60 @@ lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps[:2], layout)
 t0 = time.perf_counter(); lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps, layout, post=post); dt = time.perf_counter() - t0
 out['hp_grid_N5000'] = dict(lml_per_s=len(hps) / dt, ms_per_lml=1e3 * dt / len(hps), finite=bool(np.isfinite(lm).all()))
 print('hp', out['hp_grid_N5000'], flush=True)
+
+# multi-objective: 2 objectives on the C2 geometry (N=2000), linear and Tchebychev UCB scalarisations, device candidates
+def moo():
+  from dragonfly_b200 import multiobjective_gpb_acquisitions as M, _lib
+  w = synth_data.make_workload('c2_hartmann6_matern_ucb', n_cand=1000000 // scale)
+  k = w['kernel']
+  Y2 = -np.sum((w['X'] - 0.4) ** 2, axis=1)
+  gps = [gp_core.GP(w['X'], w['Y'], kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                    gp_core.ConstantMean(w['mean_const']), w['noise_var']),
+         gp_core.GP(w['X'], Y2, kernel.SEKernel(6, float(Y2.var()), [0.35] * 6),
+                    gp_core.ConstantMean(float(np.median(Y2))), 0.01 * float(Y2.var()))]
+  cd = torch.from_numpy(w['candidates']).cuda()
+  beta = float(M._get_ucb_beta_th(6, 2000))
+  res = {}
+  for name, kind in [('lin_ucb', _lib.DFB_MOO_LIN_UCB), ('tch_ucb', _lib.DFB_MOO_TCH_UCB)]:
+    def run():
+      mus, sds = zip(*[gp.eval(cd, uncert_form='std') for gp in gps])
+      return gps[0]._post.moo_score_argmax(kind, list(mus), list(sds), [0.6, 0.4], [0.1, -1.0], beta)
+    dt, r = timeit(run)
+    res[name] = dict(cands_per_s=len(cd) / dt, argmax=int(r[1]), objectives=2,
+                     note='fp64 dfb_eval per objective (exact mu, sigma) + one dfb_moo_score_argmax')
+  return res
+out['moo_2obj_N2000'] = moo()
+print('moo', out['moo_2obj_N2000'], flush=True)
+
+
+# incremental posterior update at the metric's N: one new observation, and 4 hallucinated points around a scoring call
+def incremental():
+  w = synth_data.make_workload('headline_hartmann6_matern_ei', n_cand=200000 // scale)
+  k = w['kernel']
+  X, Y = w['X'], w['Y']
+  gp = gp_core.GP(X[:4995], Y[:4995], kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                  gp_core.ConstantMean(w['mean_const']), w['noise_var'])
+  res = {}
+  ts = []
+  for i in range(4995, 5000):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    gp.add_data_single(X[i], Y[i])
+    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+  res['add_data_single_ms'] = [1e3 * t for t in ts]
+  dt, _ = timeit(lambda: gp_core.GP(X, Y, gp.kernel, gp.mean_func, w['noise_var']))
+  res['full_build_ms'] = 1e3 * dt
+  cd = torch.from_numpy(w['candidates']).cuda()
+  acq = device.make_acq_desc('ucb', beta=float(A._get_ucb_beta_th(6, 5000)))
+  Xh = list(np.random.RandomState(3).random_sample((4, 6)))
+  for inc in (True, False):
+    gp.incremental_updates = inc
+    dt, r = timeit(lambda: gp._fused_score(acq, cd, halluc=Xh))
+    res['score_with_4_hallucinations_ms_%s' % ('in_place' if inc else 'fresh_build')] = 1e3 * dt
+    res['argmax_%s' % ('in_place' if inc else 'fresh_build')] = int(r[1])
+  dt, _ = timeit(lambda: gp._fused_score(acq, cd))
+  res['score_without_hallucinations_ms'] = 1e3 * dt
+  res['candidates'] = len(cd)
+  return res
+out['incremental_N5000'] = incremental()
+print('inc', out['incremental_N5000'], flush=True)
 json.dump(out, open('gpurun_out/bench_configs.json', 'w'), indent=1)
