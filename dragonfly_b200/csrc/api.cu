@@ -184,22 +184,82 @@ static int ensure_test_scaled(dfb_handle* h) {
 
 // The blocked right-looking factorisation of the tall matrix [A ; I ; y^T] (see gemm.cuh):
 // top -> L, bottom -> L^-T, y row -> (L^-1 y)^T.
+//
+// Schedule: chol_diag is a one-CTA, latency-bound kernel (~0.1 ms x npad/128 steps), so the plain
+// step-after-step order leaves 147 SMs idle for a third of the build.  With look-ahead the trailing update of
+// step k is split: the column of the NEXT panel (block k+1) is updated first on the critical-path stream, so
+// chol_diag(k+1) and the panel solve of step k+1 run while the bulk of update k (column blocks >= k+2) is still
+// in flight on a second stream.
+//   hi:  chol(k) panel(k) [P_k] wait(R_k-1) next(k)  chol(k+1) panel(k+1) [P_k+1] wait(R_k) next(k+1) ...
+//   lo:                   wait(P_k) rest(k) [R_k]                         wait(P_k+1) rest(k+1) [R_k+1]
+// next(k) and rest(k-1) both accumulate into column block k+1, hence wait(R_k-1); rest(k) after rest(k-1) by
+// stream order.  The arithmetic per tile is unchanged (same kernel, same k-order): results are bit-identical
+// to the single-stream schedule.
+struct StreamSwap {
+  dfb_handle* h;
+  cudaStream_t user;
+  explicit StreamSwap(dfb_handle* hh) : h(hh), user(hh->stream) {}
+  ~StreamSwap() { h->stream = user; }
+};
+
+static int ensure_factor_streams(dfb_handle* h) {
+  if (h->fs_hi != nullptr) return 0;
+  int lo = 0, hi = 0;
+  DFB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least, hi = greatest priority
+  DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->fs_hi, cudaStreamNonBlocking, hi));
+  DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->fs_lo, cudaStreamNonBlocking, lo));
+  cudaEvent_t* evs[5] = {&h->fe_fork, &h->fe_panel, &h->fe_rest, &h->fe_join_hi, &h->fe_join_lo};
+  for (int i = 0; i < 5; i++) DFB_CUDA_OK(cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming));
+  return 0;
+}
+
 static int factorise_tall(dfb_handle* h, double* T, int64_t npad, double* Dinv, int* info,
                           bool with_bottom) {
   const int nb = (int)(npad / TILE);
+  const bool la = h->lookahead != 0 && nb >= 4;
+  StreamSwap guard(h);
+  if (la) {
+    DFB_TRY(ensure_factor_streams(h));
+    DFB_CUDA_OK(cudaEventRecord(h->fe_fork, guard.user));
+    DFB_CUDA_OK(cudaStreamWaitEvent(h->fs_hi, h->fe_fork, 0));
+    DFB_CUDA_OK(cudaStreamWaitEvent(h->fs_lo, h->fe_fork, 0));
+  }
+  bool rest_pending = false;
   for (int step = 0; step < nb; step++) {
+    if (la) h->stream = h->fs_hi;
     DFB_TRY(launch_chol_diag(h, T, npad, step, Dinv, info));
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.A = T; g.lda = npad; g.B = Dinv; g.ldb = TILE; g.D = T; g.ldd = npad;
     g.alpha = 1.0; g.mode = MODE_PANEL; g.K = TILE; g.step = step; g.nb = nb; g.info = info;
     g.skip_bottom = with_bottom ? 0 : 1;
-    DFB_TRY(launch_gemm(h, g, EPI_STORE, 2 * nb + 1 - (step + 1)));
+    const int rows = 2 * nb + 1 - (step + 1);
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, rows));
     const int ncols = nb - step - 1;
-    if (ncols > 0) {
-      g.mode = MODE_TRAIL; g.alpha = -1.0; g.B = nullptr; g.ldb = npad;
-      DFB_TRY(launch_gemm(h, g, EPI_STORE, (2 * nb + 1 - (step + 1)) * ncols));
+    if (ncols <= 0) continue;
+    g.mode = MODE_TRAIL; g.alpha = -1.0; g.B = nullptr; g.ldb = npad;
+    if (!la) {
+      DFB_TRY(launch_gemm(h, g, EPI_STORE, rows * ncols));
+      continue;
     }
+    DFB_CUDA_OK(cudaEventRecord(h->fe_panel, h->fs_hi));
+    if (rest_pending) DFB_CUDA_OK(cudaStreamWaitEvent(h->fs_hi, h->fe_rest, 0));
+    g.tr_j0 = 0; g.tr_nc = 1;                       // the next panel's column, on the critical path
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, rows));
+    if (ncols > 1) {
+      h->stream = h->fs_lo;
+      DFB_CUDA_OK(cudaStreamWaitEvent(h->fs_lo, h->fe_panel, 0));
+      g.tr_j0 = 1; g.tr_nc = ncols - 1;
+      DFB_TRY(launch_gemm(h, g, EPI_STORE, rows * (ncols - 1)));
+      DFB_CUDA_OK(cudaEventRecord(h->fe_rest, h->fs_lo));
+      rest_pending = true;
+    }
+  }
+  if (la) {
+    DFB_CUDA_OK(cudaEventRecord(h->fe_join_hi, h->fs_hi));
+    DFB_CUDA_OK(cudaEventRecord(h->fe_join_lo, h->fs_lo));
+    DFB_CUDA_OK(cudaStreamWaitEvent(guard.user, h->fe_join_hi, 0));
+    DFB_CUDA_OK(cudaStreamWaitEvent(guard.user, h->fe_join_lo, 0));
   }
   return 0;
 }
@@ -548,6 +608,11 @@ int dfb_create(dfb_handle** out, int device) {
 
 void dfb_destroy(dfb_handle* h) {
   if (h == nullptr) return;
+  if (h->fs_hi != nullptr) {
+    cudaStreamDestroy(h->fs_hi); cudaStreamDestroy(h->fs_lo);
+    cudaEventDestroy(h->fe_fork); cudaEventDestroy(h->fe_panel); cudaEventDestroy(h->fe_rest);
+    cudaEventDestroy(h->fe_join_hi); cudaEventDestroy(h->fe_join_lo);
+  }
   if (h->prof != nullptr) {
     for (int c = 0; c < PROF_CLASSES; c++)
       if (h->prof[c].created)
@@ -1042,6 +1107,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
     return 0;
   }
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
+  if (strcmp(name, "lookahead") == 0) { h->lookahead = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {

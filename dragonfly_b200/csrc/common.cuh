@@ -152,6 +152,11 @@ struct dfb_handle {
   int64_t n = 0, npad = 0;
   int32_t d = 0;
   double noise_plus_jitter = 0.0;
+  // look-ahead factorisation (api.cu: factorise_tall): critical path on a high-priority stream, bulk trailing
+  // updates on a second one; created on first use, destroyed with the handle
+  cudaStream_t fs_hi = nullptr, fs_lo = nullptr;
+  cudaEvent_t fe_fork = nullptr, fe_panel = nullptr, fe_rest = nullptr, fe_join_hi = nullptr, fe_join_lo = nullptr;
+  int lookahead = 1;          // option "lookahead": 0 = the single-stream schedule
   // dfb_extend_posterior / dfb_restore_posterior
   double* ext_save = nullptr;   // (2*TILE + 1) * npad + TILE doubles
   bool ext_saved = false;

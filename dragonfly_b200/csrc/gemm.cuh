@@ -43,6 +43,8 @@ struct GemmArgs {
   int lower_only;                   // GENERIC: skip tiles with cb > rb
   int step, nb;                     // PANEL / TRAIL: factorisation step and #top row blocks
   int skip_bottom;                  // PANEL / TRAIL: the L^-T rows are absent (LML-only build)
+  int tr_j0, tr_nc;                 // TRAIL: column blocks step+1+tr_j0 .. +tr_nc-1 only (tr_nc = 0: all of them) --
+                                    // the look-ahead schedule updates the next panel's column first
   double* partial; int64_t ld_partial;   // SUMSQ output [n_rb][ld_partial]
   const int* info;                  // nullable: do nothing if *info != 0 (failed factorisation)
 };
@@ -92,9 +94,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
     D = g.D + (int64_t)rbk * TILE * g.ldd + (int64_t)g.step * TILE;
     k_hi = TILE;
   } else if (g.mode == MODE_TRAIL) {
-    const int ncols = g.nb - g.step - 1;
+    const int ncols = g.tr_nc > 0 ? g.tr_nc : g.nb - g.step - 1;
     const int rbk = g.step + 1 + bid / ncols;
-    const int j = g.step + 1 + bid % ncols;
+    const int j = g.step + 1 + g.tr_j0 + bid % ncols;
     if (!tall_row_active(rbk, g.step, g.nb, g.skip_bottom)) return;
     if (rbk < g.nb && j > rbk) return;        // top part: lower triangle only
     A = g.A + (int64_t)rbk * TILE * g.lda + (int64_t)g.step * TILE;

@@ -263,6 +263,9 @@ int64_t dfb_launch_count(dfb_handle* h);
  *                 5e-9 max(1, k(x,x)) for the training kernel, else radix 128.
  *  "i8_fuse"    : 1 (default) = the K_* kernel emits the int8 digit planes directly, 0 = via an fp64 K_* buffer.
  *  "i8_ts"      : i8_impl 0 only: 1 = stage W's digits in tensor memory (tcgen05.cp), default 0.
+ *  "lookahead"  : 1 (default) = look-ahead schedule of the blocked factorisation (next panel's column updated first,
+ *                 chol_diag + panel solve of step k+1 overlap the bulk trailing update of step k on a second stream;
+ *                 bit-identical results), 0 = one stream, step after step.
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
 /* Diagnostics: "i8_sigma2_bound", "i8_ready", "i8_impl", "i8_radix256", "last_used_i8", "last_shortlist"
