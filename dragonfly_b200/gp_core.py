@@ -416,7 +416,7 @@ class GP(object):
                             train_coords=[int(g) for g in group_j], cand_coords=list(range(d_j)))
 
   # -- sampling (gp_core.py:250-261) --------------------------------------------------------------------
-  def _draw_samples_on(self, post, num_samples, X_test):
+  def _draw_samples_on(self, post, num_samples, X_test, cols=None):
     """ draw_gaussian_samples (general_utils.py:224-232) per block of <= TS_BLOCK candidates:
         L = stable_cholesky(covar) with the same jitter ladder, U = np.random.normal(size=(M, S))
         drawn ONCE from the global RNG exactly like the reference, samples = (L U)^T + mu.
@@ -428,8 +428,14 @@ class GP(object):
     M = len(Xm)
     U = np.random.normal(size=(M, int(num_samples)))
     out = np.empty((int(num_samples), M))
+    if cols is not None:
+      # multi-GPU sharding by whole blocks (gpb_acquisitions._draw_one_sample): foreign blocks stay -inf
+      assert cols[0] % post.TS_BLOCK == 0
+      out.fill(-np.inf)
     for lo in range(0, M, post.TS_BLOCK):
       hi = min(M, lo + post.TS_BLOCK)
+      if cols is not None and not (cols[0] <= lo < cols[1]):
+        continue
       xb = Xm[lo:hi]
       for s_lo in range(0, int(num_samples), 256):
         s_hi = min(int(num_samples), s_lo + 256)
@@ -447,19 +453,19 @@ class GP(object):
         out[s_lo:s_hi, lo:hi] = smp.cpu().numpy()
     return out
 
-  def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None):
-    """ gp_core.py:250-254 """
+  def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None, cols=None):
+    """ gp_core.py:250-254 (`cols`: multi-GPU block range, see _draw_samples_on) """
     if X_test is None:
       raise NotImplementedError('draw_samples from a caller-supplied (mean, covar) is host-side '
                                 'NumPy in the reference and outside the device path.')
-    return self._draw_samples_on(self._post, num_samples, X_test)
+    return self._draw_samples_on(self._post, num_samples, X_test, cols=cols)
 
-  def draw_samples_with_hallucinated_observations(self, num_samples, X_test, X_halluc):
+  def draw_samples_with_hallucinated_observations(self, num_samples, X_test, X_halluc, cols=None):
     """ gp_core.py:256-261 """
     if len(X_halluc) == 0:
-      return self.draw_samples(num_samples, X_test)
+      return self.draw_samples(num_samples, X_test, cols=cols)
     with self._hallucinated(X_halluc) as post:
-      return self._draw_samples_on(post, num_samples, X_test)
+      return self._draw_samples_on(post, num_samples, X_test, cols=cols)
 
   def __str__(self):
     return '%s, noise-var=%0.3f (n=%d)' % (self._child_str(), self.noise_var, len(self.Y))

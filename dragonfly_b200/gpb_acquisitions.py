@@ -43,12 +43,50 @@ def _check_rand_euclidean(anc_data):
   return anc_data.acq_opt_method in ['rand']
 
 
+# Multi-GPU: when torch.distributed is initialised with more than one rank, every rank runs
+# the same acquisition call in lock-step -- same seed, hence the same candidate matrix -- scores only its
+# contiguous shard of the rows on its own GPU and joins with ONE 16-byte all-gather (dist.all_reduce_argmax).
+# The recommendation is identical on every rank and to the single-process result, for any world size.
+SHARD_ACROSS_RANKS = True
+
+
+def _shard_info():
+  """ (rank, world, device for the collective's 16-byte buffers) -- (0, 1, None) when not distributed. """
+  if not SHARD_ACROSS_RANKS:
+    return 0, 1, None
+  import torch
+  import torch.distributed as tdist
+  if not (tdist.is_available() and tdist.is_initialized()) or tdist.get_world_size() < 2:
+    return 0, 1, None
+  dev = torch.device('cuda', torch.cuda.current_device()) if tdist.get_backend() == 'nccl' else None
+  return tdist.get_rank(), tdist.get_world_size(), dev
+
+
+def _sharded_argmax(scorer, n_rows, align=1):
+  """ scorer(lo, hi) -> (best_score, best_index_within_the_slice) over global rows [lo, hi); returns the
+      global arg-max index (np.argmax order).  `align` keeps shard boundaries on multiples of a block size. """
+  rank, world, dev = _shard_info()
+  if world == 1:
+    return int(scorer(0, n_rows)[1])
+  from . import dist as dfb_dist
+  n_units = (n_rows + align - 1) // align
+  u_lo, u_hi = dfb_dist.shard_bounds(n_units, rank, world)
+  lo, hi = min(u_lo * align, n_rows), min(u_hi * align, n_rows)
+  if hi > lo:
+    best, idx = scorer(lo, hi)[:2]
+    best, idx = float(best), int(idx) + lo
+  else:
+    best, idx = 0.0, -1
+  _, gidx = dfb_dist.all_reduce_argmax(best, idx, device=dev)
+  return int(gidx)
+
+
 def _fused_maximise(scorer, anc_data, bounds=None):
-  """ maximise_acquisition (:23-40) for the `rand` method: draw candidates, one device call,
+  """ maximise_acquisition (:23-40) for the `rand` method: draw candidates, one device call (per rank),
       return the arg-max point. """
   bounds = anc_data.domain.bounds if bounds is None else bounds
   rand_pts = draw_candidates(bounds, anc_data.max_evals)
-  _, idx, _ = scorer(rand_pts)
+  idx = _sharded_argmax(lambda lo, hi: scorer(rand_pts[lo:hi]), len(rand_pts))
   return rand_pts[idx]
 
 
@@ -281,11 +319,52 @@ def asy_ts(gp, anc_data):
     anc_data.max_evals = 4 * anc_data.max_evals
   halluc = _halluc_points(anc_data)
   rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
+  sample = _draw_one_sample(gp, rand_pts, halluc)
+  return rand_pts[_argmax_of_sharded_sample(sample)]
+
+
+def _ts_block(gp):
+  post = getattr(gp, '_post', None) or getattr(getattr(gp, 'mfgp', None), '_post', None)
+  return int(getattr(post, 'TS_BLOCK', 4096))
+
+
+def _ts_cols(gp, n_rows):
+  """ This rank's share [lo, hi) of the candidate rows, in whole TS blocks; None when not distributed. """
+  rank, world, _ = _shard_info()
+  if world == 1:
+    return None
+  from . import dist as dfb_dist
+  blk = _ts_block(gp)
+  b_lo, b_hi = dfb_dist.shard_bounds((n_rows + blk - 1) // blk, rank, world)
+  return (min(b_lo * blk, n_rows), min(b_hi * blk, n_rows))
+
+
+def _draw_one_sample(gp, rand_pts, halluc):
+  """ One joint posterior draw over the candidates (gp_core.py:250-261).  Under torch.distributed each rank
+      computes only its share of the independent 4096-candidate blocks -- the normals are still
+      drawn for ALL candidates so that every rank consumes the global RNG like the single-process run -- and
+      the entries of the other ranks' blocks are -inf. """
+  cols = _ts_cols(gp, len(rand_pts))
+  kw = {} if cols is None else {'cols': cols}
   if len(halluc) > 0:
-    sample = gp.draw_samples_with_hallucinated_observations(1, rand_pts, halluc).ravel()
+    return gp.draw_samples_with_hallucinated_observations(1, rand_pts, halluc, **kw).ravel()
+  return gp.draw_samples(1, rand_pts, **kw).ravel()
+
+
+def _argmax_of_sharded_sample(sample):
+  """ np.argmax of a sample vector whose foreign-shard entries are -inf, joined across ranks. """
+  rank, world, dev = _shard_info()
+  idx = int(sample.argmax())
+  if world == 1:
+    return idx
+  from . import dist as dfb_dist
+  own = np.isfinite(sample) | np.isnan(sample) | (sample == np.inf)
+  if not own.any():
+    best, idx = 0.0, -1
   else:
-    sample = gp.draw_samples(1, rand_pts).ravel()
-  return rand_pts[sample.argmax()]
+    best = float(sample[idx])
+  _, gidx = dfb_dist.all_reduce_argmax(best, idx, device=dev)
+  return int(gidx)
 
 
 def syn_ts(num_workers, list_of_gps, anc_datas):

@@ -14,7 +14,8 @@ import numpy as np
 
 from . import _lib
 from .gpb_acquisitions import (draw_candidates, _check_rand_euclidean, _halluc_points,
-                               _delegate_to_reference_maximiser)
+                               _delegate_to_reference_maximiser, _sharded_argmax, _draw_one_sample,
+                               _ts_cols, _shard_info)
 
 
 def _get_ucb_beta_th(dim, time_step):
@@ -37,13 +38,17 @@ def _mo_ucb(kind, gps, anc_data):
       return _mo_ucb_scores(kind, gps, np.asarray(x, dtype=np.float64), weights, refs, beta_th)
     return _delegate_to_reference_maximiser(acquisition, anc_data)
   rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
-  Xd, post = _device_candidates(gps, rand_pts)
-  mus, sds = [], []
-  for gp in gps:
-    mu, sd = gp.eval(Xd, uncert_form='std')       # CUDA tensors; the M x d upload happened once
-    mus.append(mu); sds.append(sd)
-  _, idx, _ = post.moo_score_argmax(kind, mus, sds, weights, refs, beta_th)
-  return rand_pts[idx]
+
+  def scorer(lo, hi):
+    """ This rank's rows (all of them in a single process): one upload, one dfb_eval per objective. """
+    Xd, post = _device_candidates(gps, rand_pts[lo:hi])
+    mus, sds = [], []
+    for gp in gps:
+      mu, sd = gp.eval(Xd, uncert_form='std')     # CUDA tensors
+      mus.append(mu); sds.append(sd)
+    return post.moo_score_argmax(kind, mus, sds, weights, refs, beta_th)
+
+  return rand_pts[_sharded_argmax(scorer, len(rand_pts))]
 
 
 def _mo_ucb_scores(kind, gps, X, weights, refs, beta_th):
@@ -72,14 +77,21 @@ def _mo_ts(kind, gps, anc_data):
     anc_data.max_evals = 4 * anc_data.max_evals
   halluc = _halluc_points(anc_data)
   rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
-  samples = []
-  for gp in gps:                                  # one joint draw per objective, in order (global RNG)
-    if len(halluc) > 0:
-      samples.append(gp.draw_samples_with_hallucinated_observations(1, rand_pts, halluc).ravel())
-    else:
-      samples.append(gp.draw_samples(1, rand_pts).ravel())
+  # one joint draw per objective, in order (global RNG); under torch.distributed each rank computes only
+  # its blocks of candidates (the same blocks for every objective)
+  samples = [_draw_one_sample(gp, rand_pts, halluc) for gp in gps]
   refs = list(anc_data.reference_point) if kind == _lib.DFB_MOO_TCH_VAL else None
-  _, idx, _ = gps[0]._post.moo_score_argmax(kind, samples, None, list(anc_data.obj_weights), refs)
+  cols = _ts_cols(gps[0], len(rand_pts))
+  lo, hi = (0, len(rand_pts)) if cols is None else cols
+  if hi > lo:
+    best, idx, _ = gps[0]._post.moo_score_argmax(kind, [v[lo:hi] for v in samples], None,
+                                                 list(anc_data.obj_weights), refs)
+    idx += lo
+  else:
+    best, idx = 0.0, -1
+  if cols is not None:
+    from . import dist as dfb_dist
+    _, idx = dfb_dist.all_reduce_argmax(best, idx, device=_shard_info()[2])
   return rand_pts[idx]
 
 

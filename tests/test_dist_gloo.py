@@ -103,3 +103,60 @@ def test_two_rank_hp_grid_gather(tmp_path):
     lmls, probs = np.load(os.path.join(str(tmp_path), 'gather_%d.npy' % r))
     assert (lmls == want).all()
     assert np.allclose(probs, w, rtol=1e-15)
+
+
+# ---- the acquisition operators themselves under two ranks (host logic; NumPy stand-in for the device scorer) ----
+def _acq_worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT)
+  from argparse import Namespace
+  import torch.distributed as dist
+  from dragonfly_b200 import gpb_acquisitions as A
+  from dragonfly_b200.domains import EuclideanDomain
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  calls = []
+
+  def scorer(pts):                                   # what gp._fused_score returns: (best, index, scores)
+    vals = np.sin(7.0 * pts[:, 0]) + pts[:, 1] ** 2
+    calls.append(len(pts))
+    i = int(np.argmax(vals))
+    return vals[i], i, None
+  anc = Namespace(domain=EuclideanDomain([[0, 1], [-1, 2]]), max_evals=1001)
+  np.random.seed(3)
+  pt = A._fused_maximise(scorer, anc)
+  # a sample vector with this rank's blocks filled in and the others at -inf (asy_ts)
+  full = np.random.RandomState(5).standard_normal(10000)
+  blk = 4096
+  lo, hi = [(0, 8192), (8192, 10000)][rank] if world == 2 else (0, 10000)
+  mine = np.full(10000, -np.inf); mine[lo:hi] = full[lo:hi]
+  ts_idx = A._argmax_of_sharded_sample(mine)
+  np.save(os.path.join(out_dir, 'acq_%d.npy' % rank), np.concatenate((pt, [calls[0], ts_idx])))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_rank_fused_maximise_equals_single_process(tmp_path):
+  """ gpb_acquisitions._fused_maximise under 2 ranks: each rank scores half of the SAME seeded candidates,
+      one 16-byte all-gather, identical recommendation on both ranks and to the single-process run. """
+  from argparse import Namespace
+  from dragonfly_b200 import gpb_acquisitions as A
+  from dragonfly_b200.domains import EuclideanDomain
+  port = 33500 + (os.getpid() % 2000)
+  mp.spawn(_acq_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  np.random.seed(3)
+  anc = Namespace(domain=EuclideanDomain([[0, 1], [-1, 2]]), max_evals=1001)
+
+  def scorer(pts):
+    vals = np.sin(7.0 * pts[:, 0]) + pts[:, 1] ** 2
+    i = int(np.argmax(vals))
+    return vals[i], i, None
+  want = A._fused_maximise(scorer, anc)               # not distributed here: scores all 1001 rows
+  want_ts = int(np.argmax(np.random.RandomState(5).standard_normal(10000)))
+  sizes = []
+  for r in range(2):
+    got = np.load(os.path.join(str(tmp_path), 'acq_%d.npy' % r))
+    assert (got[:2] == want).all()
+    assert int(got[3]) == want_ts
+    sizes.append(int(got[2]))
+  assert sorted(sizes) == [500, 501]                  # each rank scored only its shard
