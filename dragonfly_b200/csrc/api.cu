@@ -391,24 +391,33 @@ static int replay_last_block(dfb_handle* h, int32_t flags, double* lml_out_host)
                        n - m0, h->d, TILE, h->Ks, npad, n, npad, 0.0, nullptr, nullptr));
   DFB_TRY(launch_set_diag(h, h->Ks + m0, npad, 0, n - m0, h->noise_plus_jitter, 1));
   DFB_TRY(launch_set_diag(h, h->Ks + m0, npad, n - m0, TILE, 1.0, 0));
+  // The four left-looking products have 1 .. nb-1 output tiles with k-depths up to m0 ~ N: each tile's k-range is
+  // split over several CTAs (launch_gemm_splitk) so that they fill the GPU; scratch lives in the K_* chunk buffer
+  // behind the 128 rows of A.
+  const int KS = 8;
+  double* scratch = h->Ks + (int64_t)TILE * npad;
+  const bool split = step >= 2 && h->chunk >= (int64_t)TILE * (1 + KS);       // KS * 128 x npad doubles of scratch
   GemmArgs g;
   if (step > 0) {
     // P[a][i] = sum_{k <= i} A[a][k] W[i][k]
     memset(&g, 0, sizeof(g));
     g.A = h->Ks; g.lda = npad; g.B = h->W; g.ldb = npad; g.D = top_row; g.ldd = npad; g.alpha = 1.0;
     g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = step; g.K = (int)m0; g.tri = 2;
-    DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
+    if (split) DFB_TRY(launch_gemm_splitk(h, g, 4, scratch));
+    else DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
     // Wt_c[j][a] = -sum_k Wt[j][k] P[a][k]
     memset(&g, 0, sizeof(g));
     g.A = mid; g.lda = npad; g.B = top_row; g.ldb = npad; g.D = mid + m0; g.ldd = npad; g.alpha = -1.0;
     g.mode = MODE_GENERIC; g.n_rb = step; g.n_cb = 1; g.K = (int)m0;
-    DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
+    if (split) DFB_TRY(launch_gemm_splitk(h, g, 4, scratch));
+    else DFB_TRY(launch_gemm(h, g, EPI_STORE, step));
   }
   // S = A[last, last] - P P^T  (K = 0 degenerates to a copy)
   memset(&g, 0, sizeof(g));
   g.A = top_row; g.lda = npad; g.B = top_row; g.ldb = npad; g.C = h->Ks + m0; g.ldc = npad;
   g.D = top_row + m0; g.ldd = npad; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = 1; g.K = (int)m0;
-  DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
+  if (split) DFB_TRY(launch_gemm_splitk(h, g, KS, scratch));
+  else DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
   // identity in the diagonal block of L^-T
   DFB_CUDA_OK(cudaMemset2DAsync(mid + m0 * npad + m0, sizeof(double) * npad, 0, sizeof(double) * TILE, TILE, h->stream));
   DFB_TRY(launch_set_diag(h, mid, npad, m0, npad, 1.0, 0));
@@ -417,7 +426,8 @@ static int replay_last_block(dfb_handle* h, int32_t flags, double* lml_out_host)
   memset(&g, 0, sizeof(g));
   g.A = yrow; g.lda = npad; g.B = top_row; g.ldb = npad; g.C = yrow + m0; g.ldc = npad;
   g.D = yrow + m0; g.ldd = npad; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = 1; g.n_cb = 1; g.K = (int)m0;
-  DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
+  if (split) DFB_TRY(launch_gemm_splitk(h, g, KS, scratch));
+  else DFB_TRY(launch_gemm(h, g, EPI_STORE, 1));
   // replay of factorisation step nb-1
   DFB_TRY(launch_chol_diag(h, h->T, npad, step, h->Dinv, h->info));
   memset(&g, 0, sizeof(g));

@@ -45,6 +45,9 @@ struct GemmArgs {
   int skip_bottom;                  // PANEL / TRAIL: the L^-T rows are absent (LML-only build)
   int tr_j0, tr_nc;                 // TRAIL: column blocks step+1+tr_j0 .. +tr_nc-1 only (tr_nc = 0: all of them) --
                                     // the look-ahead schedule updates the next panel's column first
+  int ksplit;                       // GENERIC: > 1 = split the k-range of every tile over `ksplit` CTAs; slice s writes
+  double* part;                     //   alpha * (its partial sum) to part + s * (n_rb*128) * (n_cb*128) (compact tiles grid,
+                                    //   ld = n_cb*128) and splitk_reduce_kernel adds the slices in a fixed order (+ C)
   double* partial; int64_t ld_partial;   // SUMSQ output [n_rb][ld_partial]
   const int* info;                  // nullable: do nothing if *info != 0 (failed factorisation)
 };
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
   // ---- decode which tile this CTA owns ---------------------------------------------------------
   const int bid = blockIdx.x;
   const double* A; const double* B; const double* C = nullptr; double* D = nullptr;
-  int rb = 0, cb = 0, k_hi = g.K;
+  int rb = 0, cb = 0, k_hi = g.K, k_lo = 0;
+  int64_t ldd = g.ldd;
   if (g.mode == MODE_SCORE) {
     rb = g.n_rb - 1 - bid / g.n_cb;          // heaviest (longest k-range) row blocks first
     cb = bid % g.n_cb;
@@ -105,15 +109,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
     D = g.D + (int64_t)rbk * TILE * g.ldd + (int64_t)j * TILE;
     k_hi = TILE;
   } else {
-    rb = bid / g.n_cb;
-    cb = bid % g.n_cb;
+    const int ks = g.ksplit > 1 ? g.ksplit : 1;
+    const int tile = bid / ks, slice = bid - tile * ks;
+    rb = tile / g.n_cb;
+    cb = tile % g.n_cb;
     if (g.lower_only && cb > rb) return;
     A = g.A + (int64_t)rb * TILE * g.lda;
     B = g.B + (int64_t)cb * TILE * g.ldb;
-    if (g.C) C = g.C + (int64_t)rb * TILE * g.ldc + (int64_t)cb * TILE;
-    D = g.D + (int64_t)rb * TILE * g.ldd + (int64_t)cb * TILE;
     if (g.tri == 1) k_hi = min(g.K, (rb + 1) * TILE);
     else if (g.tri == 2) k_hi = min(g.K, (cb + 1) * TILE);
+    if (ks > 1) {
+      // slice `slice` of this tile's k-range, in multiples of the pipeline stage; empty slices store zeros
+      const int chunk = ((k_hi + ks - 1) / ks + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+      k_lo = min(k_hi, slice * chunk);
+      k_hi = min(k_hi, k_lo + chunk);
+      ldd = (int64_t)g.n_cb * TILE;
+      D = g.part + (int64_t)slice * g.n_rb * TILE * ldd + (int64_t)rb * TILE * ldd + (int64_t)cb * TILE;
+      A += k_lo; B += k_lo;
+    } else {
+      if (g.C) C = g.C + (int64_t)rb * TILE * g.ldc + (int64_t)cb * TILE;
+      D = g.D + (int64_t)rb * TILE * g.ldd + (int64_t)cb * TILE;
+    }
   }
   const int64_t lda = g.lda;
   const int64_t ldb = (g.mode == MODE_TRAIL) ? g.lda : g.ldb;
@@ -121,7 +137,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
-  const int nk = k_hi / GEMM_BK;
+  const int nk = (k_hi - k_lo) / GEMM_BK;
 
   // ---- global -> shared loader: 8 threads cover one 128 B row slab, 32 rows per pass ------------
   const int ld_row = tid >> 3;
@@ -216,13 +232,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
           v.x += cc.x;
           v.y += cc.y;
         }
-        *reinterpret_cast<double2*>(D + (int64_t)row * g.ldd + col) = v;
+        *reinterpret_cast<double2*>(D + (int64_t)row * ldd + col) = v;
       }
     }
   }
 }
 
-// Host-side launcher (defined in kernels.cu).
+// Host-side launchers (defined in kernels.cu).  launch_gemm_splitk runs a MODE_GENERIC product with every tile's
+// k-range split over `ksplit` CTAs (scratch: ksplit * n_rb*128 * n_cb*128 doubles at `part`) followed by the
+// fixed-order reduction D = C + sum_s part_s: for the skinny products of dfb_extend_posterior, whose 1..40 tiles
+// would otherwise occupy 1..40 of the 148 SMs for a k-depth of ~N.
 int launch_gemm(dfb_handle* h, const GemmArgs& g, int epi, int n_blocks);
+int launch_gemm_splitk(dfb_handle* h, GemmArgs g, int ksplit, double* part);
 
 }  // namespace dfb

@@ -1054,6 +1054,33 @@ int launch_gemm(dfb_handle* h, const GemmArgs& g, int epi, int n_blocks) {
   return 0;
 }
 
+// D[r][c] = (C ? C[r][c] : 0) + part_0[r][c] + part_1[r][c] + ...  (fixed order: deterministic)
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int ksplit, int64_t rows, int64_t cols,
+                                     const double* __restrict__ C, int64_t ldc, double* __restrict__ D, int64_t ldd) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t r = idx / cols, c = idx - r * cols;
+  double s = (C != nullptr) ? C[r * ldc + c] : 0.0;
+  for (int k = 0; k < ksplit; k++) s += part[(int64_t)k * rows * cols + idx];
+  D[r * ldd + c] = s;
+}
+
+int launch_gemm_splitk(dfb_handle* h, GemmArgs g, int ksplit, double* part) {
+  const int tiles = g.n_rb * g.n_cb;
+  if (tiles <= 0) return 0;
+  if (g.mode != MODE_GENERIC || ksplit < 2 || g.lower_only) { set_error("launch_gemm_splitk: bad arguments"); return -1; }
+  const double* C = g.C; const int64_t ldc = g.ldc;
+  double* D = g.D; const int64_t ldd = g.ldd;
+  g.C = nullptr; g.ksplit = ksplit; g.part = part;
+  { const int r = launch_gemm(h, g, EPI_STORE, tiles * ksplit); if (r != 0) return r; }
+  const int64_t rows = (int64_t)g.n_rb * TILE, cols = (int64_t)g.n_cb * TILE;
+  splitk_reduce_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, h->stream>>>(part, ksplit, rows, cols, C, ldc,
+                                                                                  D, ldd);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- TMA tensor maps + the v2 scoring kernel ---------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
