@@ -471,7 +471,9 @@ struct ChunkMode {
   bool collect;                // gather the shortlist for the exact re-score
   double margin, sd_min;       // shortlist thresholds
   const int64_t* idx_map;      // global index of each row (re-score pass), NULL = c0 + i
+  bool allow_small;            // dfb_eval of <= SMALL_EVAL_M points: row-streaming kernel instead of the tile GEMM
 };
+constexpr int64_t SMALL_EVAL_M = 16;
 
 static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, int64_t m, int32_t dc,
                       int32_t space, double mean_const, ChunkOut out, const ChunkMode& md) {
@@ -522,7 +524,15 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
                            h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
     DFB_TRY(prof_end(h, DFB_PROF_KSTAR, (double)mc));
-    if (want_std) {
+    int small_warps = 0;
+    const bool small = want_std && md.allow_small && !md.use_i8 && m <= SMALL_EVAL_M &&
+                       (int64_t)((h->n + 7) / 8 * 8) * SMALL_EVAL_M <= (int64_t)nb * Mc;
+    if (small) {
+      // the padded rows of K_* beyond mc are zero, so an 8-wide pass may run past mc (within the 128-row tile)
+      DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
+      DFB_TRY(launch_small_sumsq(h, h->W, npad, h->Ks, npad, h->n, (int)mc, h->partial, SMALL_EVAL_M, &small_warps));
+      DFB_TRY(prof_end(h, DFB_PROF_GEMM, (double)mc));
+    } else if (want_std) {
       GemmArgs g;
       memset(&g, 0, sizeof(g));
       g.A = h->W; g.lda = npad; g.B = h->Ks; g.ldb = npad; g.mode = MODE_SCORE;
@@ -556,8 +566,8 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     }
     if (want_std || do_argmax || sc_dev != nullptr) {
       DFB_TRY(prof_begin(h, DFB_PROF_ACQ));
-      DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, Mc, nb, h->kssv, mc, c0, want_std ? 1 : 0,
-                         want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map));
+      DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, small ? SMALL_EVAL_M : Mc, small ? small_warps : nb, h->kssv, mc, c0,
+                         want_std ? 1 : 0, want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map));
       if (md.collect)
         DFB_TRY(launch_collect_shortlist(h, sc_dev, sd_dev, mc, c0, md.margin, md.sd_min, xc_dev, dc,
                                          h->list_idx, h->list_X, h->list_count, SHORTLIST_CAP));
@@ -865,6 +875,7 @@ int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t spa
   const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
   ChunkMode md = {sd != nullptr, false, false, false, 0.0, 0.0, nullptr};
   md.use_i8 = (sd != nullptr) && (h->score_impl == 1) && i8_usable(h, desc);
+  md.allow_small = h->small_eval != 0;
   h->last_used_i8 = md.use_i8 ? 1 : 0;
   DFB_TRY(run_chunks(h, acq, Xc, m, dc, space, mean_const, out, md));
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1118,6 +1129,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   }
   if (strcmp(name, "kstar_fast") == 0) { h->kstar_fast = value ? 1 : 0; return 0; }
   if (strcmp(name, "lookahead") == 0) { h->lookahead = value ? 1 : 0; return 0; }
+  if (strcmp(name, "small_eval") == 0) { h->small_eval = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {

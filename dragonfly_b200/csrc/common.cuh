@@ -157,6 +157,7 @@ struct dfb_handle {
   cudaStream_t fs_hi = nullptr, fs_lo = nullptr;
   cudaEvent_t fe_fork = nullptr, fe_panel = nullptr, fe_rest = nullptr, fe_join_hi = nullptr, fe_join_lo = nullptr;
   int lookahead = 1;          // option "lookahead": 0 = the single-stream schedule
+  int small_eval = 1;         // option "small_eval": dfb_eval of <= 16 points streams W's rows (small_sumsq_kernel)
   // dfb_extend_posterior / dfb_restore_posterior
   double* ext_save = nullptr;   // (2*TILE + 1) * npad + TILE doubles
   bool ext_saved = false;

@@ -1081,6 +1081,64 @@ int launch_gemm_splitk(dfb_handle* h, GemmArgs g, int ksplit, double* part) {
   return 0;
 }
 
+// ---- |L^-1 k_*|^2 for a handful of candidates (GP.eval of 1..16 points: the sequential maximisers' one-point
+// objective, TTEI's reference arm, BOCA's fidelity scan) ---------------------------------------------------------
+// The tile kernels spend a 128-wide candidate tile (and ~0.7 ms at N = 5000: 40 CTAs with k-depths up to N) on
+// a single point.  Here one warp owns one row i of W = L^-1 at a time: v_i = sum_{k <= i} W[i][k] k_*[k] with the
+// row streamed once, coalesced (the read of W's lower triangle -- 105 MB at N = 5000 -- is the whole cost), for MC
+// candidates at once; squares accumulate per warp and acq_kernel adds the per-warp partials in index order
+// (deterministic).
+template <int MC>
+__global__ void __launch_bounds__(256)
+small_sumsq_kernel(const double* __restrict__ W, int64_t ldw, const double* __restrict__ Ks, int64_t ldk,
+                   int64_t n_rows, int c0, double* __restrict__ part, int64_t ld_part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  double vs[MC];
+#pragma unroll
+  for (int c = 0; c < MC; c++) vs[c] = 0.0;
+  for (int64_t i = warp_global; i < n_rows; i += warps_total) {
+    const double* wr = W + i * ldw;
+    double acc[MC];
+#pragma unroll
+    for (int c = 0; c < MC; c++) acc[c] = 0.0;
+    for (int64_t k = lane; k <= i; k += 32) {
+      const double w = wr[k];
+#pragma unroll
+      for (int c = 0; c < MC; c++) acc[c] = fma(w, Ks[(int64_t)(c0 + c) * ldk + k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < MC; c++) {
+      double a = acc[c];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      vs[c] = fma(a, a, vs[c]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < MC; c++) part[warp_global * ld_part + c0 + c] = vs[c];
+  }
+}
+
+int launch_small_sumsq(dfb_handle* h, const double* W, int64_t ldw, const double* Ks, int64_t ldk, int64_t n_rows,
+                       int m, double* part, int64_t ld_part, int* n_warps_out) {
+  const unsigned blocks = (unsigned)((n_rows + 7) / 8);
+  *n_warps_out = (int)blocks * 8;
+  for (int c0 = 0; c0 < m; c0 += 8) {
+    const int mc = (m - c0 < 8) ? (m - c0) : 8;
+    if (mc == 8) small_sumsq_kernel<8><<<blocks, 256, 0, h->stream>>>(W, ldw, Ks, ldk, n_rows, c0, part, ld_part);
+    else if (mc >= 5) {       // 5..7: an 8-wide pass over rows c0 .. c0+7 (rows beyond m are zero K_* rows)
+      small_sumsq_kernel<8><<<blocks, 256, 0, h->stream>>>(W, ldw, Ks, ldk, n_rows, c0, part, ld_part);
+    } else if (mc >= 3) small_sumsq_kernel<4><<<blocks, 256, 0, h->stream>>>(W, ldw, Ks, ldk, n_rows, c0, part, ld_part);
+    else if (mc == 2) small_sumsq_kernel<2><<<blocks, 256, 0, h->stream>>>(W, ldw, Ks, ldk, n_rows, c0, part, ld_part);
+    else small_sumsq_kernel<1><<<blocks, 256, 0, h->stream>>>(W, ldw, Ks, ldk, n_rows, c0, part, ld_part);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 // ---- TMA tensor maps + the v2 scoring kernel ---------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

@@ -38,6 +38,8 @@ int launch_collect_shortlist(dfb_handle* h, const double* score, const double* s
                              int64_t* list_idx, double* list_X, int* list_count, int cap);
 int launch_vec_max(dfb_handle* h, const double* v, int64_t n, double* out);
 int launch_reset_best(dfb_handle* h);
+int launch_small_sumsq(dfb_handle* h, const double* W, int64_t ldw, const double* Ks, int64_t ldk, int64_t n_rows,
+                       int m, double* part, int64_t ld_part, int* n_warps_out);
 int launch_moo(dfb_handle* h, const dfb_moo_desc& d, const double* const* a, const double* const* b, int64_t m,
                double* scores);
 int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, int64_t cols,

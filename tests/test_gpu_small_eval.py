@@ -1,0 +1,87 @@
+"""
+GP.eval of a handful of points (-m gpu): the row-streaming kernel behind dfb_eval for m <= 16 (the one-point
+objective of the sequential maximisers, TTEI's reference arm, BOCA's fidelity scan; gp_core.py:165-190) against
+the tile kernels on the same points and against the oracle / reference golden.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def B():
+  import torch
+  assert torch.cuda.is_available()
+  from dragonfly_b200 import kernel, gp_core, device, _lib, synth_data
+  from oracle import gp_oracle as O
+  return Namespace(kernel=kernel, gp_core=gp_core, device=device, lib=_lib, synth=synth_data, O=O, torch=torch)
+
+
+@pytest.mark.parametrize('n', [50, 300, 1500])
+def test_small_batches_match_tile_kernels_and_oracle(B, n):
+  w = B.synth.make_workload('c2_hartmann6_matern_ucb', n_train=n, n_cand=400)
+  k = w['kernel']
+  gp = B.gp_core.GP(w['X'], w['Y'], B.kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                    B.gp_core.ConstantMean(w['mean_const']), w['noise_var'])
+  ogp = B.O.OGP(w['X'], w['Y'], B.O.OMaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                lambda x: np.array([w['mean_const']] * len(x)), w['noise_var'])
+  C = w['candidates']
+  mu_big, sd_big = gp.eval(C, 'std')                       # 400 points: tile kernels
+  mu_o, var_o = B.O.eval_std_diag(ogp, C[:16])
+  for m in [1, 2, 3, 4, 5, 7, 8, 9, 12, 16]:
+    mu, sd = gp.eval(C[:m], 'std')
+    np.testing.assert_array_equal(mu, mu_big[:m])          # the mean comes from the same K_* kernel
+    np.testing.assert_allclose(sd ** 2, sd_big[:m] ** 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(sd ** 2, var_o[:m], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(mu, mu_o[:m], rtol=0, atol=1e-10)
+  # 17 points are back on the tile path: bit-identical to the big batch
+  mu17, sd17 = gp.eval(C[:17], 'std')
+  assert (sd17 == sd_big[:17]).all()
+  # the switch
+  gp._post.set_option('small_eval', 0)
+  mu1, sd1 = gp.eval(C[:1], 'std')
+  assert (sd1 == sd_big[:1]).all()
+  gp._post.set_option('small_eval', 1)
+  # device-tensor candidates take the same path
+  mu_d, sd_d = gp.eval(B.torch.from_numpy(C[:3]).cuda(), 'std')
+  mu_h, sd_h = gp.eval(C[:3], 'std')
+  assert (sd_d.cpu().numpy() == sd_h).all() and (mu_d.cpu().numpy() == mu_h).all()
+
+
+def test_single_points_against_the_reference_golden(B):
+  g = load_golden('c1_se')
+  gp = B.gp_core.GP(g['X'], g['Y'], B.kernel.SEKernel(2, float(g['scale']), g['bws']),
+                    B.gp_core.ConstantMean(float(g['mean_const'])), float(g['noise_var']))
+  for i in [0, 1, 17, 555]:
+    mu, sd = gp.eval(g['C'][i:i + 1], 'std')
+    assert abs(mu[0] - g['mu'][i]) <= 1e-10 and abs(sd[0] ** 2 - g['sd'][i] ** 2) <= 1e-8
+  mu, sd = gp.eval(g['C'][:11], 'std')
+  np.testing.assert_allclose(mu, g['mu'][:11], rtol=0, atol=1e-10)
+  np.testing.assert_allclose(sd ** 2, g['sd'][:11] ** 2, rtol=0, atol=1e-8)
+
+
+def test_one_point_latency_at_n5000(B):
+  """ Prints the per-call time of gp.eval(1 point) at the metric's N with and without the row-streaming kernel. """
+  import time
+  w = B.synth.make_workload('headline_hartmann6_matern_ei', n_cand=64)
+  k = w['kernel']
+  gp = B.gp_core.GP(w['X'], w['Y'], B.kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
+                    B.gp_core.ConstantMean(w['mean_const']), w['noise_var'])
+  x = w['candidates'][:1]
+  res = {}
+  for opt in (1, 0):
+    gp._post.set_option('small_eval', opt)
+    for _ in range(5):
+      gp.eval(x, 'std')
+    B.torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(50):
+      mu, sd = gp.eval(x, 'std')
+    B.torch.cuda.synchronize()
+    res[opt] = (1e3 * (time.perf_counter() - t0) / 50, float(sd[0]))
+  print('gp.eval(1 point, std) at N=5000: row-streaming %.3f ms, tile kernels %.3f ms' % (res[1][0], res[0][0]))
+  assert abs(res[1][1] ** 2 - res[0][1] ** 2) <= 1e-12
