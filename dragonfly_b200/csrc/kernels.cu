@@ -1103,7 +1103,17 @@ small_sumsq_kernel(const double* __restrict__ W, int64_t ldw, const double* __re
     double acc[MC];
 #pragma unroll
     for (int c = 0; c < MC; c++) acc[c] = 0.0;
-    for (int64_t k = lane; k <= i; k += 32) {
+    int64_t k = lane;
+    for (; k + 96 <= i; k += 128) {          // four independent 256-byte row segments in flight per warp
+      const double w0 = wr[k], w1 = wr[k + 32], w2 = wr[k + 64], w3 = wr[k + 96];
+#pragma unroll
+      for (int c = 0; c < MC; c++) {
+        const double* kr = Ks + (int64_t)(c0 + c) * ldk + k;
+        const double k0 = kr[0], k1 = kr[32], k2 = kr[64], k3 = kr[96];
+        acc[c] = fma(w3, k3, fma(w2, k2, fma(w1, k1, fma(w0, k0, acc[c]))));
+      }
+    }
+    for (; k <= i; k += 32) {
       const double w = wr[k];
 #pragma unroll
       for (int c = 0; c < MC; c++) acc[c] = fma(w, Ks[(int64_t)(c0 + c) * ldk + k], acc[c]);
