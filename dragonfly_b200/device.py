@@ -97,6 +97,11 @@ class DevicePosterior(object):
     except Exception:  # pylint: disable=broad-except
       pass
 
+  def bind_current_stream(self):
+    """ Issue this handle's work on the calling thread's current torch stream from now on. """
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    _lib.check(self.lib.dfb_set_stream(self.h, C.c_void_p(stream)), 'dfb_set_stream')
+
   # -- model ------------------------------------------------------------------------------------
   def set_kernel(self, desc):
     _lib.check(self.lib.dfb_set_kernel(self.h, C.byref(desc)), 'dfb_set_kernel')

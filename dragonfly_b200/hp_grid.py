@@ -76,25 +76,72 @@ class EuclideanHPLayout(object):
     return float(mean_const), float(noise_var), kern
 
 
-def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None):
+# One LML-only build at N = 5000 is a 40-step dependency chain (chol_diag -> panel -> next column) that leaves most
+# of the GPU idle (7.7 ms for 42 GFLOP); the hp samples are independent, so `lanes` of them are built
+# concurrently -- one DevicePosterior (handle + workspace) per lane, each on its own CUDA stream, driven from its
+# own host thread (ctypes releases the GIL during the C call).  Sample i goes to lane i % lanes; every LML is
+# computed by the same kernels whatever the lane count, so the values do not depend on it.
+DEFAULT_LANES = 3
+
+
+def _lane_worker(lane_post, stream, X, Y, hps, idxs, layout, nus, out):
+  import torch
+  with torch.cuda.device(lane_post.device), torch.cuda.stream(stream):
+    lane_post.bind_current_stream()
+    last_mean = None
+    for i in idxs:
+      mean_const, noise_var, kern = layout.unpack(hps[i], Y, None if nus is None else nus[i])
+      if last_mean is None or mean_const != last_mean:
+        lane_post.set_train(X, Y - mean_const)
+        last_mean = mean_const
+      lane_post.set_kernel(build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
+      out[i], _ = stable_cholesky_on_device(lane_post, noise_var, flags=_lib.DFB_BUILD_LML_ONLY)
+
+
+def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lanes=None):
   """ LML of the GP built from each hp vector (rows of `hps`); `nus` optionally gives the discrete
       Matern nu per sample.  Returns (lmls, post) -- `post` can be passed back in to reuse the
-      device workspace. """
+      device workspaces (it carries the extra lanes). """
+  import threading
+  import torch
   from .device import DevicePosterior
   X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
   Y = np.asarray(Y, dtype=np.float64)
   if post is None or post.n_max < len(X):
     post = DevicePosterior(len(X), device=device)
   lmls = np.empty(len(hps))
-  last_mean = None
-  for i, hp in enumerate(hps):
-    mean_const, noise_var, kern = layout.unpack(hp, Y, None if nus is None else nus[i])
-    if last_mean is None or mean_const != last_mean:
-      post.set_train(X, Y - mean_const)
-      last_mean = mean_const
-    post.set_kernel(build_descriptor(kern, train_dim=X.shape[1], cand_dim=X.shape[1]))
-    lml, _ = stable_cholesky_on_device(post, noise_var, flags=_lib.DFB_BUILD_LML_ONLY)
-    lmls[i] = lml
+  if lanes is None:
+    lanes = DEFAULT_LANES if len(hps) >= 2 * DEFAULT_LANES else 1
+  lanes = max(1, min(int(lanes), len(hps)))
+  if lanes == 1:
+    _lane_worker(post, torch.cuda.current_stream(post.device), X, Y, hps, range(len(hps)), layout, nus, lmls)
+    return lmls, post
+  extra = getattr(post, '_hp_lanes', [])
+  while len(extra) < lanes - 1:
+    extra.append((DevicePosterior(len(X), device=post.device.index), torch.cuda.Stream(post.device)))
+  post._hp_lanes = extra
+  main_stream = torch.cuda.current_stream(post.device)
+  workers, errors = [], []
+
+  def guarded(*a):
+    try:
+      _lane_worker(*a)
+    except BaseException as e:  # pylint: disable=broad-except
+      errors.append(e)
+  for j in range(1, lanes):
+    lane_post, stream = extra[j - 1]
+    stream.wait_stream(main_stream)
+    t = threading.Thread(target=guarded, args=(lane_post, stream, X, Y, hps, range(j, len(hps), lanes), layout,
+                                               nus, lmls))
+    t.start()
+    workers.append(t)
+  guarded(post, main_stream, X, Y, hps, range(0, len(hps), lanes), layout, nus, lmls)
+  for t in workers:
+    t.join()
+  for j in range(1, lanes):
+    main_stream.wait_stream(extra[j - 1][1])
+  if errors:
+    raise errors[0]
   return lmls, post
 
 

@@ -481,6 +481,14 @@ def test_hp_grid_through_the_fitter_layout(B):
   close(probs, want, rtol=1e-7, atol=1e-12)
   lmls2, _ = hp_grid.sharded_lml_grid(g['X'], g['Y'], g['hps'][:3], layout)   # no process group: local
   close(lmls2, g['lmls'][:3], rtol=1e-10)
+  # concurrent lanes (one handle + stream + host thread each) give the very same values as one lane,
+  # and the returned posterior re-uses its lanes
+  hps = np.concatenate((g['hps'], g['hps'][::-1]), axis=0)
+  one, _ = hp_grid.lml_for_hyperparams(g['X'], g['Y'], hps, layout, lanes=1)
+  three, post3 = hp_grid.lml_for_hyperparams(g['X'], g['Y'], hps, layout, lanes=3)
+  again, post3b = hp_grid.lml_for_hyperparams(g['X'], g['Y'], hps, layout, post=post3, lanes=3)
+  assert (one == three).all() and (again == one).all() and post3b is post3 and len(post3._hp_lanes) == 2
+  close(one[:len(g['hps'])], g['lmls'], rtol=1e-10)
 
 
 def test_tma_kernel_matches_cp_async_kernel(B):

@@ -106,9 +106,14 @@ layout = hp_grid.EuclideanHPLayout(6, 'matern', nu=2.5)
 rs = np.random.RandomState(0)
 hps = np.concatenate((np.log(w['Y'].var()) + rs.uniform(-6, -3, (12, 1)), np.log(w['Y'].var()) + rs.uniform(-1, 1, (12, 1)),
                       rs.uniform(np.log(0.15), np.log(1.0), (12, 6))), axis=1)
-lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps[:2], layout)
-t0 = time.perf_counter(); lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps, layout, post=post); dt = time.perf_counter() - t0
-out['hp_grid_N5000'] = dict(lml_per_s=len(hps) / dt, ms_per_lml=1e3 * dt / len(hps), finite=bool(np.isfinite(lm).all()))
+out['hp_grid_N5000'] = {}
+for lanes in (1, 2, 3, 4):
+  lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps[:2 * lanes], layout, lanes=lanes)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter(); lm, post = hp_grid.lml_for_hyperparams(w['X'], w['Y'], hps, layout, post=post, lanes=lanes); dt = time.perf_counter() - t0
+  out['hp_grid_N5000']['lanes%d' % lanes] = dict(lml_per_s=len(hps) / dt, ms_per_lml=1e3 * dt / len(hps), finite=bool(np.isfinite(lm).all()),
+                                                 lml_head=[float(v) for v in lm[:3]])
+  del post
 print('hp', out['hp_grid_N5000'], flush=True)
 
 # multi-objective: 2 objectives on the C2 geometry (N=2000), linear and Tchebychev UCB scalarisations, device candidates
