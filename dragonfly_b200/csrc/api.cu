@@ -1096,6 +1096,21 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
   return 0;
 }
 
+int dfb_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int32_t S, int64_t m, int32_t what, double* out_dev) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (out_dev == nullptr || S < 1 || m < 1 || col0 < 0 || (what != DFB_RNG_NORMAL && what != DFB_RNG_UNIFORM)) { set_error("bad fill_rng arguments"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  return launch_fill_rng(h, seed, col0, S, m, what, out_dev);
+}
+
+int dfb_ts_argmax(dfb_handle* h, const double* samples_dev, int64_t ld, int32_t S, int64_t m, int64_t idx_base,
+                  int32_t reset, double* best_dev, int64_t* index_dev) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (samples_dev == nullptr || best_dev == nullptr || index_dev == nullptr || S < 1 || m < 1 || ld < m) { set_error("bad ts_argmax arguments"); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  return launch_ts_argmax(h, samples_dev, ld, S, m, idx_base, reset, best_dev, index_dev);
+}
+
 int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }
 
 int dfb_query(dfb_handle* h, const char* name, double* out) {

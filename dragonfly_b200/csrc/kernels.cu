@@ -887,6 +887,72 @@ moo_kernel(const MooArgs g, int64_t m, int64_t idx_base, double* __restrict__ sc
   }
 }
 
+// ---- counter-based normals for Thompson sampling at scale ----------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter = (column index lo, hi, draw index, stream), key = seed.  Element (s, a)
+// of the S x m matrix depends only on (seed, col0 + a, s), so a candidate gets the same normals whatever the block,
+// chunk or rank layout.  Box-Muller in fp64 on two 53-bit uniforms in (0, 1).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {      // (0, 1): (53-bit integer + 1/2) 2^-53
+  const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)v + 0.5) * 0x1p-53;
+}
+__global__ void fill_rng_kernel(uint64_t seed, int64_t col0, int S, int64_t m, int what, double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S * m) return;
+  const int64_t s = idx / m, a = idx - s * m;
+  const uint64_t col = (uint64_t)(col0 + a);
+  uint32_t r[4];
+  philox4x32_10((uint32_t)col, (uint32_t)(col >> 32), (uint32_t)s, (uint32_t)what, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const double u1 = u53(r[0], r[1]);
+  if (what == DFB_RNG_UNIFORM) { out[idx] = u1; return; }
+  const double u2 = u53(r[2], r[3]);
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  out[idx] = sqrt(-2.0 * log(u1)) * cs;
+}
+
+// running arg-max per draw: row s of samples (S x ld) over columns [0, m) -> (best[s], index[s]) in np.argmax order
+__global__ void __launch_bounds__(256)
+ts_argmax_kernel(const double* __restrict__ samples, int64_t ld, int64_t m, int64_t idx_base, int reset,
+                 double* best, int64_t* index) {
+  const int s = blockIdx.x;
+  double score = 0.0;
+  int64_t idx = -1;
+  if (!reset && threadIdx.x == 0) { score = best[s]; idx = index[s]; }
+  for (int64_t a = threadIdx.x; a < m; a += blockDim.x) {
+    const double v = samples[(int64_t)s * ld + a];
+    if (better(v, idx_base + a, score, idx)) { score = v; idx = idx_base + a; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double so = __shfl_xor_sync(0xffffffffu, score, o);
+    const int64_t io = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (better(so, io, score, idx)) { score = so; idx = io; }
+  }
+  __shared__ double ss[8];
+  __shared__ int64_t si[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ss[warp] = score; si[warp] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(ss[w], si[w], score, idx)) { score = ss[w]; idx = si[w]; }
+    best[s] = score;
+    index[s] = idx;
+  }
+}
+
 __global__ void reset_best_kernel(double* best_score, int64_t* best_index) {
   *best_score = 0.0;
   *best_index = -1;
@@ -1578,6 +1644,24 @@ int launch_moo(dfb_handle* h, const dfb_moo_desc& d, const double* const* a, con
     h->launches++;
     DFB_CUDA_OK(cudaGetLastError());
   }
+  return 0;
+}
+
+int launch_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int S, int64_t m, int what, double* out) {
+  const int64_t total = (int64_t)S * m;
+  if (total <= 0) return 0;
+  fill_rng_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(seed, col0, S, m, what, out);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_ts_argmax(dfb_handle* h, const double* samples, int64_t ld, int S, int64_t m, int64_t idx_base, int reset,
+                     double* best, int64_t* index) {
+  if (S <= 0) return 0;
+  ts_argmax_kernel<<<(unsigned)S, 256, 0, h->stream>>>(samples, ld, m, idx_base, reset, best, index);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

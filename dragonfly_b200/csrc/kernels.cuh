@@ -38,6 +38,9 @@ int launch_collect_shortlist(dfb_handle* h, const double* score, const double* s
                              int64_t* list_idx, double* list_X, int* list_count, int cap);
 int launch_vec_max(dfb_handle* h, const double* v, int64_t n, double* out);
 int launch_reset_best(dfb_handle* h);
+int launch_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int S, int64_t m, int what, double* out);
+int launch_ts_argmax(dfb_handle* h, const double* samples, int64_t ld, int S, int64_t m, int64_t idx_base, int reset,
+                     double* best, int64_t* index);
 int launch_small_sumsq(dfb_handle* h, const double* W, int64_t ldw, const double* Ks, int64_t ldk, int64_t n_rows,
                        int m, double* part, int64_t ld_part, int* n_warps_out);
 int launch_moo(dfb_handle* h, const dfb_moo_desc& d, const double* const* a, const double* const* b, int64_t m,

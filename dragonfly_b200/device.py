@@ -285,6 +285,21 @@ class DevicePosterior(object):
         C.byref(bs), C.byref(bi)), 'dfb_moo_score_argmax')
     return bs.value, bi.value, sc
 
+  def fill_rng(self, seed, col0, S, m, what=_lib.DFB_RNG_NORMAL, out=None):
+    """ dfb_fill_rng: the S x m matrix of counter-based normals / uniforms for global columns col0 .. col0+m-1. """
+    if out is None:
+      out = torch.empty((int(S), int(m)), dtype=torch.float64, device=self.device)
+    _lib.check(self.lib.dfb_fill_rng(self.h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), int(col0), int(S), int(m),
+                                     int(what), C.c_void_p(out.data_ptr())), 'dfb_fill_rng')
+    return out
+
+  def ts_argmax(self, samples, idx_base, best, index, reset):
+    """ dfb_ts_argmax: fold one block of draws (S x m CUDA tensor) into the running per-draw arg-max. """
+    S, m = int(samples.shape[0]), int(samples.shape[1])
+    _lib.check(self.lib.dfb_ts_argmax(self.h, C.c_void_p(samples.data_ptr()), int(samples.stride(0)), S, m,
+                                      int(idx_base), 1 if reset else 0, C.c_void_p(best.data_ptr()),
+                                      C.c_void_p(index.data_ptr())), 'dfb_ts_argmax')
+
   def launch_count(self):
     return int(self.lib.dfb_launch_count(self.h))
 

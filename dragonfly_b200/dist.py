@@ -62,6 +62,25 @@ def all_reduce_argmax(score, global_index, device=None, group=None):
   return reduce_pairs(scores, stacked[:, 1])
 
 
+def all_reduce_argmax_many(scores, global_indices, device=None, group=None):
+  """ K independent arg-maxes at once (Add-UCB groups, Thompson draws): one all-gather of K packed
+      (score bits, index) pairs per rank, K local reductions.  Returns (scores (K,), indices (K,)). """
+  scores = np.asarray(scores, dtype=np.float64).reshape(-1)
+  idx = np.asarray(global_indices, dtype=np.int64).reshape(-1)
+  if not (dist.is_available() and dist.is_initialized()):
+    return scores.copy(), idx.copy()
+  world = dist.get_world_size(group)
+  dev = torch.device('cpu') if device is None else device
+  mine = torch.from_numpy(np.stack((scores.view(np.int64), idx), axis=1).copy()).to(dev)
+  gathered = [torch.empty_like(mine) for _ in range(world)]
+  dist.all_gather(gathered, mine, group=group)
+  stacked = torch.stack(gathered).cpu().numpy()                 # (world, K, 2)
+  out_s, out_i = np.empty(len(scores)), np.empty(len(scores), dtype=np.int64)
+  for k in range(len(scores)):
+    out_s[k], out_i[k] = reduce_pairs(stacked[:, k, 0].copy().view(np.float64), stacked[:, k, 1])
+  return out_s, out_i
+
+
 def sharded_score_argmax(score_fn, m_total, device=None, group=None):
   """ score_fn(lo, hi) -> (best_score, best_local_index) over global rows [lo, hi).  Returns the
       global (score, index) on every rank. """

@@ -453,6 +453,55 @@ class GP(object):
         out[s_lo:s_hi, lo:hi] = smp.cpu().numpy()
     return out
 
+  def draw_samples_argmax(self, num_samples, X_test, seed=0, X_halluc=None, return_values=True):
+    """ Thompson sampling at scale (BASELINE config 5: 256 draws x 10^6 candidates): the arg-max of each of
+        `num_samples` joint posterior draws over X_test -- what asy_ts does with each draw
+        (gpb_acquisitions.py:119-127) -- without ever moving normals or samples through the host.  Same
+        algorithm as draw_samples (gp_core.py:250-254, general_utils.py:224-232; exact within 4096-candidate
+        blocks), but the standard normals come from the device's counter-based generator
+        (dfb_fill_rng: a candidate's normals depend only on (seed, its global row, draw index)) instead of
+        np.random.normal, and a running per-draw arg-max (dfb_ts_argmax) replaces the (S, M) sample matrix.
+        Under torch.distributed the blocks are shared out over the ranks and joined with one all-gather of S
+        16-byte pairs.  Returns (values (S,), indices (S,)) as NumPy arrays. """
+    import torch
+    from . import dist as dfb_dist
+    from .gpb_acquisitions import _shard_info
+    if self._mean_const is None:
+      raise NotImplementedError('Thompson sampling on device needs a constant mean function.')
+    S = int(num_samples)
+    with self._hallucinated([] if X_halluc is None else X_halluc) as post:
+      Xm = self._test_matrix(X_test)
+      M = len(Xm)
+      blk = post.TS_BLOCK
+      n_blocks = (M + blk - 1) // blk
+      rank, world, coll_dev = _shard_info()
+      b_lo, b_hi = dfb_dist.shard_bounds(n_blocks, rank, world) if world > 1 else (0, n_blocks)
+      best = torch.zeros((S,), dtype=torch.float64, device=post.device)
+      index = torch.full((S,), -1, dtype=torch.int64, device=post.device)
+      first = True
+      for b in range(b_lo, b_hi):
+        lo, hi = b * blk, min(M, (b + 1) * blk)
+        xb = Xm[lo:hi]
+        for s_lo in range(0, S, 256):
+          s_hi = min(S, s_lo + 256)
+          Ut = post.fill_rng(seed, lo, S, hi - lo)[s_lo:s_hi] if S > 256 else post.fill_rng(seed, lo, S, hi - lo)
+          info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=0.0)
+          power = -11
+          while info != 0:                                    # stable_cholesky's ladder, per block
+            jitter = (10 ** power) * max_diag
+            info, smp, _ = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=jitter)
+            if info != 0:
+              power += 1
+              if power >= 5:
+                raise ValueError('Could not compute Cholesky decomposition despite adding %0.4f to '
+                                 'the diagonal.' % (jitter))
+          post.ts_argmax(smp, lo, best[s_lo:s_hi], index[s_lo:s_hi], reset=first)
+        first = False
+      vals, idxs = best.cpu().numpy(), index.cpu().numpy()
+    if world > 1:
+      vals, idxs = dfb_dist.all_reduce_argmax_many(vals, idxs, device=coll_dev)
+    return (vals, idxs) if return_values else idxs
+
   def draw_samples(self, num_samples, X_test=None, mean_vals=None, covar=None, cols=None):
     """ gp_core.py:250-254 (`cols`: multi-GPU block range, see _draw_samples_on) """
     if X_test is None:

@@ -221,6 +221,20 @@ int dfb_moo_score_argmax(dfb_handle* h, const dfb_moo_desc* desc, const double* 
                          const double* const* b_dev, int64_t m, double* scores_dev,
                          double* best_score_host, int64_t* best_index_host);
 
+/* Thompson sampling at scale (BASELINE config 5: 256 draws x 10^6 candidates).  The reference draws its normals
+ * with np.random.normal on the host (general_utils.py:230), which dfb_ts_draws reproduces when the caller supplies
+ * them; at 10^6 x 256 that is 2 GB of host RNG and copies per call.  dfb_fill_rng generates them on the device
+ * with a counter-based generator (Philox4x32-10 + Box-Muller, fp64): element (s, a) of the S x m output depends
+ * only on (seed, col0 + a, s) -- the same candidate gets the same normals whatever the block or rank layout.
+ * what: DFB_RNG_NORMAL or DFB_RNG_UNIFORM (53-bit uniforms in (0, 1), e.g. random_sample's U, oper_utils.py:62).
+ * dfb_ts_argmax folds one block of draws (S x m, row stride ld) into running per-draw (value, index) pairs in
+ * np.argmax order (sample.argmax() of asy_ts, gpb_acquisitions.py:127); reset != 0 starts a new arg-max.  */
+#define DFB_RNG_NORMAL  0
+#define DFB_RNG_UNIFORM 1
+int dfb_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int32_t S, int64_t m, int32_t what, double* out_dev);
+int dfb_ts_argmax(dfb_handle* h, const double* samples_dev, int64_t ld, int32_t S, int64_t m, int64_t idx_base,
+                  int32_t reset, double* best_dev, int64_t* index_dev);
+
 /* Kernel.__call__(X1, X2) (kernel.py:72-83): the n1 x n2 Gram matrix, device pointers. */
 int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,
                       int32_t d1, const double* X2_dev, int64_t n2, int32_t d2, double* K_dev);

@@ -51,6 +51,9 @@ def run_all(counts=None):
   out['ucb_halluc'] = A.asy.ucb(gp, anc('ucb', 2000, in_progress=Xh))
   np.random.seed(23)
   out['ts'] = A.asy.ts(gp, anc('ts', 9000))               # 3 blocks of 4096: ranks get 2 + 1
+  vals, idxs = gp.draw_samples_argmax(5, np.random.RandomState(31).random_sample((9000, 6)), seed=77)
+  out['ts_device_rng_idx'] = idxs.astype(np.float64)
+  out['ts_device_rng_val'] = vals
   # additive GP, Add-UCB
   rs = np.random.RandomState(0)
   Xa = rs.random_sample((150, 8))

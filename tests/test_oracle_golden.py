@@ -308,3 +308,23 @@ def test_add_data_matches_reference():
   mu, sd = gp.eval(g['C'], 'std')
   close(mu, g['mu'], atol=1e-11)
   close(sd ** 2, g['sd'] ** 2, atol=1e-11)
+
+
+def test_philox_known_answers():
+  """ oracle/philox.py against the published Random123 known-answer vectors for Philox4x32-10 (the generator
+      behind dfb_fill_rng); moments of the Box-Muller normals. """
+  from oracle import philox as P
+  u32 = lambda *v: [np.array([x], dtype=np.uint32) for x in v]
+  kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+          ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+          ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+           (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+  for ctr, key, want in kats:
+    got = P.philox4x32_10(*u32(*ctr), *u32(*key))
+    assert tuple(int(g[0]) for g in got) == want
+  z = P.fill(11, 0, 32, 8192)
+  assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and np.isfinite(z).all()
+  u = P.fill(11, 0, 32, 8192, what=1)
+  assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.005
+  # layout invariance: columns [100, 300) of a wide fill == a fill that starts at column 100
+  assert (P.fill(3, 0, 4, 300)[:, 100:] == P.fill(3, 100, 4, 200)).all()
