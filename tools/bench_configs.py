@@ -96,7 +96,20 @@ def c5():
   return dict(cands_per_s=len(w['candidates']) / dt, draws=256, finite=bool(np.isfinite(samples).all()),
               argmax_head=[int(i) for i in samples.argmax(axis=1)[:4]],
               note='block-exact joint draws (4096-candidate blocks), host normals + H2D/D2H included')
-out['c5_park1_20_ts_N5000'] = {'auto': c5()}
+def c5_device_rng():
+  w = synth_data.make_workload('c5_park1_20_ts', n_cand=1000000 // scale)
+  k = w['kernel']
+  gp = gp_core.GP(w['X'], w['Y'], kernel.MaternKernel(20, 2.5, k['scale'], k['dim_bandwidths']),
+                  gp_core.ConstantMean(w['mean_const']), w['noise_var'])
+  cd = torch.from_numpy(w['candidates']).cuda()
+  gp.draw_samples_argmax(256, cd[:4096], seed=2)
+  torch.cuda.synchronize(); t0 = time.perf_counter()
+  vals, idxs = gp.draw_samples_argmax(256, cd, seed=2)
+  torch.cuda.synchronize(); dt = time.perf_counter() - t0
+  return dict(cands_per_s=len(cd) / dt, draws=256, candidates=len(cd), seconds=dt, finite=bool(np.isfinite(vals).all()),
+              argmax_head=[int(i) for i in idxs[:4]],
+              note='GP.draw_samples_argmax: device Philox normals + running per-draw arg-max, nothing but 256 pairs leaves the GPU')
+out['c5_park1_20_ts_N5000'] = {'auto': c5(), 'device_rng_argmax': c5_device_rng()}
 print('c5', out['c5_park1_20_ts_N5000'], flush=True)
 
 # hp grid: LML-only builds at N=5000
