@@ -996,7 +996,7 @@ int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* 
 // mu and the padded posterior covariance (h->ts_Cov, ld = mbp) of one block of m candidates:
 // K_* -> V^T = K_* W^T -> Cov = K** - V^T V    (gp_core.py:173-181)
 static int posterior_covariance(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc,
-                                double mean_const, int64_t* mbp_out) {
+                                double mean_const, int64_t* mbp_out, bool lower_only) {
   const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
   const dfb_kernel_desc* d_desc = h->have_test_kernel ? h->d_desc_te : h->d_desc_tr;
   const ScaledSet& ss = h->have_test_kernel ? h->te : h->tr;
@@ -1026,6 +1026,7 @@ static int posterior_covariance(dfb_handle* h, const double* Xc_dev, int64_t m, 
   g.A = h->ts_Vt; g.lda = npad; g.B = h->ts_Vt; g.ldb = npad; g.C = h->ts_Cov; g.ldc = mbp;
   g.D = h->ts_Cov; g.ldd = mbp; g.alpha = -1.0; g.mode = MODE_GENERIC; g.n_rb = mbb; g.n_cb = mbb;
   g.K = (int)npad;
+  g.lower_only = lower_only ? 1 : 0;     // the factorisation that follows reads the lower triangle only
   DFB_TRY(launch_gemm(h, g, EPI_STORE, mbb * mbb));
   *mbp_out = mbp;
   return 0;
@@ -1050,7 +1051,7 @@ int dfb_eval_covar(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, d
   if (Xc_dev == nullptr || mu_dev == nullptr || covar_dev == nullptr) { set_error("bad eval_covar arguments"); return -1; }
   DFB_CUDA_OK(cudaSetDevice(h->device));
   int64_t mbp = 0;
-  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp));
+  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp, false));
   DFB_TRY(launch_copy_pad(h, h->ts_mu, m, mu_dev, m));
   DFB_TRY(launch_copy_rows(h, h->ts_Cov, mbp, covar_dev, m, m, m));
   DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1064,7 +1065,7 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
   if (Xc_dev == nullptr || Ut_dev == nullptr || samples_dev == nullptr || S < 1 || S > 256) { set_error("bad ts_draws arguments (1 <= S <= 256)"); return -1; }
   DFB_CUDA_OK(cudaSetDevice(h->device));
   int64_t mbp = 0;
-  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp));
+  DFB_TRY(posterior_covariance(h, Xc_dev, m, dc, mean_const, &mbp, true));
   DFB_TRY(launch_diag_max(h, h->ts_Cov, mbp, m, h->ts_red));
   // stable_cholesky(K) (general_utils.py:224-229): factorise Cov + jitter I (identity padding)
   DFB_CUDA_OK(cudaMemsetAsync(h->ts_info, 0, sizeof(int) * 4, h->stream));
