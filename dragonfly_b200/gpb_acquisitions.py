@@ -90,14 +90,34 @@ def _fused_maximise(scorer, anc_data, bounds=None):
   return rand_pts[idx]
 
 
+def _reference_fortran_direct_available():
+  """ True when a Dragonfly install with its Fortran DIRECT extension is importable: only then does the
+      reference's 'direct' differ from PDOO (oper_utils.py:23-31, 121-137). """
+  try:
+    from dragonfly.utils import oper_utils as ref_oper  # pylint: disable=import-error
+  except Exception:  # pylint: disable=broad-except
+    return False
+  return getattr(ref_oper, 'direct_ft_wrap', None) is not None
+
+
 def _delegate_to_reference_maximiser(acq_fn, anc_data):
-  """ Non-vectorised maximisers are the reference's own host code (oper_utils.py / doo.py). """
+  """ The non-vectorised maximisers of maximise_acquisition (:29-37).  `acq_fn` takes a (k, d) array.
+      'pdoo' -- and 'direct' wherever the reference itself would fall back to PDOO because its Fortran DIRECT is
+      not built (oper_utils.py:121-137) -- run the batched PDOO of dragonfly_b200/doo.py: the same search as
+      dragonfly/utils/doo.py with the two children of every split scored in one device call.  Fortran DIRECT
+      itself stays the reference's (a sequential host code driving the device-backed objective point by point). """
+  method = str(anc_data.acq_opt_method).lower()
+  if method.startswith('pdoo') or (method.startswith('direct') and not _reference_fortran_direct_available()):
+    from .doo import pdoo_maximise
+    _, opt_pt, _ = pdoo_maximise(lambda X: acq_fn(np.asarray(X, dtype=np.float64)), anc_data.domain.bounds,
+                                 anc_data.max_evals)
+    return opt_pt
   try:
     from dragonfly.exd.exd_utils import maximise_with_method  # pylint: disable=import-error
   except ImportError:
     raise NotImplementedError(
-        "acq_opt_method '%s' is a sequential host maximiser outside the B200 hot path; only 'rand' "
-        'is served without a Dragonfly install.' % (anc_data.acq_opt_method))
+        "acq_opt_method '%s' is a sequential host maximiser outside the B200 hot path; 'rand', 'pdoo' and "
+        "'direct' (as PDOO) are served without a Dragonfly install." % (anc_data.acq_opt_method))
   acquisition = lambda x: acq_fn(np.asarray(x).reshape((1, -1)))
   _, opt_pt = maximise_with_method(anc_data.acq_opt_method, acquisition, anc_data.domain,
                                    anc_data.max_evals)

@@ -185,3 +185,40 @@ def test_product_never_imports_the_oracle():
       if f.endswith(('.py', '.cu', '.cuh', '.h')):
         src = open(os.path.join(dirpath, f)).read()
         assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+# ---- PDOO with batched children (dragonfly_b200/doo.py) against the reference's own runs -----------------------------
+def _pdoo_objectives():
+  from dragonfly_b200 import synth_data
+  return {
+    'neg_branin': (lambda X: -synth_data.branin(np.asarray(X, dtype=np.float64)), [[0, 1], [0, 1]], 300),
+    'hartmann6': (lambda X: synth_data.hartmann6(np.asarray(X, dtype=np.float64)), [[0, 1]] * 6, 400),
+    'shifted_1d': (lambda X: np.sin(3 * X[:, 0]) - 0.1 * X[:, 0] ** 2, [[-2, 5]], 120),
+    'plateau_3d': (lambda X: np.floor(4 * X[:, 0]) + np.round(X[:, 1], 1) - np.abs(X[:, 2] - 3.0),
+                   [[0, 1], [-1, 1], [2, 4]], 250),
+  }
+
+
+@pytest.mark.parametrize('name', ['neg_branin', 'hartmann6', 'shifted_1d', 'plateau_3d'])
+def test_pdoo_visits_the_cells_the_reference_visits(name):
+  """ tests/golden/pdoo.npz = dragonfly.utils.oper_utils.pdoo_maximise (doo.py) run on these objectives: same
+      recommendation, same value, same sequence of evaluated points -- with the children of each split fetched
+      in one batched call (about half as many objective calls as evaluations). """
+  from conftest import load_golden
+  from dragonfly_b200 import doo
+  g = load_golden('pdoo')
+  f, bounds, evals = _pdoo_objectives()[name]
+  val, pt, hist = doo.pdoo_maximise(f, bounds, evals)
+  assert hist is None
+  assert (np.asarray(pt) == g[name + '_pt']).all()
+  assert abs(val - float(g[name + '_val'])) <= 1e-13 * max(1.0, abs(val))   # (k, d) vs (1, d) NumPy reductions: 1 ulp
+  s = doo.pdoo_maximise.last_search
+  b = np.array(bounds, dtype=np.float64)
+  q = np.array(s.query_pts) * (b[:, 1] - b[:, 0]) + b[:, 0]
+  assert q.shape == g[name + '_query_pts'].shape and (q == g[name + '_query_pts']).all()
+  np.testing.assert_allclose(np.array(s.query_vals), g[name + '_query_vals'], rtol=1e-13, atol=1e-13)
+  assert s.num_device_calls < 0.6 * len(s.query_vals) + 20
+  # one point per call (the reference's calling convention) gives the same search
+  val1, pt1, _ = doo.pdoo_maximise(lambda x: float(f(np.asarray(x).reshape(1, -1))[0]), bounds, evals,
+                                   vectorised=False)
+  assert abs(val1 - val) <= 1e-13 * max(1.0, abs(val)) and (pt1 == pt).all()
