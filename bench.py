@@ -41,7 +41,7 @@ def parse_args():
   p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   p.add_argument('--n-train', type=int, default=5000)
   p.add_argument('--cands-per-gpu', type=int, default=1000000)
-  p.add_argument('--cpu-sample', type=int, default=6000)
+  p.add_argument('--cpu-sample', type=int, default=24000)
   p.add_argument('--no-cpu-baseline', action='store_true')
   return p.parse_args()
 
