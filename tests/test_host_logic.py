@@ -222,3 +222,68 @@ def test_pdoo_visits_the_cells_the_reference_visits(name):
   val1, pt1, _ = doo.pdoo_maximise(lambda x: float(f(np.asarray(x).reshape(1, -1))[0]), bounds, evals,
                                    vectorised=False)
   assert abs(val1 - val) <= 1e-13 * max(1.0, abs(val)) and (pt1 == pt).all()
+
+
+# ---- the int8 digit scheme of the tcgen05 contraction, emulated in integers on the CPU ----------------------------
+def _digits_radix256(x):
+  """ NumPy restatement of digits_radix256 (dragonfly_b200/csrc/kernels.cu): five signed digits of |x| <= 1/2,
+      x ~ a0 2^-7 + a1 2^-15 + a2 2^-23 + a3 2^-31 + a4 2^-39. """
+  x = np.asarray(x, dtype=np.float64)
+  hi = np.rint(x * 2.0 ** 15)                      # round-half-even, like the magic-number trick
+  rem = x * 2.0 ** 15 - hi                         # exact
+  lo = np.rint(rem * 2.0 ** 24).astype(np.int64)
+  hi = hi.astype(np.int64)
+  s8 = lambda v: ((v + 128) % 256) - 128           # sign-extended low byte
+  a4 = s8(lo); r = (lo - a4) >> 8
+  a3 = s8(r); r = (r - a3) >> 8
+  a2 = s8(r); hi = hi + ((r - a2) >> 8)
+  a1 = s8(hi); a0 = (hi - a1) >> 8
+  return [a0, a1, a2, a3, a4]
+
+
+def test_radix256_digits_are_int8_and_exact_to_2_pow_minus_40():
+  rs = np.random.RandomState(0)
+  x = np.concatenate((rs.uniform(-0.5, 0.5, 200000), [0.5, -0.5, 0.0, 2.0 ** -41, -2.0 ** -41, 0.49999999999,
+                                                        2.0 ** -8, 2.0 ** -16 * 255.5, 1.0 / 3, -1.0 / 3]))
+  d = _digits_radix256(x)
+  assert all(int(a.min()) >= -128 and int(a.max()) <= 127 for a in d)
+  assert int(d[0].min()) >= -64 and int(d[0].max()) <= 64                    # the top digit keeps 7 bits
+  recon = sum(a.astype(np.float64) * 2.0 ** -(8 * (s + 1) - 1) for s, a in enumerate(d))
+  assert np.abs(recon - x).max() <= 2.0 ** -40
+
+
+def test_int8_slice_contraction_error_is_inside_the_a_priori_bound():
+  """ The scheme of gemm_i8c2.cuh in exact integer arithmetic: W = L^-1-like rows scaled by 2^-E_i, K_* columns by
+      2^-F, five radix-256 digits each, the 15 products with s + t <= 6 accumulated as integers per power of 256,
+      recombined in fp64 -- against the fp64 contraction.  The sigma^2 error must sit inside api.cu's a-priori
+      bound 8 rowscale_max sqrt(n) colscale 2^-40 sqrt(kss) (i8_sigma2_bound), and the group sums inside int32. """
+  from oracle import gp_oracle as O
+  rs = np.random.RandomState(1)
+  n, m, kss = 640, 48, 2.7
+  # a genuine posterior: W = L^-1 of K + noise I, K_* = k(X*, X) (the bound uses |v|^2 = k** - sigma^2 <= k(x, x))
+  X, Xs = rs.random_sample((n, 4)), rs.random_sample((m, 4))
+  kern = O.OMaternKernel(4, 2.5, kss, [0.3] * 4)
+  L = np.linalg.cholesky(kern(X, X) + 0.01 * kss * np.eye(n))
+  W = np.linalg.inv(L)
+  W = np.tril(W)
+  Kst = kern(Xs, X)
+  e_row = np.frexp(np.abs(W).max(axis=1))[1] + 1
+  rowscale = np.ldexp(1.0, e_row)
+  colscale = np.ldexp(1.0, np.frexp(kss * (1 + 1e-9))[1] + 1)
+  A = _digits_radix256(W / rowscale[:, None])
+  Bd = _digits_radix256(Kst / colscale)
+  v = np.zeros((n, m))
+  for dsum in range(2, 7):                          # groups d = s + t (1-based digits), weight 2^-(8 d - 2)
+    G = np.zeros((n, m), dtype=np.int64)
+    for s in range(1, 6):
+      t = dsum - s
+      if 1 <= t <= 5:
+        G += A[s - 1] @ Bd[t - 1].T                 # what one chain of tcgen05.mma kind::i8 accumulates
+    assert np.abs(G).max() < 2 ** 31
+    v += G.astype(np.float64) * 2.0 ** -(8 * dsum - 2)
+  v *= rowscale[:, None] * colscale
+  v_ref = (W.astype(np.longdouble) @ Kst.T.astype(np.longdouble)).astype(np.float64)
+  err_sigma2 = np.abs((v ** 2).sum(axis=0) - (v_ref ** 2).sum(axis=0)).max()
+  bound = 8.0 * rowscale.max() * np.sqrt(n) * colscale * 2.0 ** -40 * np.sqrt(kss)
+  assert err_sigma2 <= bound, (err_sigma2, bound)
+  assert err_sigma2 > 0.0                            # (it is an approximation: 2^-40 digits, dropped s + t = 7 terms)
