@@ -287,3 +287,204 @@ def test_int8_slice_contraction_error_is_inside_the_a_priori_bound():
   bound = 8.0 * rowscale.max() * np.sqrt(n) * colscale * 2.0 ** -40 * np.sqrt(kss)
   assert err_sigma2 <= bound, (err_sigma2, bound)
   assert err_sigma2 > 0.0                            # (it is an approximation: 2^-40 digits, dropped s + t = 7 terms)
+
+
+# ---- incremental posterior: the host's decisions (no device: a NumPy-backed stand-in for DevicePosterior) -----------
+class NumpyPost(object):
+  """ Implements what GP needs of DevicePosterior with the oracle's arithmetic; records which calls were made. """
+  TS_BLOCK = 4096
+
+  def __init__(self, n_max, log, kern_of):
+    self.log, self.kern_of = log, kern_of
+    self.n, self.dim, self.saved = 0, 0, None
+
+  def set_kernel(self, desc):
+    self.desc = desc
+
+  def set_train(self, X, yc):
+    self.X, self.yc = np.array(X), np.array(yc)
+    self.n, self.dim = self.X.shape
+
+  def capacity(self):
+    return (self.n + 127) // 128 * 128
+
+  def build(self, noise_var, jitter, flags):
+    self.log.append(('build', self.n))
+    self.noise = noise_var + jitter
+    return self._factor()
+
+  def _factor(self):
+    K = self.kern_of()(self.X, self.X) + self.noise * np.eye(self.n)
+    try:
+      self.L = np.linalg.cholesky(K)
+    except np.linalg.LinAlgError:
+      return 3, None
+    self.alpha = O.solve_upper_triangular(self.L.T, O.solve_lower_triangular(self.L, self.yc))
+    lml = -0.5 * self.yc.dot(self.alpha) - np.log(np.diag(self.L)).sum() - 0.5 * self.n * np.log(2 * np.pi)
+    return 0, lml
+
+  def extend(self, X_new, yc_new, flags=0, save=False):
+    self.log.append(('extend', len(X_new), bool(save)))
+    assert self.n + len(X_new) <= self.capacity()
+    if save:
+      self.saved = (self.X, self.yc, self.L, self.alpha)
+    self.X = np.concatenate((self.X, np.asarray(X_new)), axis=0)
+    self.yc = np.concatenate((self.yc, np.asarray(yc_new)))
+    self.n = len(self.X)
+    info, lml = self._factor()
+    if save:                                      # NO_ALPHA semantics: alpha stays the old one, zero-extended
+      self.alpha = np.concatenate((self.saved[3], np.zeros(len(X_new))))
+    return info, lml
+
+  def set_alpha(self, alpha):
+    a = np.zeros(self.n); a[:len(alpha)] = alpha
+    self.alpha = a
+
+  def get_state(self, want_L=False, want_alpha=False, want_K=False):
+    import torch
+    t = lambda a: torch.from_numpy(np.array(a))
+    return (t(self.L) if want_L else None, t(self.alpha) if want_alpha else None, None)
+
+  def restore(self, n_before):
+    self.log.append(('restore', n_before))
+    self.X, self.yc, self.L, self.alpha = self.saved
+    self.n, self.saved = len(self.X), None
+
+  def eval(self, Xc, mean_const=0.0, want_std=True):
+    Ks = self.kern_of()(np.asarray(Xc), self.X)
+    mu = mean_const + Ks.dot(self.alpha)
+    if not want_std:
+      return mu, None
+    V = O.solve_lower_triangular(self.L, Ks.T)
+    return mu, np.sqrt(O.kernel_diag(self.kern_of(), np.asarray(Xc)) - (V * V).sum(axis=0))
+
+
+def _fake_gp(n, log, incremental=True):
+  from dragonfly_b200 import gp_core, synth_data
+  rs = np.random.RandomState(4)
+  X = rs.random_sample((n + 140, 3)); Y = np.sin(4 * X[:, 0]) + X[:, 1] * X[:, 2]
+  kern = K.SEKernel(3, 1.3, [0.4, 0.5, 0.6])
+  okern = O.OSEKernel(3, 1.3, [0.4, 0.5, 0.6])
+
+  class G(gp_core.GP):
+    incremental_updates = incremental
+
+    def _new_device_posterior(self, n_max):
+      return NumpyPost(n_max, log, lambda: okern)
+  gp = G(X[:n], Y[:n], kern, gp_core.ConstantMean(0.2), 0.05)
+  return gp, X, Y, okern
+
+
+def test_add_data_extends_only_when_it_is_the_same_mathematical_object():
+  from copy import copy
+  log = []
+  gp, X, Y, okern = _fake_gp(100, log)
+  assert log == [('build', 100)]
+  gp.add_data_multiple(list(X[100:103]), list(Y[100:103]))
+  gp.add_data_single(X[103], Y[103])
+  assert log[1:] == [('extend', 3, False), ('extend', 1, False)] and gp.num_tr_data == 104
+  ogp = O.OGP(X[:104], Y[:104], okern, lambda x: np.array([0.2] * len(x)), 0.05)
+  np.testing.assert_allclose(gp.compute_log_marginal_likelihood(), ogp.compute_log_marginal_likelihood(), rtol=1e-12)
+  # 104 + 25 > 128: the padded size is exceeded -> the reference's full rebuild
+  del log[:]
+  gp.add_data_multiple(list(X[104:129]), list(Y[104:129]))
+  assert log == [('build', 129)]
+  # a copy shares the posterior: neither side may extend it for good
+  del log[:]
+  twin = copy(gp)
+  twin.X, twin.Y = list(gp.X), list(gp.Y)
+  twin.add_data_single(X[129], Y[129])
+  assert log == [('build', 130)] and gp.num_tr_data == 129 and gp._post.n == 129
+  # changed noise (or kernel / mean object) -> rebuild; switch off -> rebuild
+  del log[:]
+  twin.noise_var = 0.06
+  twin.add_data_single(X[130], Y[130])
+  assert log == [('build', 131)]
+  del log[:]
+  twin.incremental_updates = False
+  twin.add_data_single(X[131], Y[131])
+  assert log == [('build', 132)]
+  # build_posterior=False defers everything
+  del log[:]
+  twin.incremental_updates = True
+  twin.add_data_multiple([X[132]], [Y[132]], build_posterior=False)
+  assert log == [] and twin.num_tr_data == 133
+  twin.build_posterior()
+  assert log == [('build', 133)]
+
+
+def test_hallucinations_extend_temporarily_and_fall_back_when_they_must():
+  log = []
+  gp, X, Y, okern = _fake_gp(100, log)
+  ogp = O.OGP(X[:100], Y[:100], okern, lambda x: np.array([0.2] * len(x)), 0.05)
+  C = np.random.RandomState(9).random_sample((40, 3))
+  Xh = list(np.random.RandomState(10).random_sample((3, 3)))
+  mu0, sd0 = gp.eval(C, 'std')
+  del log[:]
+  mu, sd = gp.eval_with_hallucinated_observations(C, Xh, 'std')
+  assert log == [('extend', 3, True), ('restore', 100)]
+  mu_o, sd_o = ogp.eval_with_hallucinated_observations(C, Xh, 'std')
+  np.testing.assert_allclose(mu, mu_o, atol=1e-11); np.testing.assert_allclose(sd, sd_o, atol=1e-9)
+  mu1, sd1 = gp.eval(C, 'std')
+  assert (mu1 == mu0).all() and (sd1 == sd0).all() and gp._post.n == 100
+  # 'none' never touches the factorisation; an empty list neither
+  del log[:]
+  gp.eval_with_hallucinated_observations(C, Xh, 'none'); gp.eval_with_hallucinated_observations(C, [], 'std')
+  assert log == []
+  # 100 + 30 > 128 -> a fresh (N + q)-point posterior, built like the reference does, alpha from the old one
+  many = list(np.random.RandomState(11).random_sample((30, 3)))
+  mu2, sd2 = gp.eval_with_hallucinated_observations(C, many, 'std')
+  assert log == [('build', 130)]
+  mu2_o, sd2_o = ogp.eval_with_hallucinated_observations(C, many, 'std')
+  np.testing.assert_allclose(mu2, mu2_o, atol=1e-11); np.testing.assert_allclose(sd2, sd2_o, atol=1e-9)
+  # the restore also happens when the consumer raises
+  del log[:]
+  with pytest.raises(ValueError):
+    gp.eval_with_hallucinated_observations(C, Xh, 'nonsense')
+  assert log == []
+  class Boom(Exception):
+    pass
+  with pytest.raises(Boom):
+    with gp._hallucinated(Xh) as post:
+      assert post.n == 103
+      raise Boom()
+  assert log == [('extend', 3, True), ('restore', 100)] and gp._post.n == 100
+
+
+def test_extension_algebra_of_dfb_extend_posterior():
+  """ The left-looking rebuild + replay of the last factorisation step (api.cu: replay_last_block), in NumPy on the
+      padded tall matrix [A ; I ; y^T] -> [L ; L^-T ; (L^-1 y)^T]: appending q points inside the last 128-row block
+      must give the factorisation of the enlarged matrix (identity padding), i.e. L, W = L^-1 and v = L^-1 y. """
+  rs = np.random.RandomState(2)
+  T_, n0, q, noise = 128, 300, 9, 0.05
+  n1, npad = n0 + q, 384
+  m0 = npad - T_
+  X = rs.random_sample((n1, 3)); y = rs.standard_normal(n1)
+  kern = O.OSEKernel(3, 1.1, [0.3, 0.4, 0.5])
+
+  def padded(n):
+    A = np.eye(npad); A[:n, :n] = kern(X[:n], X[:n]) + noise * np.eye(n)
+    yy = np.zeros(npad); yy[:n] = y[:n]
+    L = np.linalg.cholesky(A)
+    W = np.linalg.inv(L)
+    return A, yy, L, W, W @ yy
+  _, _, L0, W0, v0 = padded(n0)
+  A1, y1, L1, W1, v1 = padded(n1)
+  # state before the call: the n0-point factorisation; inputs: rows m0.. of the enlarged A, the new y entries
+  L, W, v = L0.copy(), W0.copy(), v0.copy()
+  A_last = A1[m0:, :]
+  P = A_last[:, :m0] @ W[:m0, :m0].T                       # P = A[last, :m0] L00^-T
+  S = A_last[:, m0:] - P @ P.T                             # Schur complement of the last diagonal block
+  Wt_c = -(W[:m0, :m0].T @ P.T)                            # pre-step state of L^-T's last block column
+  y_c = y1[m0:] - v[:m0] @ P.T
+  Ldd = np.linalg.cholesky(S); Dinv = np.linalg.inv(Ldd)   # chol_diag_kernel: L_dd and its inverse
+  L[m0:, :m0], L[m0:, m0:] = P, Ldd
+  Wt = W.T.copy()
+  Wt[:m0, m0:] = Wt_c @ Dinv.T                             # panel solve: X <- X inv(L_dd)^T
+  Wt[m0:, m0:] = Dinv.T
+  v[m0:] = y_c @ Dinv.T
+  np.testing.assert_allclose(L, L1, rtol=0, atol=1e-11)
+  np.testing.assert_allclose(Wt.T, W1, rtol=0, atol=1e-9)
+  np.testing.assert_allclose(v, v1, rtol=0, atol=1e-10)
+  # rows above the last block are untouched by construction
+  assert (L[:m0, :m0] == L0[:m0, :m0]).all()
