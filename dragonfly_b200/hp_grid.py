@@ -145,6 +145,82 @@ def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lan
   return lmls, post
 
 
+def default_max_evals(method, num_hps):
+  """ gp_core.py:456-462 """
+  if method in ('direct', 'pdoo'):
+    return int(min(1e4, max(500, num_hps * 50)))
+  if method == 'rand':
+    return int(min(1e4, max(500, num_hps * 200)))
+  if method == 'rand_exp_sampling':
+    return int(min(1e5, max(500, num_hps * 400)))
+  raise ValueError('Unknown ml_hp_tune_opt method %s.' % (method))
+
+
+def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampling', max_evals=None,
+           device=None, gp_factory=None):
+  """ GPFitter.fit_gp for hp_tune_criterion == 'ml' (gp_core.py:783-808) with the marginal likelihood of every
+      hyper-parameter vector evaluated on the device, in batches instead of one _tuning_objective call at a time
+      (gp_core.py:551-563):
+        'rand'               random_maximise over the continuous hps for every combination of the discrete ones
+                             (oper_utils.py:69-80, gp_core.py:787-799): all max_evals candidates of a combination are
+                             one lml_for_hyperparams call (concurrent build lanes);
+        'pdoo' / 'direct'    pdoo_maximise (oper_utils.py:257-271; 'direct' is PDOO wherever the reference's Fortran
+                             DIRECT is not built) through dragonfly_b200.doo: both children of a split in one call;
+        'rand_exp_sampling'  random_sample_cts_dscr + exp(lml - max) weights (oper_utils.py:362-371,
+                             gp_core.py:439-445): one call for all samples.
+      The global NumPy RNG is consumed exactly like the reference does, so a seeded run picks the same
+      hyper-parameters.  `cts_hp_bounds` / `dscr_hp_vals` are the fitter's (euclidean_gp.py:222-320); for this layout
+      the only discrete hp is the Matern nu.  Returns what the reference returns:
+        ('fitted_gp', gp, (cts_hps, dscr_hps))   or   ('sample_hps_with_probs', cts, dscr, [None] * n, probs). """
+  from itertools import product as itertools_product
+  from .gp_core import GP, ConstantMean
+  from .gpb_acquisitions import map_to_bounds, _reference_fortran_direct_available
+  X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+  Y = np.asarray(Y, dtype=np.float64)
+  bounds = np.asarray(cts_hp_bounds, dtype=np.float64)
+  dscr_hp_vals = [list(v) for v in dscr_hp_vals]
+  if len(dscr_hp_vals) > 1:
+    raise NotImplementedError('Only the Matern nu is a discrete hyper-parameter on the device path.')
+  if max_evals is None:
+    max_evals = default_max_evals(method, len(bounds) + len(dscr_hp_vals))
+  n_evals = int(max_evals)
+  state = {'post': None}
+
+  def lmls_of(hps, nus):
+    vals, state['post'] = lml_for_hyperparams(X, Y, hps, layout, nus=nus, post=state['post'], device=device)
+    return vals
+
+  def build(cts, dscr):
+    mean_const, noise_var, kern = layout.unpack(cts, Y, dscr[0] if len(dscr) > 0 else None)
+    make = GP if gp_factory is None else gp_factory
+    return make(list(X), list(Y), kern, ConstantMean(mean_const), noise_var)
+
+  if method == 'rand_exp_sampling':
+    cts = map_to_bounds(np.random.random((n_evals, len(bounds))), bounds)
+    dscr = [[np.random.choice(categ) for categ in dscr_hp_vals] for _ in range(n_evals)]
+    vals = lmls_of(cts, [d[0] for d in dscr] if dscr_hp_vals else None)
+    return 'sample_hps_with_probs', cts, dscr, [None] * n_evals, rand_exp_sampling_probs(vals)
+  if method == 'direct' and _reference_fortran_direct_available():
+    raise NotImplementedError('Fortran DIRECT is a sequential host optimiser; use pdoo / rand / rand_exp_sampling.')
+  if method not in ('rand', 'pdoo', 'direct'):
+    raise ValueError('Unknown ml_hp_tune_opt method %s.' % (method))
+  best_val, best_cts, best_dscr = -np.inf, None, None
+  for dscr in itertools_product(*dscr_hp_vals):
+    nu = dscr[0] if len(dscr) > 0 else None
+    if method == 'rand':
+      pts = map_to_bounds(np.random.random((n_evals, len(bounds))), bounds)
+      vals = lmls_of(pts, None if nu is None else [nu] * len(pts))
+      idx = int(np.argmax(vals))
+      opt_val, opt_pt = vals[idx], pts[idx]
+    else:
+      from .doo import pdoo_maximise
+      opt_val, opt_pt, _ = pdoo_maximise(lambda P: lmls_of(P, None if nu is None else [nu] * len(P)), bounds,
+                                         max_evals)
+    if opt_val > best_val:
+      best_val, best_cts, best_dscr = opt_val, list(opt_pt), list(dscr)
+  return 'fitted_gp', build(best_cts, best_dscr), (best_cts, best_dscr)
+
+
 def rand_exp_sampling_probs(lml_vals):
   """ gp_core.py:443-444 """
   lml_vals = np.asarray(lml_vals, dtype=np.float64)

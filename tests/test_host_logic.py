@@ -488,3 +488,52 @@ def test_extension_algebra_of_dfb_extend_posterior():
   np.testing.assert_allclose(v, v1, rtol=0, atol=1e-10)
   # rows above the last block are untouched by construction
   assert (L[:m0, :m0] == L0[:m0, :m0]).all()
+
+
+# ---- hp_grid.fit_gp against the reference's EuclideanGPFitter (golden fitter.npz), LMLs from the oracle -------------
+@pytest.mark.parametrize('method', ['rand', 'rand_exp_sampling', 'pdoo'])
+def test_fit_gp_selects_what_the_reference_fitter_selects(method, monkeypatch):
+  from conftest import load_golden
+  from dragonfly_b200 import hp_grid
+  g = load_golden('fitter')
+  X, Y = g['X'], g['Y']
+  layout = hp_grid.EuclideanHPLayout(3, 'matern', mean_func_type=str(g['mean_func_type']),
+                                     noise_var_type=str(g['noise_var_type']))
+  calls = []
+
+  def oracle_lmls(X_, Y_, hps, layout_, nus=None, post=None, device=None, lanes=None):
+    calls.append(len(hps))
+    out = []
+    for i, hp in enumerate(hps):
+      m, nv, k = layout_.unpack(hp, Y_, None if nus is None else nus[i])
+      ok = O.OMaternKernel(3, k.hyperparams['nu'], k.hyperparams['scale'], k.hyperparams['dim_bandwidths'])
+      out.append(O.OGP(X_, Y_, ok, lambda x, c=m: np.array([c] * len(x)), nv).compute_log_marginal_likelihood())
+    return np.array(out), post
+  monkeypatch.setattr(hp_grid, 'lml_for_hyperparams', oracle_lmls)
+
+  def oracle_gp(Xl, Yl, kern, mean, noise):
+    ok = O.OMaternKernel(3, kern.hyperparams['nu'], kern.hyperparams['scale'], kern.hyperparams['dim_bandwidths'])
+    return O.OGP(np.array(Xl), np.array(Yl), ok, mean, noise)
+  np.random.seed(5)
+  res = hp_grid.fit_gp(X, Y, layout, g[method + '_bounds'], g[method + '_dscr_vals'], method=method,
+                       max_evals=int(g[method + '_max_evals']), gp_factory=oracle_gp)
+  if method == 'rand_exp_sampling':
+    tag, cts, dscr, other, probs = res
+    assert tag == 'sample_hps_with_probs' and other == [None] * len(cts)
+    assert (cts == g[method + '_cts']).all() and (np.array(dscr) == g[method + '_dscr']).all()
+    np.testing.assert_allclose(probs, g[method + '_probs'], rtol=1e-9, atol=1e-15)
+    assert calls == [len(cts)]                                # every sample in ONE batched call
+  else:
+    tag, gp, (cts, dscr) = res
+    assert tag == 'fitted_gp'
+    assert (np.array(cts) == g[method + '_cts']).all() and (np.array(dscr) == g[method + '_dscr']).all()
+    np.testing.assert_allclose(gp.compute_log_marginal_likelihood(), float(g[method + '_lml']), rtol=1e-12)
+    mu, sd = gp.eval(g[method + '_C'], 'std')
+    np.testing.assert_allclose(mu, g[method + '_mu'], atol=1e-10)
+    np.testing.assert_allclose(sd, g[method + '_sd'], atol=1e-9)
+    if method == 'rand':
+      assert calls == [int(g[method + '_max_evals'])] * 3     # one batch per discrete nu
+    else:
+      assert max(calls) <= 2                                  # PDOO: the two children of a split per call
+  assert hp_grid.default_max_evals('rand', 8) == 1600 and hp_grid.default_max_evals('pdoo', 8) == 500
+  assert hp_grid.default_max_evals('rand_exp_sampling', 8) == 3200
