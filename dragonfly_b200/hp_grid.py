@@ -41,6 +41,32 @@ class EuclideanHPLayout(object):
     n += 1 if self.noise_var_type == 'tune' else 0
     return n
 
+  def bounds(self, X, Y, tune_nu=None):
+    """ (cts_hp_bounds, dscr_hp_vals) the way the reference's fitter sets them up from the data
+        (gp_core.py:336-338, 396-416; euclidean_gp.py:253-276): mean value (if tuned), log noise (if tuned),
+        log scale, log bandwidth(s); discrete [0.5, 1.5, 2.5] for a Matern kernel whose nu is tuned
+        (options.matern_nu < 0; default here: tuned iff self.nu is None or negative). """
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    Y_var = Y.std() ** 2 + 0.0001 if len(Y) > 0 else 0.0001
+    out = []
+    if self.mean_func_type == 'tune':
+      Y_std = np.sqrt(Y_var)
+      Y_median = np.median(Y) if len(Y) > 0 else 0.0
+      Y_half_range = 0.5 * (max(Y) - min(Y)) if len(Y) > 0 else 1.0
+      Y_width = 0.5 * (Y_half_range + Y_std)
+      out.append([Y_median - 3 * Y_width, Y_median + 3 * Y_width])
+    if self.noise_var_type == 'tune':
+      out.append([np.log(0.005 * Y_var), np.log(0.2 * Y_var)])
+    out.append([np.log(0.1 * Y_var), np.log(10 * Y_var)])
+    X_std_norm = np.linalg.norm(X, 'fro') + 1e-4
+    single = [np.log(0.01 * X_std_norm), np.log(10 * X_std_norm)]
+    out += [single] * (1 if self.use_same_bandwidth else self.dim)
+    if tune_nu is None:
+      tune_nu = self.kernel_type == 'matern' and (self.nu is None or self.nu < 0)
+    dscr = [[0.5, 1.5, 2.5]] if (self.kernel_type == 'matern' and tune_nu) else []
+    return np.array(out), dscr
+
   def unpack(self, hp, Y, nu=None):
     """ gp_core.py:509-538 + euclidean_gp.py:801-861 """
     hp = list(np.asarray(hp, dtype=np.float64))

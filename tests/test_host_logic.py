@@ -535,5 +535,9 @@ def test_fit_gp_selects_what_the_reference_fitter_selects(method, monkeypatch):
       assert calls == [int(g[method + '_max_evals'])] * 3     # one batch per discrete nu
     else:
       assert max(calls) <= 2                                  # PDOO: the two children of a split per call
+  # the bounds the reference's fitter derives from the data (gp_core.py:396-416, euclidean_gp.py:253-276)
+  b, dv = hp_grid.EuclideanHPLayout(3, 'matern', nu=-1.0, mean_func_type=str(g['mean_func_type']),
+                                    noise_var_type=str(g['noise_var_type'])).bounds(X, Y)
+  assert (b == g[method + '_bounds']).all() and (np.array(dv) == g[method + '_dscr_vals']).all()
   assert hp_grid.default_max_evals('rand', 8) == 1600 and hp_grid.default_max_evals('pdoo', 8) == 500
   assert hp_grid.default_max_evals('rand_exp_sampling', 8) == 3200
