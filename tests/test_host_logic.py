@@ -541,3 +541,33 @@ def test_fit_gp_selects_what_the_reference_fitter_selects(method, monkeypatch):
   assert (b == g[method + '_bounds']).all() and (np.array(dv) == g[method + '_dscr_vals']).all()
   assert hp_grid.default_max_evals('rand', 8) == 1600 and hp_grid.default_max_evals('pdoo', 8) == 500
   assert hp_grid.default_max_evals('rand_exp_sampling', 8) == 3200
+
+
+# ---- property tests of the multi-rank arg-max reduction (no process group needed) ---------------------------------
+def test_sharded_reduction_equals_numpy_argmax_property():
+  """ For any score vector (ties, NaNs, infinities) and any number of ranks, reducing the per-shard winners with
+      dist.reduce_pairs gives np.argmax of the whole vector. """
+  from hypothesis import given, settings, strategies as st
+  from dragonfly_b200 import dist as D
+
+  vals = st.one_of(st.floats(allow_nan=True, allow_infinity=True, width=64),
+                   st.sampled_from([0.0, 1.0, -1.0, 7.5]))          # plenty of exact ties
+
+  @settings(max_examples=300, deadline=None)
+  @given(st.lists(vals, min_size=1, max_size=60), st.integers(min_value=1, max_value=9))
+  def check(scores, world):
+    s = np.array(scores, dtype=np.float64)
+    winners_s, winners_i = [], []
+    for r in range(world):
+      lo, hi = D.shard_bounds(len(s), r, world)
+      if hi > lo:
+        j = int(np.argmax(s[lo:hi]))
+        winners_s.append(s[lo + j]); winners_i.append(lo + j)
+      else:
+        winners_s.append(0.0); winners_i.append(-1)
+    _, idx = D.reduce_pairs(winners_s, winners_i)
+    assert idx == int(np.argmax(s))
+  check()
+  # the K-at-once variant without a process group is the identity
+  sc, ix = D.all_reduce_argmax_many([1.0, np.nan], [4, 9])
+  assert sc[0] == 1.0 and np.isnan(sc[1]) and ix.tolist() == [4, 9]
