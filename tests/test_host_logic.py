@@ -571,3 +571,81 @@ def test_sharded_reduction_equals_numpy_argmax_property():
   # the K-at-once variant without a process group is the identity
   sc, ix = D.all_reduce_argmax_many([1.0, np.nan], [4, 9])
   assert sc[0] == 1.0 and np.isnan(sc[1]) and ix.tolist() == [4, 9]
+
+
+def test_fit_gp_through_the_lane_machinery_with_a_numpy_device(monkeypatch):
+  """ hp_grid.fit_gp -> lml_for_hyperparams with 3 concurrent lanes (threads, one posterior each), per-sample Matern
+      nu and a tuned mean (set_train per sample) -- everything except CUDA itself: DevicePosterior is replaced by a
+      NumPy stand-in and torch.cuda's stream / device context managers by no-ops.  Same selections as the reference. """
+  import contextlib
+  import threading
+  import torch
+  from conftest import load_golden
+  from dragonfly_b200 import hp_grid, device as dfb_device
+  g = load_golden('fitter')
+  X, Y = g['X'], g['Y']
+  seen_threads, builds = set(), []
+
+  class FakeDevice(object):
+    index = 0
+
+  class LanePost(object):
+    def __init__(self, n_max, device=None):
+      self.n_max, self.device = n_max, FakeDevice()
+
+    def bind_current_stream(self):
+      seen_threads.add(threading.get_ident())
+
+    def set_train(self, Xm, yc):
+      self.X, self.yc = np.array(Xm), np.array(yc)
+
+    def set_kernel(self, kern):                      # build_descriptor is patched to hand the kernel object through
+      self.kern = O.OMaternKernel(3, kern.hyperparams['nu'], kern.hyperparams['scale'],
+                                  kern.hyperparams['dim_bandwidths'])
+
+    def build(self, noise_var, jitter, flags):
+      assert flags == hp_grid._lib.DFB_BUILD_LML_ONLY
+      builds.append(threading.get_ident())
+      gp = O.OGP(self.X, self.yc, self.kern, lambda x: np.zeros(len(x)), noise_var + jitter)
+      return 0, gp.compute_log_marginal_likelihood()
+
+  class FakeStream(object):
+    def __init__(self, *a, **k):
+      pass
+
+    def wait_stream(self, other):
+      pass
+  monkeypatch.setattr(dfb_device, 'DevicePosterior', LanePost)
+  monkeypatch.setattr(hp_grid, 'build_descriptor', lambda kern, **kw: kern)
+  monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: FakeStream())
+  monkeypatch.setattr(torch.cuda, 'Stream', FakeStream)
+  monkeypatch.setattr(torch.cuda, 'device', lambda *a, **k: contextlib.nullcontext())
+  monkeypatch.setattr(torch.cuda, 'stream', lambda *a, **k: contextlib.nullcontext())
+  layout = hp_grid.EuclideanHPLayout(3, 'matern', mean_func_type=str(g['mean_func_type']),
+                                     noise_var_type=str(g['noise_var_type']))
+  oracle_gp = lambda Xl, Yl, kern, mean, noise: O.OGP(
+      np.array(Xl), np.array(Yl), O.OMaternKernel(3, kern.hyperparams['nu'], kern.hyperparams['scale'],
+                                                  kern.hyperparams['dim_bandwidths']), mean, noise)
+  np.random.seed(5)
+  tag, gp, (cts, dscr) = hp_grid.fit_gp(X, Y, layout, g['rand_bounds'], g['rand_dscr_vals'], method='rand',
+                                        max_evals=int(g['rand_max_evals']), gp_factory=oracle_gp)
+  assert (np.array(cts) == g['rand_cts']).all() and (np.array(dscr) == g['rand_dscr']).all()
+  assert len(seen_threads) == 3 and len(set(builds)) == 3 and len(builds) == 3 * int(g['rand_max_evals'])
+  np.random.seed(5)
+  tag, cts, dscr, other, probs = hp_grid.fit_gp(X, Y, layout, g['rand_exp_sampling_bounds'],
+                                                g['rand_exp_sampling_dscr_vals'], method='rand_exp_sampling',
+                                                max_evals=int(g['rand_exp_sampling_max_evals']))
+  assert (cts == g['rand_exp_sampling_cts']).all()
+  np.testing.assert_allclose(probs, g['rand_exp_sampling_probs'], rtol=1e-9, atol=1e-15)
+  del builds[:]
+  tag, gp, (cts, dscr) = hp_grid.fit_gp(X, Y, layout, g['pdoo_bounds'], g['pdoo_dscr_vals'], method='pdoo',
+                                        max_evals=int(g['pdoo_max_evals']), gp_factory=oracle_gp)
+  assert (np.array(cts) == g['pdoo_cts']).all() and (np.array(dscr) == g['pdoo_dscr']).all()
+  assert len(set(builds)) == 1                       # batches of <= 2 hp vectors stay on the calling thread
+  # an exception inside a lane surfaces in the caller
+  def boom(self, noise_var, jitter, flags):
+    raise RuntimeError('lane failure')
+  monkeypatch.setattr(LanePost, 'build', boom)
+  with pytest.raises(RuntimeError):
+    hp_grid.lml_for_hyperparams(X, Y, np.tile((g['rand_bounds'][:, 0] + g['rand_bounds'][:, 1]) / 2, (9, 1)), layout,
+                                nus=[2.5] * 9, lanes=3)
