@@ -17,7 +17,7 @@ CPU tests of the sharding logic).
 import numpy as np
 
 from . import _lib
-from .kernel import SEKernel, MaternKernel, build_descriptor
+from .kernel import SEKernel, MaternKernel, AdditiveKernel, build_descriptor
 from .gp_core import stable_cholesky_on_device
 
 
@@ -26,7 +26,8 @@ class EuclideanHPLayout(object):
 
   def __init__(self, dim, kernel_type='matern', nu=2.5, use_same_bandwidth=False,
                mean_func_type='median', mean_func_const=0.0, noise_var_type='tune',
-               noise_var_label=0.05, noise_var_value=0.1):
+               noise_var_label=0.05, noise_var_value=0.1, use_additive_gp=False, add_max_group_size=6,
+               num_groups_per_group_size=-1):
     if kernel_type not in ('se', 'matern'):
       raise NotImplementedError('kernel_type %s is outside the B200 hot-path scope.' % (kernel_type))
     self.dim, self.kernel_type, self.nu = dim, kernel_type, nu
@@ -34,6 +35,11 @@ class EuclideanHPLayout(object):
     self.mean_func_type, self.mean_func_const = mean_func_type, mean_func_const
     self.noise_var_type = noise_var_type
     self.noise_var_label, self.noise_var_value = noise_var_label, noise_var_value
+    # additive models (euclidean_gp.py:50-60, 243-248): the group size is one more discrete hyper-parameter and
+    # every objective evaluation carries a random grouping of the coordinates
+    self.use_additive_gp = use_additive_gp
+    self.add_max_group_size = min(add_max_group_size, dim)
+    self.num_groups_per_group_size = num_groups_per_group_size
 
   def num_hps(self):
     n = 1 + (1 if self.use_same_bandwidth else self.dim)
@@ -65,9 +71,11 @@ class EuclideanHPLayout(object):
     if tune_nu is None:
       tune_nu = self.kernel_type == 'matern' and (self.nu is None or self.nu < 0)
     dscr = [[0.5, 1.5, 2.5]] if (self.kernel_type == 'matern' and tune_nu) else []
+    if self.use_additive_gp:
+      dscr.append([x + 1 for x in range(self.add_max_group_size)])
     return np.array(out), dscr
 
-  def unpack(self, hp, Y, nu=None):
+  def unpack(self, hp, Y, nu=None, groupings=None):
     """ gp_core.py:509-538 + euclidean_gp.py:801-861 """
     hp = list(np.asarray(hp, dtype=np.float64))
     Y = np.asarray(Y, dtype=np.float64)
@@ -95,10 +103,18 @@ class EuclideanHPLayout(object):
     else:
       bws = [np.exp(hp.pop(0)) for _ in range(self.dim)]
     assert len(hp) == 0
-    if self.kernel_type == 'se':
+    nu = self.nu if nu is None else nu
+    if groupings is not None:
+      # get_euclidean_integral_gp_kernel_with_scale (euclidean_gp.py:826-831, 850-861, 895-897): group kernels
+      # with scale 1 on their own bandwidths, the outer scale on the sum
+      groups = [[int(i) for i in grp] for grp in groupings]
+      make = (lambda grp: SEKernel(len(grp), 1.0, [bws[i] for i in grp])) if self.kernel_type == 'se' else \
+             (lambda grp: MaternKernel(len(grp), nu, 1.0, [bws[i] for i in grp]))
+      kern = AdditiveKernel(scale, [make(grp) for grp in groups], groups)
+    elif self.kernel_type == 'se':
       kern = SEKernel(self.dim, scale, bws)
     else:
-      kern = MaternKernel(self.dim, self.nu if nu is None else nu, scale, bws)
+      kern = MaternKernel(self.dim, nu, scale, bws)
     return float(mean_const), float(noise_var), kern
 
 
@@ -110,13 +126,14 @@ class EuclideanHPLayout(object):
 DEFAULT_LANES = 3
 
 
-def _lane_worker(lane_post, stream, X, Y, hps, idxs, layout, nus, out):
+def _lane_worker(lane_post, stream, X, Y, hps, idxs, layout, nus, out, groupings=None):
   import torch
   with torch.cuda.device(lane_post.device), torch.cuda.stream(stream):
     lane_post.bind_current_stream()
     last_mean = None
     for i in idxs:
-      mean_const, noise_var, kern = layout.unpack(hps[i], Y, None if nus is None else nus[i])
+      mean_const, noise_var, kern = layout.unpack(hps[i], Y, None if nus is None else nus[i],
+                                                  None if groupings is None else groupings[i])
       if last_mean is None or mean_const != last_mean:
         lane_post.set_train(X, Y - mean_const)
         last_mean = mean_const
@@ -124,7 +141,7 @@ def _lane_worker(lane_post, stream, X, Y, hps, idxs, layout, nus, out):
       out[i], _ = stable_cholesky_on_device(lane_post, noise_var, flags=_lib.DFB_BUILD_LML_ONLY)
 
 
-def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lanes=None):
+def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lanes=None, groupings=None):
   """ LML of the GP built from each hp vector (rows of `hps`); `nus` optionally gives the discrete
       Matern nu per sample.  Returns (lmls, post) -- `post` can be passed back in to reuse the
       device workspaces (it carries the extra lanes). """
@@ -140,7 +157,8 @@ def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lan
     lanes = DEFAULT_LANES if len(hps) >= 2 * DEFAULT_LANES else 1
   lanes = max(1, min(int(lanes), len(hps)))
   if lanes == 1:
-    _lane_worker(post, torch.cuda.current_stream(post.device), X, Y, hps, range(len(hps)), layout, nus, lmls)
+    _lane_worker(post, torch.cuda.current_stream(post.device), X, Y, hps, range(len(hps)), layout, nus, lmls,
+                 groupings)
     return lmls, post
   extra = getattr(post, '_hp_lanes', [])
   while len(extra) < lanes - 1:
@@ -158,10 +176,10 @@ def lml_for_hyperparams(X, Y, hps, layout, nus=None, post=None, device=None, lan
     lane_post, stream = extra[j - 1]
     stream.wait_stream(main_stream)
     t = threading.Thread(target=guarded, args=(lane_post, stream, X, Y, hps, range(j, len(hps), lanes), layout,
-                                               nus, lmls))
+                                               nus, lmls, groupings))
     t.start()
     workers.append(t)
-  guarded(post, main_stream, X, Y, hps, range(0, len(hps), lanes), layout, nus, lmls)
+  guarded(post, main_stream, X, Y, hps, range(0, len(hps), lanes), layout, nus, lmls, groupings)
   for t in workers:
     t.join()
   for j in range(1, lanes):
@@ -205,23 +223,47 @@ def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampli
   Y = np.asarray(Y, dtype=np.float64)
   bounds = np.asarray(cts_hp_bounds, dtype=np.float64)
   dscr_hp_vals = [list(v) for v in dscr_hp_vals]
-  if len(dscr_hp_vals) > 1:
-    raise NotImplementedError('Only the Matern nu is a discrete hyper-parameter on the device path.')
+  additive = bool(getattr(layout, 'use_additive_gp', False))
+  if len(dscr_hp_vals) > (2 if additive else 1):
+    raise NotImplementedError('Discrete hyper-parameters on the device path: the Matern nu and, for additive '
+                              'models, the group size.')
+  has_nu = len(dscr_hp_vals) == (2 if additive else 1)       # [nu]? then [group size]? (euclidean_gp.py:226-248)
+  dim = layout.dim
   if max_evals is None:
     max_evals = default_max_evals(method, len(bounds) + len(dscr_hp_vals))
   n_evals = int(max_evals)
   state = {'post': None}
 
-  def lmls_of(hps, nus):
-    vals, state['post'] = lml_for_hyperparams(X, Y, hps, layout, nus=nus, post=state['post'], device=device)
+  def lmls_of(hps, nus, groupings=None):
+    vals, state['post'] = lml_for_hyperparams(X, Y, hps, layout, nus=nus, post=state['post'], device=device,
+                                              groupings=groupings)
     return vals
 
-  def build(cts, dscr):
-    mean_const, noise_var, kern = layout.unpack(cts, Y, dscr[0] if len(dscr) > 0 else None)
+  def build(cts, dscr, groupings=None):
+    mean_const, noise_var, kern = layout.unpack(cts, Y, dscr[0] if has_nu else None, groupings)
     make = GP if gp_factory is None else gp_factory
     return make(list(X), list(Y), kern, ConstantMean(mean_const), noise_var)
 
+  def random_grouping(group_size):
+    rand_perm = list(np.random.permutation(dim))               # euclidean_gp.py:733-735, 760-761
+    return [rand_perm[i:i + group_size] for i in range(0, dim, group_size)]
+
   if method == 'rand_exp_sampling':
+    if additive:
+      # sample_cts_dscr_hps_for_rand_exp_sampling_in_add_model (euclidean_gp.py:749-776): per sample a group size, a
+      # random grouping, the discrete hps (group size overwritten), the continuous hps -- in that RNG order; the
+      # weights are exp(lml) / sum WITHOUT subtracting the maximum, as written there
+      cts, dscr, groupings = [], [], []
+      for _ in range(n_evals):
+        group_size = np.random.choice(dscr_hp_vals[-1])
+        groupings.append(random_grouping(group_size))
+        cur = [np.random.choice(categ) for categ in dscr_hp_vals]
+        cur[-1] = group_size
+        dscr.append(cur)
+        cts.append(map_to_bounds(np.random.random((len(bounds),)), bounds))
+      vals = lmls_of(np.array(cts), [d[0] for d in dscr] if has_nu else None, groupings)
+      probs = np.exp(vals)
+      return 'sample_hps_with_probs', cts, dscr, groupings, probs / probs.sum()
     cts = map_to_bounds(np.random.random((n_evals, len(bounds))), bounds)
     dscr = [[np.random.choice(categ) for categ in dscr_hp_vals] for _ in range(n_evals)]
     vals = lmls_of(cts, [d[0] for d in dscr] if dscr_hp_vals else None)
@@ -230,21 +272,40 @@ def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampli
     raise NotImplementedError('Fortran DIRECT is a sequential host optimiser; use pdoo / rand / rand_exp_sampling.')
   if method not in ('rand', 'pdoo', 'direct'):
     raise ValueError('Unknown ml_hp_tune_opt method %s.' % (method))
-  best_val, best_cts, best_dscr = -np.inf, None, None
-  for dscr in itertools_product(*dscr_hp_vals):
-    nu = dscr[0] if len(dscr) > 0 else None
+
+  def optimise_cts(nu, evals, groupings=None):
+    """ cts_hp_optimise (gp_core.py:463-472) for one setting of the discrete hps (and one grouping). """
+    rep = (lambda k: None) if groupings is None else (lambda k: [groupings] * k)
     if method == 'rand':
-      pts = map_to_bounds(np.random.random((n_evals, len(bounds))), bounds)
-      vals = lmls_of(pts, None if nu is None else [nu] * len(pts))
+      pts = map_to_bounds(np.random.random((int(evals), len(bounds))), bounds)
+      vals = lmls_of(pts, None if nu is None else [nu] * len(pts), rep(len(pts)))
       idx = int(np.argmax(vals))
-      opt_val, opt_pt = vals[idx], pts[idx]
+      return vals[idx], pts[idx]
+    from .doo import pdoo_maximise
+    val, pt, _ = pdoo_maximise(lambda P: lmls_of(P, None if nu is None else [nu] * len(P), rep(len(P))), bounds,
+                               evals)
+    return val, pt
+
+  best_val, best_cts, best_dscr, best_groupings = -np.inf, None, None, None
+  for dscr in itertools_product(*dscr_hp_vals):
+    nu = dscr[0] if has_nu else None
+    if not additive:
+      opt_val, opt_pt, opt_groupings = optimise_cts(nu, max_evals) + (None,)
     else:
-      from .doo import pdoo_maximise
-      opt_val, opt_pt, _ = pdoo_maximise(lambda P: lmls_of(P, None if nu is None else [nu] * len(P)), bounds,
-                                         max_evals)
+      # optimise_cts_hps_for_given_dscr_hps_in_add_model (euclidean_gp.py:718-746)
+      group_size = dscr[-1]
+      n_groupings = layout.num_groups_per_group_size
+      if n_groupings < 0:
+        n_groupings = 1 if group_size == 1 else max(5, min(2 * dim, 25))
+      opt_val, opt_pt, opt_groupings = -np.inf, None, None
+      for _ in range(n_groupings):
+        groupings = random_grouping(group_size)
+        val, pt = optimise_cts(nu, int(max(500, max_evals / n_groupings)), groupings)
+        if val > opt_val:
+          opt_val, opt_pt, opt_groupings = val, pt, groupings
     if opt_val > best_val:
-      best_val, best_cts, best_dscr = opt_val, list(opt_pt), list(dscr)
-  return 'fitted_gp', build(best_cts, best_dscr), (best_cts, best_dscr)
+      best_val, best_cts, best_dscr, best_groupings = opt_val, list(opt_pt), list(dscr), opt_groupings
+  return 'fitted_gp', build(best_cts, best_dscr, best_groupings), (best_cts, best_dscr)
 
 
 def rand_exp_sampling_probs(lml_vals):

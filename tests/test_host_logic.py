@@ -501,7 +501,7 @@ def test_fit_gp_selects_what_the_reference_fitter_selects(method, monkeypatch):
                                      noise_var_type=str(g['noise_var_type']))
   calls = []
 
-  def oracle_lmls(X_, Y_, hps, layout_, nus=None, post=None, device=None, lanes=None):
+  def oracle_lmls(X_, Y_, hps, layout_, nus=None, post=None, device=None, lanes=None, groupings=None):
     calls.append(len(hps))
     out = []
     for i, hp in enumerate(hps):
@@ -649,3 +649,61 @@ def test_fit_gp_through_the_lane_machinery_with_a_numpy_device(monkeypatch):
   with pytest.raises(RuntimeError):
     hp_grid.lml_for_hyperparams(X, Y, np.tile((g['rand_bounds'][:, 0] + g['rand_bounds'][:, 1]) / 2, (9, 1)), layout,
                                 nus=[2.5] * 9, lanes=3)
+
+
+def _oracle_kernel_of(kern):
+  """ Our kernel mirror -> the oracle's kernel object (plain Matern or additive of Materns). """
+  if hasattr(kern, 'kernel_list'):
+    return O.OAdditiveKernel(kern.hyperparams['scale'],
+                             [O.OMaternKernel(k.dim, k.hyperparams['nu'], k.hyperparams['scale'],
+                                              k.hyperparams['dim_bandwidths']) for k in kern.kernel_list],
+                             kern.groupings)
+  return O.OMaternKernel(kern.dim, kern.hyperparams['nu'], kern.hyperparams['scale'],
+                         kern.hyperparams['dim_bandwidths'])
+
+
+@pytest.mark.parametrize('method', ['rand', 'rand_exp_sampling'])
+def test_fit_gp_additive_model_matches_the_reference_fitter(method, monkeypatch):
+  """ use_additive_gp (euclidean_gp.py:243-248, 718-776; kernels :826-897): random groupings per objective
+      evaluation, the group size as a discrete hyper-parameter -- against golden fitter_add.npz (the reference's
+      EuclideanGPFitter under np.random.seed(7)); LMLs from the oracle. """
+  from conftest import load_golden
+  from dragonfly_b200 import hp_grid
+  g = load_golden('fitter_add')
+  X, Y = g['X'], g['Y']
+  layout = hp_grid.EuclideanHPLayout(5, 'matern', nu=-1.0, mean_func_type=str(g['mean_func_type']),
+                                     noise_var_type=str(g['noise_var_type']), use_additive_gp=True,
+                                     add_max_group_size=3, num_groups_per_group_size=2)
+  b, dv = layout.bounds(X, Y)
+  assert (b == g[method + '_bounds']).all()
+  assert dv == [list(g[method + '_dscr_vals_nu']), [int(v) for v in g[method + '_dscr_vals_grp']]]
+
+  def oracle_lmls(X_, Y_, hps, layout_, nus=None, post=None, device=None, lanes=None, groupings=None):
+    out = []
+    for i, hp in enumerate(hps):
+      m, nv, k = layout_.unpack(hp, Y_, None if nus is None else nus[i], None if groupings is None else groupings[i])
+      out.append(O.OGP(X_, Y_, _oracle_kernel_of(k), lambda x, c=m: np.array([c] * len(x)),
+                       nv).compute_log_marginal_likelihood())
+    return np.array(out), post
+  monkeypatch.setattr(hp_grid, 'lml_for_hyperparams', oracle_lmls)
+  oracle_gp = lambda Xl, Yl, kern, mean, noise: O.OGP(np.array(Xl), np.array(Yl), _oracle_kernel_of(kern), mean, noise)
+  np.random.seed(7)
+  res = hp_grid.fit_gp(X, Y, layout, b, dv, method=method, max_evals=int(g[method + '_max_evals']),
+                       gp_factory=oracle_gp)
+  unpad = lambda rows: [[int(v) for v in r if v >= 0] for r in rows if (np.asarray(r) >= 0).any()]
+  if method == 'rand':
+    tag, gp, (cts, dscr) = res
+    assert tag == 'fitted_gp'
+    assert (np.array(cts) == g['rand_cts']).all() and (np.array(dscr, dtype=np.float64) == g['rand_dscr']).all()
+    assert [list(map(int, grp)) for grp in gp.kernel.groupings] == unpad(g['rand_groupings'])
+    np.testing.assert_allclose(gp.compute_log_marginal_likelihood(), float(g['rand_lml']), rtol=1e-12)
+    mu, sd = gp.eval(g['rand_C'], 'std')
+    np.testing.assert_allclose(mu, g['rand_mu'], atol=1e-10)
+    np.testing.assert_allclose(sd, g['rand_sd'], atol=1e-9)
+  else:
+    tag, cts, dscr, groupings, probs = res
+    assert tag == 'sample_hps_with_probs'
+    assert (np.array(cts) == g[method + '_cts']).all()
+    assert (np.array(dscr, dtype=np.float64) == g[method + '_dscr']).all()
+    assert [[list(map(int, grp)) for grp in gs] for gs in groupings] == [unpad(gs) for gs in g[method + '_groupings']]
+    np.testing.assert_allclose(probs, g[method + '_probs'], rtol=1e-9, atol=1e-300)
