@@ -194,6 +194,13 @@ class GP(object):
         inputs (multi-fidelity [z || x] rows) override this. """
     return _as_2d(self.X)
 
+  def _get_training_kernel_matrix(self):
+    """ gp_core.py:149-153: K(X, X) without noise, evaluated on the device (Kernel.__call__ -> dfb_kernel_matrix).
+        build_posterior does not need it -- the device forms K inside dfb_build_posterior -- but subclasses and
+        callers of the reference may. """
+    X_mat = self._train_matrix()
+    return self.kernel(X_mat, X_mat)
+
   def _new_device_posterior(self, n_max):
     from .device import DevicePosterior
     return DevicePosterior(n_max, device=getattr(self, '_device', None))

@@ -89,6 +89,16 @@ class SEKernel(Kernel):
   def change_smoothness(self, factor):
     self.hyperparams['dim_bandwidths'] *= factor
 
+  # host-side metadata helpers of the reference's SEKernel (kernel.py:179-190): no kernel evaluation involved
+  def get_scaled_repr(self, X):
+    return X / self.hyperparams['dim_bandwidths']
+
+  def get_effective_norm(self, X, order=None, is_single=True):
+    scaled_X = self.get_scaled_repr(X)
+    if is_single:
+      return np.linalg.norm(scaled_X, ord=order)
+    return np.array([np.linalg.norm(sx, ord=order) for sx in scaled_X])
+
   def __str__(self):
     return 'SE: sc:%0.4f avg-bw: %0.4f' % (self.hyperparams['scale'],
                                            np.mean(self.hyperparams['dim_bandwidths']))

@@ -120,6 +120,11 @@ class EuclideanMFGP(GP):
   def add_mf_data_single(self, zz_new, xx_new, yy_new, *args, **kwargs):
     self.add_mf_data_multiple([zz_new], [xx_new], [yy_new], *args, **kwargs)
 
+  def draw_mf_samples(self, num_samples, ZZ_test=None, XX_test=None, *args, **kwargs):
+    """ mf_gp.py:88-91 """
+    ZX_test = None if ZZ_test is None else self.get_ZX_matrix(ZZ_test, XX_test)
+    return self.draw_samples(num_samples, ZX_test, *args, **kwargs)
+
   def get_fidel_kernel(self):
     return self.fidel_kernel
 

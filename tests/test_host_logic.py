@@ -707,3 +707,16 @@ def test_fit_gp_additive_model_matches_the_reference_fitter(method, monkeypatch)
     assert (np.array(dscr, dtype=np.float64) == g[method + '_dscr']).all()
     assert [[list(map(int, grp)) for grp in gs] for gs in groupings] == [unpad(gs) for gs in g[method + '_groupings']]
     np.testing.assert_allclose(probs, g[method + '_probs'], rtol=1e-9, atol=1e-300)
+
+
+def test_se_effective_norm_known_answers():
+  """ dragonfly/gp/unittest_kernel.py:153-176 (test_effective_length_se), restated. """
+  data_1, data_2 = np.array([1, 2]), np.array([[0, 1, 2], [1, 1, 0.5]])
+  k1, k2 = K.SEKernel(2, 1, [0.1, 1]), K.SEKernel(3, 1, [0.5, 1, 2])
+  assert abs(k1.get_effective_norm(data_1, order=2, is_single=True) - np.sqrt(104)) < 1e-5
+  assert abs(k1.get_effective_norm(data_1, order=1, is_single=True) - 12) < 1e-5
+  assert np.linalg.norm(k2.get_effective_norm(data_2, order=2, is_single=False) -
+                        np.array([np.sqrt(2), np.sqrt(5.0625)])) < 1e-5
+  assert np.linalg.norm(k2.get_effective_norm(data_2, order=1, is_single=False) - np.array([2, 3.25])) < 1e-5
+  k2.change_smoothness(2.0)
+  assert (k2.hyperparams['dim_bandwidths'] == np.array([1.0, 2.0, 4.0])).all()
