@@ -1,0 +1,191 @@
+"""
+The drop-in inside the reference's OWN Bayesian-optimisation loop (authoring container only: needs /root/reference).
+
+INTEGRATION.md section 2 is applied to the reference's classes (GP numerics re-bound, acquisition tables replaced)
+and `dragonfly.maximise_function` -- GPBandit, the hyper-parameter fitter, ask/tell, the multi-armed choice of
+acquisitions, hallucinations for pending points: all the reference's control plane, untouched -- is run twice under
+the same seed: once unmodified, once re-bound.  There is no GPU here, so the ONE thing substituted below the host
+mirror is DevicePosterior, by a NumPy stand-in that answers with the oracle's arithmetic (the CUDA path's parity
+with that arithmetic is what the -m gpu tests establish).  Everything above it is the product's host code: kernel
+descriptors, centring, jitter ladder, lazy L / alpha, incremental add_data, hallucinated extensions, candidate
+generation and RNG consumption, acquisition descriptors, TTEI's reference arm and coin flips.
+
+Pass criterion: the re-bound run queries EXACTLY the points the unmodified reference queries, evaluation by
+evaluation, and returns the same optimum.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+
+SCRIPT = r'''
+import sys, warnings
+warnings.simplefilter('ignore')
+sys.path.insert(0, %(ref)r); sys.path.insert(0, %(root)r)
+exec(open(%(shim)r + '/sitecustomize.py').read())     # NumPy-2 aliases the reference needs (np.math, ...)
+import numpy as np
+from dragonfly import maximise_function
+from dragonfly.utils.option_handler import load_options
+from dragonfly.opt.gp_bandit import get_all_euc_gp_bandit_args
+import dragonfly.gp.gp_core as ref_core
+import dragonfly.opt.gpb_acquisitions as ref_acq
+from oracle import gp_oracle as O
+
+
+def objective(x):
+  x = np.asarray(x)
+  return float(-((x[0] - 0.3) ** 2 + (x[1] - 0.7) ** 2) + 0.1 * np.sin(8 * x[0]) + 0.05 * x[2])
+
+
+def run(num_workers=1):
+  opts = load_options(get_all_euc_gp_bandit_args())
+  opts.acq_opt_method = 'rand'
+  opts.acq = 'ucb-ei-ttei-pi'
+  opts.gpb_hp_tune_criterion = 'ml'
+  opts.gpb_ml_hp_tune_opt = 'rand'
+  opts.build_new_model_every = 4
+  np.random.seed(3)
+  val, pt, hist = maximise_function(objective, [[0, 1], [0, 1], [0, 2]], 16, options=opts)
+  return val, np.asarray(pt), np.array(hist.query_points), np.array(hist.query_vals)
+
+ref_val, ref_pt, ref_q, ref_v = run()
+
+# ---- re-bind (INTEGRATION.md 2a, 2b) --------------------------------------------------------------------------
+from dragonfly_b200 import gp_core as b200_core, gpb_acquisitions as b200_acq, device as b200_device, _lib
+for name in ['build_posterior', 'eval', 'eval_with_hallucinated_observations', 'add_data_multiple',
+             'compute_log_marginal_likelihood', 'draw_samples', '_posterior_token', '_rows_as_train_matrix',
+             '_can_extend_in_place', '_extend_posterior', '_hallucinated', 'incremental_updates', '__copy__',
+             '__deepcopy__',
+             'draw_samples_with_hallucinated_observations', '_train_matrix', '_build_on_device',
+             '_new_device_posterior', '_eval_on', '_eval_covar_on', '_draw_samples_on', '_test_matrix',
+             '_augmented_posterior', '_device_posterior', '_fused_score', '_group_test_descriptor',
+             '_state']:
+  setattr(ref_core.GP, name, getattr(b200_core.GP, name))
+for prop in ['L', 'alpha', 'K_trtr_wo_noise']:
+  setattr(ref_core.GP, prop, getattr(b200_core.GP, prop))
+for ns in ('asy', 'syn', 'seq'):
+  for acq in ('ucb', 'ei', 'pi', 'ttei', 'ts', 'add_ucb'):
+    setattr(getattr(ref_acq, ns), acq, getattr(getattr(b200_acq, ns), acq))
+
+# ---- the stand-in for the device: the oracle's arithmetic behind DevicePosterior's interface -----------------------
+calls = dict(build=0, extend=0, restore=0, score=0, eval=0)
+
+
+class NumpyDevice(object):
+  TS_BLOCK = 4096
+
+  def __init__(self, n_max, device=None, chunk=0):
+    self.n, self.dim, self.saved = 0, 0, None
+
+  def set_kernel(self, kern):            # build_descriptor is patched to pass Dragonfly's own kernel object through
+    self.kern = kern
+
+  def set_train(self, X, yc):
+    self.X, self.yc = np.array(X, dtype=np.float64), np.array(yc, dtype=np.float64)
+    self.n, self.dim = self.X.shape
+
+  def capacity(self):
+    return (self.n + 127) // 128 * 128
+
+  def max_diag(self):
+    return float(np.diag(self.kern(self.X, self.X)).max() + self.noise)
+
+  def _factor(self):
+    K = self.kern(self.X, self.X) + self.noise * np.eye(self.n)
+    try:
+      self.L = np.linalg.cholesky(K)
+    except np.linalg.LinAlgError:
+      return 1, None
+    self.alpha = O.solve_upper_triangular(self.L.T, O.solve_lower_triangular(self.L, self.yc))
+    return 0, -0.5 * self.yc.dot(self.alpha) - np.log(np.diag(self.L)).sum() - 0.5 * self.n * np.log(2 * np.pi)
+
+  def build(self, noise_var, jitter=0.0, flags=0):
+    calls['build'] += 1
+    self.noise = noise_var + jitter
+    return self._factor()
+
+  def extend(self, X_new, yc_new, flags=0, save=False):
+    calls['extend'] += 1
+    if save:
+      self.saved = (self.X, self.yc, self.L, self.alpha, self.n)
+    self.X = np.concatenate((self.X, np.asarray(X_new, dtype=np.float64)), axis=0)
+    self.yc = np.concatenate((self.yc, np.asarray(yc_new, dtype=np.float64)))
+    self.n = len(self.X)
+    info, lml = self._factor()
+    if save and info == 0:
+      self.alpha = np.concatenate((self.saved[3], np.zeros(len(X_new))))
+    if info != 0 and save:
+      self.X, self.yc, self.L, self.alpha, self.n = self.saved
+    return info, lml
+
+  def restore(self, n_before):
+    calls['restore'] += 1
+    self.X, self.yc, self.L, self.alpha, self.n = self.saved
+    self.saved = None
+
+  def set_alpha(self, alpha):
+    a = np.zeros(self.n); a[:len(alpha)] = alpha
+    self.alpha = a
+
+  def get_state(self, want_L=False, want_alpha=False, want_K=False):
+    import torch
+    t = lambda a: torch.from_numpy(np.array(a))
+    return (t(self.L) if want_L else None, t(self.alpha) if want_alpha else None,
+            t(self.kern(self.X, self.X)) if want_K else None)
+
+  def _mu_sd(self, Xc, mean_const):
+    """ gp_core.py:165-190 as the reference evaluates it: full covariance, then the diagonal. """
+    Xc = np.asarray(Xc, dtype=np.float64)
+    Ks = self.kern(Xc, self.X)
+    mu = mean_const + Ks.dot(self.alpha)
+    V = O.solve_lower_triangular(self.L, Ks.T)
+    covar = self.kern(Xc, Xc) - V.T.dot(V)
+    return mu, np.sqrt(np.diag(covar))
+
+  def eval(self, Xc, mean_const=0.0, want_std=True):
+    calls['eval'] += 1
+    mu, sd = self._mu_sd(Xc, mean_const)
+    return mu, (sd if want_std else None)
+
+  def score_argmax(self, acq, Xc, mean_const=0.0, want_scores=False):
+    calls['score'] += 1
+    mu, sd = self._mu_sd(Xc, mean_const)
+    if acq.kind == _lib.DFB_ACQ_UCB:
+      sc = O.acq_ucb(mu, sd, acq.beta)
+    elif acq.kind == _lib.DFB_ACQ_EI:
+      sc = O.acq_ei(mu, sd, acq.best)
+    elif acq.kind == _lib.DFB_ACQ_PI:
+      sc = O.acq_pi(mu, sd, acq.best)
+    elif acq.kind == _lib.DFB_ACQ_TTEI:
+      sc = O.acq_ttei(mu, sd, acq.ref_mean, acq.ref_std)
+    else:
+      sc = mu
+    i = O.np_argmax_first(sc)
+    return float(sc[i]), i, (sc if want_scores else None)
+
+  def set_test_kernel(self, desc):
+    pass
+
+
+b200_device.DevicePosterior = NumpyDevice
+b200_core.build_descriptor = lambda kern, **kw: kern
+new_val, new_pt, new_q, new_v = run()
+assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0, calls
+assert new_q.shape == ref_q.shape, (new_q.shape, ref_q.shape)
+assert (new_q == ref_q).all(), np.abs(new_q - ref_q).max()
+assert (new_v == ref_v).all() and new_val == ref_val and (new_pt == ref_pt).all()
+print('BO_LOOP_OK', len(ref_q), calls)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present on this box')
+def test_rebound_bo_loop_queries_exactly_what_the_reference_queries():
+  code = SCRIPT % dict(shim=os.path.join(ROOT, 'oracle', 'ref_shim'), ref=REF, root=ROOT)
+  env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1')
+  out = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], capture_output=True, text=True, env=env,
+                       timeout=900)
+  assert 'BO_LOOP_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
