@@ -41,18 +41,29 @@ def objective(x):
   return float(-((x[0] - 0.3) ** 2 + (x[1] - 0.7) ** 2) + 0.1 * np.sin(8 * x[0]) + 0.05 * x[2])
 
 
-def run(num_workers=1):
+CONFIGS = {
+  'rand_ucb_ei_ttei_pi': dict(acq_opt_method='rand', acq='ucb-ei-ttei-pi', capital=16),
+  'rand_ts_ucb': dict(acq_opt_method='rand', acq='ts-ucb', capital=12),
+  'pdoo_ei_ucb': dict(acq_opt_method='pdoo', acq='ei-ucb', capital=11),
+  # three workers: pending evaluations are hallucinated (gp_bandit.py:45, gpb_acquisitions.py:43-64) -- in the
+  # re-bound run through the temporary in-place extension of the posterior
+  'rand_3_workers': dict(acq_opt_method='rand', acq='ucb-ei', capital=14, num_workers=3),
+}
+
+
+def run(cfg):
   opts = load_options(get_all_euc_gp_bandit_args())
-  opts.acq_opt_method = 'rand'
-  opts.acq = 'ucb-ei-ttei-pi'
+  opts.acq_opt_method = cfg['acq_opt_method']
+  opts.acq = cfg['acq']
   opts.gpb_hp_tune_criterion = 'ml'
   opts.gpb_ml_hp_tune_opt = 'rand'
   opts.build_new_model_every = 4
   np.random.seed(3)
-  val, pt, hist = maximise_function(objective, [[0, 1], [0, 1], [0, 2]], 16, options=opts)
+  val, pt, hist = maximise_function(objective, [[0, 1], [0, 1], [0, 2]], cfg['capital'], options=opts,
+                                    num_workers=cfg.get('num_workers', 1))
   return val, np.asarray(pt), np.array(hist.query_points), np.array(hist.query_vals)
 
-ref_val, ref_pt, ref_q, ref_v = run()
+reference_runs = dict((name, run(cfg)) for name, cfg in CONFIGS.items())
 
 # ---- re-bind (INTEGRATION.md 2a, 2b) --------------------------------------------------------------------------
 from dragonfly_b200 import gp_core as b200_core, gpb_acquisitions as b200_acq, device as b200_device, _lib
@@ -148,7 +159,14 @@ class NumpyDevice(object):
 
   def eval(self, Xc, mean_const=0.0, want_std=True):
     calls['eval'] += 1
-    mu, sd = self._mu_sd(Xc, mean_const)
+    Xc = np.asarray(Xc, dtype=np.float64)
+    if len(Xc) <= 16:
+      # like the device's row-streaming path, a point's result must not depend on its batch-mates (NumPy's BLAS
+      # kernels round differently for different shapes): one point at a time
+      parts = [self._mu_sd(Xc[i:i + 1], mean_const) for i in range(len(Xc))]
+      mu, sd = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    else:
+      mu, sd = self._mu_sd(Xc, mean_const)
     return mu, (sd if want_std else None)
 
   def score_argmax(self, acq, Xc, mean_const=0.0, want_scores=False):
@@ -170,15 +188,35 @@ class NumpyDevice(object):
   def set_test_kernel(self, desc):
     pass
 
+  def ts_draws(self, Xc, Ut, mean_const=0.0, jitter=0.0):
+    """ One attempt of draw_gaussian_samples (general_utils.py:224-232) on the posterior of gp_core.py:165-187. """
+    import torch
+    calls['ts'] = calls.get('ts', 0) + 1
+    Xc = np.asarray(Xc, dtype=np.float64)
+    Ks = self.kern(Xc, self.X)
+    mu = mean_const + Ks.dot(self.alpha)
+    V = O.solve_lower_triangular(self.L, Ks.T)
+    covar = self.kern(Xc, Xc) - V.T.dot(V)
+    try:
+      Lp = np.linalg.cholesky(covar + jitter * np.eye(len(Xc)))
+    except np.linalg.LinAlgError:
+      return 1, None, float(np.diag(covar).max())
+    U = np.asarray(Ut, dtype=np.float64).T                      # (m, S)
+    return 0, torch.from_numpy(Lp.dot(U).T + mu), float(np.diag(covar).max())
+
 
 b200_device.DevicePosterior = NumpyDevice
 b200_core.build_descriptor = lambda kern, **kw: kern
-new_val, new_pt, new_q, new_v = run()
-assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0, calls
-assert new_q.shape == ref_q.shape, (new_q.shape, ref_q.shape)
-assert (new_q == ref_q).all(), np.abs(new_q - ref_q).max()
-assert (new_v == ref_v).all() and new_val == ref_val and (new_pt == ref_pt).all()
-print('BO_LOOP_OK', len(ref_q), calls)
+for name, cfg in CONFIGS.items():
+  ref_val, ref_pt, ref_q, ref_v = reference_runs[name]
+  new_val, new_pt, new_q, new_v = run(cfg)
+  assert new_q.shape == ref_q.shape, (name, new_q.shape, ref_q.shape)
+  assert (new_q == ref_q).all(), (name, np.abs(new_q - ref_q).max())
+  assert (new_v == ref_v).all() and new_val == ref_val and (new_pt == ref_pt).all(), name
+  print('same trajectory:', name, len(ref_q), 'queries')
+assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0 and calls.get('ts', 0) > 0, calls
+assert calls['restore'] > 0, calls        # hallucinated (N + q)-point posteriors were extensions, undone afterwards
+print('BO_LOOP_OK', calls)
 '''
 
 
