@@ -48,6 +48,8 @@ CONFIGS = {
   # three workers: pending evaluations are hallucinated (gp_bandit.py:45, gpb_acquisitions.py:43-64) -- in the
   # re-bound run through the temporary in-place extension of the posterior
   'rand_3_workers': dict(acq_opt_method='rand', acq='ucb-ei', capital=14, num_workers=3),
+  # additive GP + Add-UCB (gpb_acquisitions.py:139-189): per-group test kernels against the full model's L, alpha
+  'additive_add_ucb': dict(acq_opt_method='rand', acq='add_ucb-ucb', capital=11),
 }
 
 
@@ -149,12 +151,20 @@ class NumpyDevice(object):
             t(self.kern(self.X, self.X)) if want_K else None)
 
   def _mu_sd(self, Xc, mean_const):
-    """ gp_core.py:165-190 as the reference evaluates it: full covariance, then the diagonal. """
+    """ gp_core.py:165-190 as the reference evaluates it: full covariance, then the diagonal.  With a test kernel
+        set (Add-UCB, gpb_acquisitions.py:160-176): K_*j = scale k_j(X*_j, X[:, g_j]) against the full L, alpha. """
     Xc = np.asarray(Xc, dtype=np.float64)
-    Ks = self.kern(Xc, self.X)
+    test = getattr(self, 'test', None)
+    if test is None:
+      Ks, Kcc = self.kern(Xc, self.X), self.kern(Xc, Xc)
+    else:
+      single, kw = test
+      calls['group_score'] = calls.get('group_score', 0) + 1
+      scale, k_j = single.hyperparams['scale'], single.kernel_list[0]
+      Ks, Kcc = scale * k_j(Xc, self.X[:, kw['train_coords']]), scale * k_j(Xc, Xc)
     mu = mean_const + Ks.dot(self.alpha)
     V = O.solve_lower_triangular(self.L, Ks.T)
-    covar = self.kern(Xc, Xc) - V.T.dot(V)
+    covar = Kcc - V.T.dot(V)
     return mu, np.sqrt(np.diag(covar))
 
   def eval(self, Xc, mean_const=0.0, want_std=True):
@@ -186,7 +196,7 @@ class NumpyDevice(object):
     return float(sc[i]), i, (sc if want_scores else None)
 
   def set_test_kernel(self, desc):
-    pass
+    self.test = desc
 
   def ts_draws(self, Xc, Ut, mean_const=0.0, jitter=0.0):
     """ One attempt of draw_gaussian_samples (general_utils.py:224-232) on the posterior of gp_core.py:165-187. """
@@ -206,7 +216,7 @@ class NumpyDevice(object):
 
 
 b200_device.DevicePosterior = NumpyDevice
-b200_core.build_descriptor = lambda kern, **kw: kern
+b200_core.build_descriptor = lambda kern, **kw: (kern, kw) if kw.get('train_coords') is not None else kern
 for name, cfg in CONFIGS.items():
   ref_val, ref_pt, ref_q, ref_v = reference_runs[name]
   new_val, new_pt, new_q, new_v = run(cfg)
@@ -215,6 +225,7 @@ for name, cfg in CONFIGS.items():
   assert (new_v == ref_v).all() and new_val == ref_val and (new_pt == ref_pt).all(), name
   print('same trajectory:', name, len(ref_q), 'queries')
 assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0 and calls.get('ts', 0) > 0, calls
+assert calls.get('group_score', 0) > 0, calls     # Add-UCB's per-group test kernels were scored
 assert calls['restore'] > 0, calls        # hallucinated (N + q)-point posteriors were extensions, undone afterwards
 print('BO_LOOP_OK', calls)
 '''
