@@ -28,7 +28,7 @@ warnings.simplefilter('ignore')
 sys.path.insert(0, %(ref)r); sys.path.insert(0, %(root)r)
 exec(open(%(shim)r + '/sitecustomize.py').read())     # NumPy-2 aliases the reference needs (np.math, ...)
 import numpy as np
-from dragonfly import maximise_function
+from dragonfly import maximise_function, maximise_multifidelity_function
 from dragonfly.utils.option_handler import load_options
 from dragonfly.opt.gp_bandit import get_all_euc_gp_bandit_args
 import dragonfly.gp.gp_core as ref_core
@@ -50,10 +50,35 @@ CONFIGS = {
   'rand_3_workers': dict(acq_opt_method='rand', acq='ucb-ei', capital=14, num_workers=3),
   # additive GP + Add-UCB (gpb_acquisitions.py:139-189): per-group test kernels against the full model's L, alpha
   'additive_add_ucb': dict(acq_opt_method='rand', acq='add_ucb-ucb', capital=11),
+  # multi-fidelity: EuclideanMFGP (product kernel on [z || x] rows) + BOCA (gpb_acquisitions.py:399-439)
+  'mf_boca': dict(acq='ucb-ei', capital=9, mf=True),
 }
 
 
+def mf_objective(z, x):
+  z, x = np.asarray(z), np.asarray(x)
+  return objective(x) - 0.3 * (1.0 - z[0]) ** 2 * (1 + np.sin(5 * x[1]))
+
+
+def run_mf(cfg):
+  from dragonfly.opt.gp_bandit import get_all_mf_euc_gp_bandit_args
+  opts = load_options(get_all_mf_euc_gp_bandit_args())
+  opts.acq_opt_method = 'rand'
+  opts.acq = cfg['acq']
+  opts.gpb_hp_tune_criterion = 'ml'
+  opts.gpb_ml_hp_tune_opt = 'rand'
+  opts.build_new_model_every = 4
+  np.random.seed(3)
+  val, pt, hist = maximise_multifidelity_function(
+      mf_objective, [[0, 1]], [[0, 1], [0, 1], [0, 2]], [1.0], lambda z: 0.2 + 0.8 * np.asarray(z)[0],
+      cfg['capital'], options=opts)
+  return val, np.asarray(pt), np.array([np.concatenate((np.ravel(f), np.ravel(p))) for f, p in
+                                        zip(hist.query_fidels, hist.query_points)]), np.array(hist.query_vals)
+
+
 def run(cfg):
+  if cfg.get('mf'):
+    return run_mf(cfg)
   opts = load_options(get_all_euc_gp_bandit_args())
   opts.acq_opt_method = cfg['acq_opt_method']
   opts.acq = cfg['acq']
@@ -83,6 +108,11 @@ for prop in ['L', 'alpha', 'K_trtr_wo_noise']:
 for ns in ('asy', 'syn', 'seq'):
   for acq in ('ucb', 'ei', 'pi', 'ttei', 'ts', 'add_ucb'):
     setattr(getattr(ref_acq, ns), acq, getattr(getattr(b200_acq, ns), acq))
+# multi-fidelity (INTEGRATION.md 2c): BOCA and the [z || x] packing it needs on the reference's MF class
+import dragonfly.gp.euclidean_gp as ref_egp
+from dragonfly_b200 import mf_gp as b200_mf
+ref_acq.boca = b200_acq.boca
+ref_egp.EuclideanMFGP.get_ZX_matrix = b200_mf.EuclideanMFGP.get_ZX_matrix
 
 # ---- the stand-in for the device: the oracle's arithmetic behind DevicePosterior's interface -----------------------
 calls = dict(build=0, extend=0, restore=0, score=0, eval=0)
