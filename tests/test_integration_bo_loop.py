@@ -2,7 +2,7 @@
 The drop-in inside the reference's OWN Bayesian-optimisation loop (authoring container only: needs /root/reference).
 
 INTEGRATION.md section 2 is applied to the reference's classes (GP numerics re-bound, acquisition tables replaced)
-and `dragonfly.maximise_function` -- GPBandit, the hyper-parameter fitter, ask/tell, the multi-armed choice of
+and `dragonfly.maximise_function` (plus `maximise_multifidelity_function` and `multiobjective_maximise_functions`) -- GPBandit, the hyper-parameter fitter, ask/tell, the multi-armed choice of
 acquisitions, hallucinations for pending points: all the reference's control plane, untouched -- is run twice under
 the same seed: once unmodified, once re-bound.  There is no GPU here, so the ONE thing substituted below the host
 mirror is DevicePosterior, by a NumPy stand-in that answers with the oracle's arithmetic (the CUDA path's parity
@@ -52,6 +52,8 @@ CONFIGS = {
   'additive_add_ucb': dict(acq_opt_method='rand', acq='add_ucb-ucb', capital=11),
   # multi-fidelity: EuclideanMFGP (product kernel on [z || x] rows) + BOCA (gpb_acquisitions.py:399-439)
   'mf_boca': dict(acq='ucb-ei', capital=9, mf=True),
+  # two objectives, MOORS scalarisations (multiobjective_gpb_acquisitions.py:19-107)
+  'moo_ucb_ts': dict(acq='ucb-ts', capital=11, moo=True),
 }
 
 
@@ -76,9 +78,28 @@ def run_mf(cfg):
                                         zip(hist.query_fidels, hist.query_points)]), np.array(hist.query_vals)
 
 
+def run_moo(cfg):
+  from dragonfly import multiobjective_maximise_functions
+  from dragonfly.opt.multiobjective_gp_bandit import get_all_euc_moo_gp_bandit_args
+  opts = load_options(get_all_euc_moo_gp_bandit_args())
+  opts.acq_opt_method = 'rand'
+  opts.acq = cfg['acq']
+  opts.gpb_hp_tune_criterion = 'ml'
+  opts.gpb_ml_hp_tune_opt = 'rand'
+  opts.build_new_model_every = 4
+  np.random.seed(3)
+  funcs = [objective, lambda x: float(-np.sum((np.asarray(x) - 0.6) ** 2))]
+  pareto_vals, pareto_pts, hist = multiobjective_maximise_functions(funcs, [[0, 1], [0, 1], [0, 2]],
+                                                                    cfg['capital'], options=opts)
+  return (np.array(pareto_vals).sum(), np.array(pareto_pts).ravel(), np.array(hist.query_points),
+          np.array(hist.query_vals))
+
+
 def run(cfg):
   if cfg.get('mf'):
     return run_mf(cfg)
+  if cfg.get('moo'):
+    return run_moo(cfg)
   opts = load_options(get_all_euc_gp_bandit_args())
   opts.acq_opt_method = cfg['acq_opt_method']
   opts.acq = cfg['acq']
@@ -112,6 +133,11 @@ for ns in ('asy', 'syn', 'seq'):
 import dragonfly.gp.euclidean_gp as ref_egp
 from dragonfly_b200 import mf_gp as b200_mf
 ref_acq.boca = b200_acq.boca
+import dragonfly.opt.multiobjective_gpb_acquisitions as ref_moo
+from dragonfly_b200 import multiobjective_gpb_acquisitions as b200_moo
+for ns in ('asy', 'seq'):
+  for acq in ('lin_ucb', 'tch_ucb', 'lin_ts', 'tch_ts'):
+    setattr(getattr(ref_moo, ns), acq, getattr(getattr(b200_moo, ns), acq))
 ref_egp.EuclideanMFGP.get_ZX_matrix = b200_mf.EuclideanMFGP.get_ZX_matrix
 
 # ---- the stand-in for the device: the oracle's arithmetic behind DevicePosterior's interface -----------------------
@@ -121,8 +147,25 @@ calls = dict(build=0, extend=0, restore=0, score=0, eval=0)
 class NumpyDevice(object):
   TS_BLOCK = 4096
 
+  device = 'cpu'
+
   def __init__(self, n_max, device=None, chunk=0):
     self.n, self.dim, self.saved = 0, 0, None
+
+  def moo_score_argmax(self, kind, a_list, b_list, weights, refs=None, beta=0.0, want_scores=False):
+    calls['moo'] = calls.get('moo', 0) + 1
+    a = [np.asarray(v, dtype=np.float64) for v in a_list]
+    b = None if b_list is None else [np.asarray(v, dtype=np.float64) for v in b_list]
+    if kind == _lib.DFB_MOO_LIN_UCB:
+      sc = O.moo_lin_ucb(a, b, weights, beta)
+    elif kind == _lib.DFB_MOO_TCH_UCB:
+      sc = O.moo_tch_ucb(a, b, weights, refs, beta)
+    elif kind == _lib.DFB_MOO_LIN_VAL:
+      sc = O.moo_lin_vals(a, weights)
+    else:
+      sc = O.moo_tch_vals(a, weights, refs)
+    i = O.np_argmax_first(sc)
+    return float(sc[i]), i, sc
 
   def set_kernel(self, kern):            # build_descriptor is patched to pass Dragonfly's own kernel object through
     self.kern = kern
@@ -255,6 +298,7 @@ for name, cfg in CONFIGS.items():
   assert (new_v == ref_v).all() and new_val == ref_val and (new_pt == ref_pt).all(), name
   print('same trajectory:', name, len(ref_q), 'queries')
 assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0 and calls.get('ts', 0) > 0, calls
+assert calls.get('moo', 0) > 0, calls             # the multi-objective scalarisations ran
 assert calls.get('group_score', 0) > 0, calls     # Add-UCB's per-group test kernels were scored
 assert calls['restore'] > 0, calls        # hallucinated (N + q)-point posteriors were extensions, undone afterwards
 print('BO_LOOP_OK', calls)
