@@ -308,7 +308,9 @@ print('BO_LOOP_OK', calls)
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present on this box')
 def test_rebound_bo_loop_queries_exactly_what_the_reference_queries():
   code = SCRIPT % dict(shim=os.path.join(ROOT, 'oracle', 'ref_shim'), ref=REF, root=ROOT)
-  env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1')
+  # single-threaded BLAS: both runs must see bit-identical NumPy reductions (and tiny matrices gain nothing from threads)
+  env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1',
+             MKL_NUM_THREADS='1')
   out = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], capture_output=True, text=True, env=env,
-                       timeout=900)
+                       timeout=1500)
   assert 'BO_LOOP_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
