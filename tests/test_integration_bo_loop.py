@@ -44,6 +44,9 @@ def objective(x):
 CONFIGS = {
   'rand_ucb_ei_ttei_pi': dict(acq_opt_method='rand', acq='ucb-ei-ttei-pi', capital=16),
   'rand_ts_ucb': dict(acq_opt_method='rand', acq='ts-ucb', capital=12),
+  # the reference's DEFAULT hyper-parameter tuning ('ml-post_sampling': marginal likelihood + slice sampling of
+  # the posterior over hps, gp_bandit.py) and default acquisition portfolio
+  'default_hp_tuning': dict(acq_opt_method='rand', acq='default', capital=10, default_hp_tune=True),
   'pdoo_ei_ucb': dict(acq_opt_method='pdoo', acq='ei-ucb', capital=11),
   # three workers: pending evaluations are hallucinated (gp_bandit.py:45, gpb_acquisitions.py:43-64) -- in the
   # re-bound run through the temporary in-place extension of the posterior
@@ -103,8 +106,9 @@ def run(cfg):
   opts = load_options(get_all_euc_gp_bandit_args())
   opts.acq_opt_method = cfg['acq_opt_method']
   opts.acq = cfg['acq']
-  opts.gpb_hp_tune_criterion = 'ml'
-  opts.gpb_ml_hp_tune_opt = 'rand'
+  if not cfg.get('default_hp_tune'):
+    opts.gpb_hp_tune_criterion = 'ml'
+    opts.gpb_ml_hp_tune_opt = 'rand'
   opts.build_new_model_every = 4
   np.random.seed(3)
   val, pt, hist = maximise_function(objective, [[0, 1], [0, 1], [0, 2]], cfg['capital'], options=opts,
