@@ -235,7 +235,7 @@ def kstar_build_line(prof, n_train, peaks):
 def run_ours(args):
   import torch
   import torch.distributed as dist
-  from dragonfly_b200 import synth_data, kernel, gp_core, device, _lib
+  from dragonfly_b200 import synth_data, kernel, gp_core, device
   from dragonfly_b200 import dist as dfb_dist
   rank, world, local = dist_env()
   assert torch.cuda.is_available(), 'bench.py needs a CUDA device: there is no CPU fallback'

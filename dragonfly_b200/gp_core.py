@@ -428,7 +428,6 @@ class GP(object):
         L = stable_cholesky(covar) with the same jitter ladder, U = np.random.normal(size=(M, S))
         drawn ONCE from the global RNG exactly like the reference, samples = (L U)^T + mu.
         Blocks are sampled independently of each other: exact for M <= TS_BLOCK. """
-    from warnings import warn as _warn
     Xm = self._test_matrix(X_test)
     if self._mean_const is None:
       raise NotImplementedError('Thompson sampling on device needs a constant mean function.')
