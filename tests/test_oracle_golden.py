@@ -328,3 +328,22 @@ def test_philox_known_answers():
   assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.005
   # layout invariance: columns [100, 300) of a wide fill == a fill that starts at column 100
   assert (P.fill(3, 0, 4, 300)[:, 100:] == P.fill(3, 100, 4, 200)).all()
+
+
+def test_stable_cholesky_and_gaussian_draws_like_the_reference_tests():
+  """ dragonfly/utils/unittest_general_utils.py:65-94 restated on the oracle: ||L L^T - M|| < 1e-5 on a random SPD
+      matrix; sample mean / covariance of 10^4 draws within the reference's 4-sigma tolerances (seeded here). """
+  rs = np.random.RandomState(0)
+  M = rs.normal(size=(5, 5)); M = M.dot(M.T)
+  L, power = O.stable_cholesky(M)
+  assert power is None and np.linalg.norm(L.dot(L.T) - M) < 1e-5
+  num_samples, num_pts = 10000, 3
+  mu = np.arange(num_pts, dtype=np.float64)
+  K = rs.normal(size=(num_pts, num_pts)); K = K.dot(K.T)
+  samples = O.draw_gaussian_samples_with_normals(mu, K, rs.normal(size=(num_pts, num_samples)))
+  assert samples.shape == (num_samples, num_pts)
+  sample_mean = samples.mean(axis=0)
+  centred = samples - sample_mean
+  sample_covar = centred.T.dot(centred) / num_samples
+  assert np.linalg.norm(mu - sample_mean) < 4 * np.linalg.norm(mu) / np.sqrt(num_samples)
+  assert np.linalg.norm(K - sample_covar) < 4 * np.linalg.norm(K) / np.sqrt(num_samples)
