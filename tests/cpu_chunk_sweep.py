@@ -1,6 +1,6 @@
 """CPU baseline chunk-size sweep: the faithful chunked gp.eval(chunk, 'std') + EI + arg-max driver of
 oracle/gp_oracle.py at N = 5000 for chunk in {500, 2000, 8000}, to show that bench.py's chunk of 2000 is not an
-adversarial choice for the reference.  Runs on the host only.  Usage: python tools/cpu_chunk_sweep.py [n_cand]"""
+adversarial choice for the reference.  Runs on the host only.  Usage: python tests/cpu_chunk_sweep.py [n_cand]"""
 import json
 import os
 import sys
@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dragonfly_b200 import synth_data  # noqa: E402
-from oracle import gp_oracle as O      # noqa: E402  (tools/ is test infrastructure, like bench.py's cpu_baseline leg)
+from oracle import gp_oracle as O      # noqa: E402  (lives under tests/: only tests/, smoke() and bench.py's CPU leg may import the oracle)
 
 n_cand = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
 w = synth_data.make_workload('headline_hartmann6_matern_ei', n_train=5000, n_cand=n_cand)
