@@ -263,7 +263,9 @@ def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampli
         cts.append(map_to_bounds(np.random.random((len(bounds),)), bounds))
       vals = lmls_of(np.array(cts), [d[0] for d in dscr] if has_nu else None, groupings)
       probs = np.exp(vals)
-      return 'sample_hps_with_probs', cts, dscr, groupings, probs / probs.sum()
+      from argparse import Namespace
+      other = [Namespace(add_gp_groupings=grp) for grp in groupings]      # as the reference returns them (:762)
+      return 'sample_hps_with_probs', cts, dscr, other, probs / probs.sum()
     cts = map_to_bounds(np.random.random((n_evals, len(bounds))), bounds)
     dscr = [[np.random.choice(categ) for categ in dscr_hp_vals] for _ in range(n_evals)]
     vals = lmls_of(cts, [d[0] for d in dscr] if dscr_hp_vals else None)

@@ -701,7 +701,8 @@ def test_fit_gp_additive_model_matches_the_reference_fitter(method, monkeypatch)
     np.testing.assert_allclose(mu, g['rand_mu'], atol=1e-10)
     np.testing.assert_allclose(sd, g['rand_sd'], atol=1e-9)
   else:
-    tag, cts, dscr, groupings, probs = res
+    tag, cts, dscr, other, probs = res
+    groupings = [o.add_gp_groupings for o in other]
     assert tag == 'sample_hps_with_probs'
     assert (np.array(cts) == g[method + '_cts']).all()
     assert (np.array(dscr, dtype=np.float64) == g[method + '_dscr']).all()
