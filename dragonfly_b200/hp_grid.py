@@ -201,7 +201,7 @@ def default_max_evals(method, num_hps):
 
 
 def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampling', max_evals=None,
-           device=None, gp_factory=None):
+           device=None, gp_factory=None, build_gp=None):
   """ GPFitter.fit_gp for hp_tune_criterion == 'ml' (gp_core.py:783-808) with the marginal likelihood of every
       hyper-parameter vector evaluated on the device, in batches instead of one _tuning_objective call at a time
       (gp_core.py:551-563):
@@ -240,6 +240,8 @@ def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampli
     return vals
 
   def build(cts, dscr, groupings=None):
+    if build_gp is not None:                         # e.g. the reference fitter's own build_gp (fit_gp_on_fitter)
+      return build_gp(cts, dscr, groupings)
     mean_const, noise_var, kern = layout.unpack(cts, Y, dscr[0] if has_nu else None, groupings)
     make = GP if gp_factory is None else gp_factory
     return make(list(X), list(Y), kern, ConstantMean(mean_const), noise_var)
@@ -308,6 +310,56 @@ def fit_gp(X, Y, layout, cts_hp_bounds, dscr_hp_vals=(), method='rand_exp_sampli
     if opt_val > best_val:
       best_val, best_cts, best_dscr, best_groupings = opt_val, list(opt_pt), list(dscr), opt_groupings
   return 'fitted_gp', build(best_cts, best_dscr, best_groupings), (best_cts, best_dscr)
+
+
+# ---- drop-in for GPFitter.fit_gp on a Dragonfly EuclideanGPFitter --------------------------------
+def layout_from_fitter(fitter):
+  """ The EuclideanHPLayout equivalent to a reference EuclideanGPFitter's options (euclidean_gp.py:205-248,
+      gp_core.py:509-538), or None when the fitter tunes something the device path does not cover. """
+  opt = fitter.options
+  if getattr(opt, 'mean_func', None) is not None:
+    return None
+  kernel_type = getattr(fitter, 'kernel_type', getattr(opt, 'kernel_type', None))
+  if kernel_type not in ('se', 'matern'):
+    return None
+  additive = bool(getattr(opt, 'use_additive_gp', False))
+  return EuclideanHPLayout(
+      fitter.dim, kernel_type, nu=getattr(opt, 'matern_nu', 2.5),
+      use_same_bandwidth=bool(getattr(opt, 'use_same_bandwidth', False)),
+      mean_func_type=opt.mean_func_type, mean_func_const=getattr(opt, 'mean_func_const', 0.0),
+      noise_var_type=opt.noise_var_type, noise_var_label=getattr(opt, 'noise_var_label', 0.05),
+      noise_var_value=getattr(opt, 'noise_var_value', 0.1), use_additive_gp=additive,
+      add_max_group_size=getattr(fitter, 'add_max_group_size', getattr(opt, 'add_max_group_size', 6)),
+      num_groups_per_group_size=getattr(opt, 'num_groups_per_group_size', -1))
+
+
+def fit_gp_on_fitter(fitter, reference_fit_gp, num_samples=1, hp_tune_criterion=None):
+  """ GPFitter.fit_gp (gp_core.py:783-821) for a reference EuclideanGPFitter instance: hp_tune_criterion 'ml' with
+      ml_hp_tune_opt rand / rand_exp_sampling / pdoo / direct-without-Fortran runs fit_gp above (every batch of
+      _tuning_objective evaluations as one lml_for_hyperparams call; same global-RNG consumption, same selection,
+      the final GP built by the fitter's own build_gp); everything else is handed to `reference_fit_gp`. """
+  from argparse import Namespace
+  from .gpb_acquisitions import _reference_fortran_direct_available
+  crit = fitter.options.hp_tune_criterion if hp_tune_criterion is None else hp_tune_criterion
+  method = getattr(fitter, 'ml_hp_tune_opt_method', None)
+  layout = layout_from_fitter(fitter) if crit == 'ml' else None
+  if (layout is None or method not in ('rand', 'rand_exp_sampling', 'pdoo', 'direct') or
+      (method == 'direct' and _reference_fortran_direct_available())):
+    return reference_fit_gp(fitter, num_samples, hp_tune_criterion)
+  other = lambda grp: None if grp is None else Namespace(add_gp_groupings=grp)
+  return fit_gp(np.array(fitter.X), np.array(fitter.Y), layout, fitter.cts_hp_bounds, fitter.dscr_hp_vals,
+                method=method, max_evals=fitter.hp_tune_max_evals,
+                build_gp=lambda cts, dscr, grp: fitter.build_gp(cts, dscr, other_gp_params=other(grp)))
+
+
+def bind_fit_gp(fitter_class):
+  """ Re-binds fit_gp on a reference GPFitter class (dragonfly.gp.gp_core.GPFitter); returns the original. """
+  original = fitter_class.fit_gp
+
+  def fit_gp_b200(self, num_samples=1, hp_tune_criterion=None):
+    return fit_gp_on_fitter(self, original, num_samples, hp_tune_criterion)
+  fitter_class.fit_gp = fit_gp_b200
+  return original
 
 
 def rand_exp_sampling_probs(lml_vals):

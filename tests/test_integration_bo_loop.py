@@ -148,13 +148,32 @@ ref_egp.EuclideanMFGP.get_ZX_matrix = b200_mf.EuclideanMFGP.get_ZX_matrix
 calls = dict(build=0, extend=0, restore=0, score=0, eval=0)
 
 
+def numpy_kernel(kern):
+  """ Kernel objects of the host mirror (hp_grid's layout builds those) evaluate on the device; the stand-in needs
+      the same kernel as a NumPy object: the reference's own class with the same hyper-parameters. """
+  import dragonfly.gp.kernel as ref_kernel
+  if not type(kern).__module__.startswith('dragonfly_b200'):
+    return kern
+  hp = kern.hyperparams
+  if type(kern).__name__ == 'SEKernel':
+    return ref_kernel.SEKernel(kern.dim, hp['scale'], hp['dim_bandwidths'])
+  if type(kern).__name__ == 'MaternKernel':
+    return ref_kernel.MaternKernel(kern.dim, hp['nu'], hp['scale'], hp['dim_bandwidths'])
+  if type(kern).__name__ == 'AdditiveKernel':
+    return ref_kernel.AdditiveKernel(hp['scale'], [numpy_kernel(k) for k in kern.kernel_list], kern.groupings)
+  raise NotImplementedError(type(kern).__name__)
+
+
 class NumpyDevice(object):
   TS_BLOCK = 4096
 
-  device = 'cpu'
-
   def __init__(self, n_max, device=None, chunk=0):
-    self.n, self.dim, self.saved = 0, 0, None
+    import torch
+    self.n, self.dim, self.saved, self.n_max = 0, 0, None, n_max
+    self.device = torch.device('cpu')
+
+  def bind_current_stream(self):
+    pass
 
   def moo_score_argmax(self, kind, a_list, b_list, weights, refs=None, beta=0.0, want_scores=False):
     calls['moo'] = calls.get('moo', 0) + 1
@@ -172,7 +191,7 @@ class NumpyDevice(object):
     return float(sc[i]), i, sc
 
   def set_kernel(self, kern):            # build_descriptor is patched to pass Dragonfly's own kernel object through
-    self.kern = kern
+    self.kern = numpy_kernel(kern)
 
   def set_train(self, X, yc):
     self.X, self.yc = np.array(X, dtype=np.float64), np.array(yc, dtype=np.float64)
@@ -305,6 +324,47 @@ assert calls['build'] > 0 and calls['score'] > 0 and calls['extend'] > 0 and cal
 assert calls.get('moo', 0) > 0, calls             # the multi-objective scalarisations ran
 assert calls.get('group_score', 0) > 0, calls     # Add-UCB's per-group test kernels were scored
 assert calls['restore'] > 0, calls        # hallucinated (N + q)-point posteriors were extensions, undone afterwards
+
+# ---- phase 2: the hyper-parameter fitter's fit_gp re-bound as well (INTEGRATION.md 2e): every batch of marginal
+# likelihoods is one hp_grid.lml_for_hyperparams call (concurrent lanes; threads here, CUDA streams stubbed) --------
+import contextlib
+import torch
+from dragonfly_b200 import hp_grid
+batches = []
+real_lmls = hp_grid.lml_for_hyperparams
+
+
+def counting_lmls(X, Y, hps, layout, **kw):
+  batches.append(len(hps))
+  return real_lmls(X, Y, hps, layout, **kw)
+
+
+class FakeStream(object):
+  def __init__(self, *a, **k):
+    pass
+
+  def wait_stream(self, other):
+    pass
+torch.cuda.current_stream = lambda *a, **k: FakeStream()
+torch.cuda.Stream = FakeStream
+torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
+torch.cuda.stream = lambda *a, **k: contextlib.nullcontext()
+hp_grid.lml_for_hyperparams = counting_lmls
+hp_grid.build_descriptor = lambda kern, **kw: kern
+hp_grid.bind_fit_gp(ref_core.GPFitter)
+for name in ['rand_ucb_ei_ttei_pi', 'default_hp_tuning', 'additive_add_ucb', 'mf_boca']:
+  ref_val, ref_pt, ref_q, ref_v = reference_runs[name]
+  del batches[:]
+  new_val, new_pt, new_q, new_v = run(CONFIGS[name])
+  assert new_q.shape == ref_q.shape and (new_q == ref_q).all(), (name, 'fit_gp re-bound')
+  assert (new_v == ref_v).all() and new_val == ref_val, name
+  if name != 'mf_boca':                      # (the MF fitter is not a EuclideanGPFitter: handed back to the reference)
+    assert len(batches) > 0, name
+    if name == 'default_hp_tuning':          # ml_hp_tune_opt 'default' -> 'direct' -> PDOO: two children per batch
+      assert max(batches) <= 2 and len(batches) > 100, (name, len(batches))
+    else:                                    # 'rand': all candidates of a discrete setting in one batch
+      assert max(batches) >= 100, (name, batches[:5])
+  print('same trajectory with fit_gp re-bound:', name, 'batches', len(batches), 'largest', max(batches or [0]))
 print('BO_LOOP_OK', calls)
 '''
 
