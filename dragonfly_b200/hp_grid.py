@@ -17,7 +17,7 @@ CPU tests of the sharding logic).
 import numpy as np
 
 from . import _lib
-from .kernel import SEKernel, MaternKernel, AdditiveKernel, build_descriptor
+from .kernel import SEKernel, MaternKernel, AdditiveKernel, CoordinateProductKernel, build_descriptor
 from .gp_core import stable_cholesky_on_device
 
 
@@ -75,10 +75,8 @@ class EuclideanHPLayout(object):
       dscr.append([x + 1 for x in range(self.add_max_group_size)])
     return np.array(out), dscr
 
-  def unpack(self, hp, Y, nu=None, groupings=None):
-    """ gp_core.py:509-538 + euclidean_gp.py:801-861 """
-    hp = list(np.asarray(hp, dtype=np.float64))
-    Y = np.asarray(Y, dtype=np.float64)
+  def _mean_and_noise(self, hp, Y):
+    """ Pops the mean value / log noise from the front of `hp` when they are tuned (gp_core.py:509-538). """
     if self.mean_func_type == 'mean':
       mean_const = np.mean(Y)
     elif self.mean_func_type == 'median':
@@ -97,6 +95,13 @@ class EuclideanHPLayout(object):
       noise_var = self.noise_var_label * (Y.std() ** 2)
     else:
       noise_var = self.noise_var_value
+    return mean_const, noise_var
+
+  def unpack(self, hp, Y, nu=None, groupings=None):
+    """ gp_core.py:509-538 + euclidean_gp.py:801-861 """
+    hp = list(np.asarray(hp, dtype=np.float64))
+    Y = np.asarray(Y, dtype=np.float64)
+    mean_const, noise_var = self._mean_and_noise(hp, Y)
     scale = np.exp(hp.pop(0))
     if self.use_same_bandwidth:
       bws = [np.exp(hp.pop(0))] * self.dim
@@ -115,6 +120,66 @@ class EuclideanHPLayout(object):
       kern = SEKernel(self.dim, scale, bws)
     else:
       kern = MaternKernel(self.dim, nu, scale, bws)
+    return float(mean_const), float(noise_var), kern
+
+
+class EuclideanMFHPLayout(EuclideanHPLayout):
+  """ Hyper-parameter vector of the reference's EuclideanMFGPFitter (euclidean_gp.py:432-483, 680-709): [mean const]?
+      [log noise]? log scale, log fidelity bandwidth(s), log domain bandwidth(s); at most one tuned Matern nu (fidelity
+      or domain) as the discrete hp.  The GP lives on [z || x] rows with the product kernel
+      scale * k_F(z, z') * k_D(x, x') (fidelity and domain kernels with scale 1). """
+
+  def __init__(self, fidel_dim, domain_dim, fidel_kernel_type='se', domain_kernel_type='se', fidel_nu=2.5,
+               domain_nu=2.5, fidel_use_same_bandwidth=False, domain_use_same_bandwidth=False, **kwargs):
+    for kt in (fidel_kernel_type, domain_kernel_type):
+      if kt not in ('se', 'matern'):
+        raise NotImplementedError('kernel_type %s is outside the B200 hot-path scope.' % (kt))
+    super(EuclideanMFHPLayout, self).__init__(fidel_dim + domain_dim, 'se', **kwargs)
+    self.fidel_dim, self.domain_dim = fidel_dim, domain_dim
+    self.fidel_kernel_type, self.domain_kernel_type = fidel_kernel_type, domain_kernel_type
+    self.fidel_nu, self.domain_nu = fidel_nu, domain_nu
+    self.fidel_use_same_bandwidth = fidel_use_same_bandwidth
+    self.domain_use_same_bandwidth = domain_use_same_bandwidth
+    if self.use_additive_gp:
+      raise NotImplementedError('Additive domain kernels in the MF fitter are outside the device path.')
+
+  def tuned_nus(self):
+    return [self.fidel_kernel_type == 'matern' and self.fidel_nu < 0,
+            self.domain_kernel_type == 'matern' and self.domain_nu < 0]
+
+  def num_hps(self):
+    n = 1 + (1 if self.fidel_use_same_bandwidth else self.fidel_dim)
+    n += 1 if self.domain_use_same_bandwidth else self.domain_dim
+    n += 1 if self.mean_func_type == 'tune' else 0
+    n += 1 if self.noise_var_type == 'tune' else 0
+    return n
+
+  def bounds(self, X, Y, tune_nu=None):
+    raise NotImplementedError('Use the bounds of the reference EuclideanMFGPFitter (fitter.cts_hp_bounds).')
+
+  def unpack(self, hp, Y, nu=None, groupings=None):
+    """ gp_core.py:509-538 + euclidean_gp.py:680-709 """
+    hp = list(np.asarray(hp, dtype=np.float64))
+    Y = np.asarray(Y, dtype=np.float64)
+    mean_const, noise_var = self._mean_and_noise(hp, Y)
+    scale = np.exp(hp.pop(0))
+
+    def bandwidths(n, same):
+      return [np.exp(hp.pop(0))] * n if same else [np.exp(hp.pop(0)) for _ in range(n)]
+    f_bws = bandwidths(self.fidel_dim, self.fidel_use_same_bandwidth)
+    d_bws = bandwidths(self.domain_dim, self.domain_use_same_bandwidth)
+    assert len(hp) == 0
+    f_tuned, d_tuned = self.tuned_nus()
+    assert not (f_tuned and d_tuned), 'at most one tuned Matern nu on the device path'
+    f_nu = nu if f_tuned else self.fidel_nu
+    d_nu = nu if d_tuned else self.domain_nu
+    k_f = SEKernel(self.fidel_dim, 1.0, f_bws) if self.fidel_kernel_type == 'se' else \
+        MaternKernel(self.fidel_dim, f_nu, 1.0, f_bws)
+    k_d = SEKernel(self.domain_dim, 1.0, d_bws) if self.domain_kernel_type == 'se' else \
+        MaternKernel(self.domain_dim, d_nu, 1.0, d_bws)
+    fidel_coords = list(range(self.fidel_dim))
+    domain_coords = list(range(self.fidel_dim, self.fidel_dim + self.domain_dim))
+    kern = CoordinateProductKernel(self.dim, scale, [k_f, k_d], [fidel_coords, domain_coords])
     return float(mean_const), float(noise_var), kern
 
 
@@ -319,6 +384,20 @@ def layout_from_fitter(fitter):
   opt = fitter.options
   if getattr(opt, 'mean_func', None) is not None:
     return None
+  common = dict(mean_func_type=opt.mean_func_type, mean_func_const=getattr(opt, 'mean_func_const', 0.0),
+                noise_var_type=opt.noise_var_type, noise_var_label=getattr(opt, 'noise_var_label', 0.05),
+                noise_var_value=getattr(opt, 'noise_var_value', 0.1))
+  if hasattr(fitter, 'fidel_dim') and hasattr(opt, 'fidel_kernel_type'):
+    # EuclideanMFGPFitter (euclidean_gp.py:418-716)
+    if (opt.fidel_kernel_type not in ('se', 'matern') or opt.domain_kernel_type not in ('se', 'matern') or
+        getattr(opt, 'domain_use_additive_gp', False)):
+      return None
+    layout = EuclideanMFHPLayout(
+        fitter.fidel_dim, fitter.domain_dim, opt.fidel_kernel_type, opt.domain_kernel_type,
+        fidel_nu=getattr(opt, 'fidel_matern_nu', 2.5), domain_nu=getattr(opt, 'domain_matern_nu', 2.5),
+        fidel_use_same_bandwidth=bool(getattr(opt, 'fidel_use_same_bandwidth', False)),
+        domain_use_same_bandwidth=bool(getattr(opt, 'domain_use_same_bandwidth', False)), **common)
+    return None if sum(layout.tuned_nus()) > 1 else layout
   kernel_type = getattr(fitter, 'kernel_type', getattr(opt, 'kernel_type', None))
   if kernel_type not in ('se', 'matern'):
     return None
@@ -347,7 +426,13 @@ def fit_gp_on_fitter(fitter, reference_fit_gp, num_samples=1, hp_tune_criterion=
       (method == 'direct' and _reference_fortran_direct_available())):
     return reference_fit_gp(fitter, num_samples, hp_tune_criterion)
   other = lambda grp: None if grp is None else Namespace(add_gp_groupings=grp)
-  return fit_gp(np.array(fitter.X), np.array(fitter.Y), layout, fitter.cts_hp_bounds, fitter.dscr_hp_vals,
+  if isinstance(layout, EuclideanMFHPLayout):
+    X_mat = np.concatenate((np.asarray(fitter.ZZ, dtype=np.float64).reshape(len(fitter.YY), -1),
+                            np.asarray(fitter.XX, dtype=np.float64).reshape(len(fitter.YY), -1)), axis=1)
+    Y_vec = np.array(fitter.YY)
+  else:
+    X_mat, Y_vec = np.array(fitter.X), np.array(fitter.Y)
+  return fit_gp(X_mat, Y_vec, layout, fitter.cts_hp_bounds, fitter.dscr_hp_vals,
                 method=method, max_evals=fitter.hp_tune_max_evals,
                 build_gp=lambda cts, dscr, grp: fitter.build_gp(cts, dscr, other_gp_params=other(grp)))
 

@@ -721,3 +721,29 @@ def test_se_effective_norm_known_answers():
   assert np.linalg.norm(k2.get_effective_norm(data_2, order=1, is_single=False) - np.array([2, 3.25])) < 1e-5
   k2.change_smoothness(2.0)
   assert (k2.hyperparams['dim_bandwidths'] == np.array([1.0, 2.0, 4.0])).all()
+
+
+def test_mf_hp_layout_unpacks_like_the_reference_mf_fitter():
+  """ euclidean_gp.py:680-709: [mean]? [log noise]? log scale, log fidelity bandwidths, log domain bandwidths; fidelity
+      coordinates first in the [z || x] rows; a tuned Matern nu goes to whichever of the two kernels tunes it. """
+  from dragonfly_b200 import hp_grid
+  lay = hp_grid.EuclideanMFHPLayout(1, 3, 'se', 'matern', domain_nu=-1.0, mean_func_type='tune', noise_var_type='tune')
+  assert lay.num_hps() == 7 and lay.tuned_nus() == [False, True] and lay.dim == 4
+  hp = [0.3, np.log(0.02), np.log(1.7), np.log(0.6), np.log(0.2), np.log(0.3), np.log(0.4)]
+  m, nv, kern = lay.unpack(hp, np.arange(5.0), nu=1.5)
+  assert m == 0.3 and abs(nv - 0.02) < 1e-15 and abs(kern.hyperparams['scale'] - 1.7) < 1e-15
+  kF, kD = kern.kernel_list
+  assert type(kF).__name__ == 'SEKernel' and type(kD).__name__ == 'MaternKernel' and kD.hyperparams['nu'] == 1.5
+  np.testing.assert_allclose(kF.hyperparams['dim_bandwidths'], [0.6])
+  np.testing.assert_allclose(kD.hyperparams['dim_bandwidths'], [0.2, 0.3, 0.4])
+  assert kF.hyperparams['scale'] == 1.0 and kD.hyperparams['scale'] == 1.0
+  assert kern.coordinate_list == [[0], [1, 2, 3]]
+  same = hp_grid.EuclideanMFHPLayout(2, 2, 'matern', 'se', fidel_nu=2.5, fidel_use_same_bandwidth=True,
+                                     mean_func_type='median', noise_var_type='value', noise_var_value=0.07)
+  m, nv, kern = same.unpack([np.log(2.0), np.log(0.5), np.log(0.1), np.log(0.9)], np.array([1.0, 5.0, 2.0]))
+  assert m == 2.0 and nv == 0.07 and same.num_hps() == 4
+  np.testing.assert_allclose(kern.kernel_list[0].hyperparams['dim_bandwidths'], [0.5, 0.5])
+  np.testing.assert_allclose(kern.kernel_list[1].hyperparams['dim_bandwidths'], [0.1, 0.9])
+  assert kern.kernel_list[0].hyperparams['nu'] == 2.5
+  with pytest.raises(NotImplementedError):
+    hp_grid.EuclideanMFHPLayout(1, 2, 'expdecay', 'se')

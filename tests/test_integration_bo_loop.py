@@ -161,6 +161,9 @@ def numpy_kernel(kern):
     return ref_kernel.MaternKernel(kern.dim, hp['nu'], hp['scale'], hp['dim_bandwidths'])
   if type(kern).__name__ == 'AdditiveKernel':
     return ref_kernel.AdditiveKernel(hp['scale'], [numpy_kernel(k) for k in kern.kernel_list], kern.groupings)
+  if type(kern).__name__ == 'CoordinateProductKernel':
+    return ref_kernel.CoordinateProductKernel(kern.dim, hp['scale'], [numpy_kernel(k) for k in kern.kernel_list],
+                                              kern.coordinate_list)
   raise NotImplementedError(type(kern).__name__)
 
 
@@ -358,8 +361,8 @@ for name in ['rand_ucb_ei_ttei_pi', 'default_hp_tuning', 'additive_add_ucb', 'mf
   new_val, new_pt, new_q, new_v = run(CONFIGS[name])
   assert new_q.shape == ref_q.shape and (new_q == ref_q).all(), (name, 'fit_gp re-bound')
   assert (new_v == ref_v).all() and new_val == ref_val, name
-  if name != 'mf_boca':                      # (the MF fitter is not a EuclideanGPFitter: handed back to the reference)
-    assert len(batches) > 0, name
+  assert len(batches) > 0, name              # (the MF fitter goes through EuclideanMFHPLayout)
+  if True:
     if name == 'default_hp_tuning':          # ml_hp_tune_opt 'default' -> 'direct' -> PDOO: two children per batch
       assert max(batches) <= 2 and len(batches) > 100, (name, len(batches))
     else:                                    # 'rand': all candidates of a discrete setting in one batch
