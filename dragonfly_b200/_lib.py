@@ -22,6 +22,7 @@ DFB_BUILD_FULL, DFB_BUILD_LML_ONLY, DFB_BUILD_NO_ALPHA = 0, 1, 2
 DFB_EXTEND_SAVE = 16
 DFB_MOO_MAX_OBJ = 8
 DFB_RNG_NORMAL, DFB_RNG_UNIFORM = 0, 1
+DFB_PEAK_TCGEN05_I8, DFB_PEAK_DMMA_F64 = 0, 1
 DFB_MOO_LIN_UCB, DFB_MOO_TCH_UCB, DFB_MOO_LIN_VAL, DFB_MOO_TCH_VAL = 0, 1, 2, 3
 
 
@@ -87,6 +88,8 @@ PROTOTYPES = {
   'dfb_ts_draws': (C.c_int, [_P, _P, _I64, _I32, _D, _P, _I32, _D, _P, _P, C.POINTER(_D)]),
   'dfb_fill_rng': (C.c_int, [_P, C.c_uint64, _I64, _I32, _I64, _I32, _P]),
   'dfb_ts_argmax': (C.c_int, [_P, _P, _I64, _I32, _I64, _I64, _I32, _P, _P]),
+  'dfb_fill_candidates': (C.c_int, [_P, C.c_uint64, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D), _P]),
+  'dfb_measure_peak': (C.c_int, [C.c_int, C.c_int, C.POINTER(_D)]),
   'dfb_launch_count': (_I64, [_P]),
   'dfb_set_option': (C.c_int, [_P, C.c_char_p, _I64]),
   'dfb_query': (C.c_int, [_P, C.c_char_p, C.POINTER(_D)]),

@@ -17,8 +17,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int SHORTLIST_CAP = 4096;
-
 static int64_t default_chunk(int64_t npad) {
   int64_t c = ((int64_t)32 << 20) / npad;   // ~256 MB of K_* rows per chunk
   c = c / TILE * TILE;
@@ -66,6 +64,10 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   int64_t* list_idx = c.take<int64_t>((size_t)SHORTLIST_CAP);
   double* list_X = c.take<double>((size_t)SHORTLIST_CAP * DFB_MAX_SLOTS);
   int* list_count = c.take<int>(4);
+  double* list_s8 = c.take<double>((size_t)SHORTLIST_CAP);
+  double* list_err = c.take<double>((size_t)SHORTLIST_CAP);
+  double* blk_lb = c.take<double>((size_t)chunk / 128 + 16);
+  double* best_lb = c.take<double>(1);
   double* partial = c.take<double>((size_t)nb * chunk);
   double* mu = c.take<double>((size_t)chunk);
   double* sd = c.take<double>((size_t)chunk);
@@ -88,7 +90,7 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
     h->ext_save = ext_save;
     h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
     h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
-    h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->list_idx = list_idx; h->list_X = list_X; h->list_count = list_count; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
+    h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->list_idx = list_idx; h->list_X = list_X; h->list_count = list_count; h->list_s8 = list_s8; h->list_err = list_err; h->blk_lb = blk_lb; h->best_lb = best_lb; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
     h->blk_score = blk_score; h->blk_index = blk_index; h->best_score = best_score;
     h->best_index = best_index; h->red = red; h->info = info;
     h->d_desc_tr = d0; h->d_desc_te = d1; h->d_desc_tmp = d2;
@@ -302,13 +304,30 @@ static int prof_end(dfb_handle* h, int cls, double units) {
   return 0;
 }
 
-// A-priori estimate of the int8-slice path's absolute sigma^2 error for the active kernel.  The error of
-// one entry of v = L^-1 k_* is a sum over k of digit-truncation and dropped-product terms of size
-// 2^-q * rowscale_i * colscale with effectively random signs (q = 43 for six radix-128 digits, 40 for five
-// radix-256 digits), so it grows like sqrt(n); d(sigma^2) = 2 sum_i v_i dv_i <= 2 sqrt(k(x,x)) max_i |dv_i|
-// in the worst alignment.  Measured maxima (tools/check_i8.py, N = 100 .. 5000, 13056 candidates) sit at
-// 0.55x (radix 128) and 0.87x (radix 256) of rowscale_max * sqrt(n) * colscale * 2^-q * sqrt(k(x,x)); the
-// constant 8 leaves a >= 9x margin over those.
+// A-priori bound on the int8-slice path's ABSOLUTE sigma^2 error for the active kernel.
+//
+// Error model.  One entry of v = L^-1 k_* is a sum over k <= i of digit-truncation and dropped-product terms, each
+// bounded by c 2^-q rowscale_i colscale (q = 43 for six radix-128 digits, 40 for five radix-256 digits; the low
+// digits of an operand are unrelated to its magnitude, so the terms do not shrink with |W_ik K_k|) and, being
+// rounding residues of unrelated numbers, of effectively independent sign: |dv_i| grows like sqrt(n), exactly as
+// the rounding error of the fp64 dot product it replaces (whose worst-case bound n eps is never approached either).
+// d(sigma^2) = 2 sum_i v_i dv_i has standard deviation <= 2 |v| max_i sd(dv_i) <= 2 sqrt(k(x,x)) max_i sd(dv_i)
+// for independent dv_i (|v|^2 <= k(x,x) - sigma^2 <= k(x,x)).  A worst-case (n instead of sqrt(n), aligned signs
+// over i) bound would be ~sqrt(n) n / 8 ~ 4 10^4 times larger at N = 5000 and is as unattainable as LAPACK's own.
+//
+// The constant 8 puts the bound >= 9x above every maximum measured over the validation sweep
+// (tools/sweep_i8_bound.py -> profiles/r02_i8_bound_sweep.json: N 1000..5000, noise 1e-2..1e-8 of the scale, scale
+// 1e-2..1e4, SE / Matern / additive / product kernels, 13056 candidates each; measured max = 0.55x (radix 128) /
+// 0.87x (radix 256) of rowscale_max sqrt(n) colscale 2^-q sqrt(k(x,x))), i.e. ~36 standard deviations of the
+// modelled error.  It is NOT a worst-case bound; three things keep the arg-max exact in spite of that:
+//   (1) the limit below is ABSOLUTE: the int8 pass is used only while the bound is <= 5e-9, half of the
+//       north-star's 1e-8 contract on sigma^2, whatever the kernel scale;
+//   (2) dfb_score_argmax re-scores in fp64 every candidate whose int8 score, widened by the bound, could reach the
+//       fp64 maximum, and returns the fp64 arg-max of those;
+//   (3) after that exact pass the int8 and fp64 scores of the shortlist are compared (selfcheck_kernel): a single
+//       candidate outside its allowance voids the int8 pass and the whole call is repeated in fp64
+//       (query "last_selfcheck_violations" / "last_selfcheck_ratio").
+// score_impl = 0 (env DFB200_SCORE=fp64, option "score_impl") switches the int8 path off altogether.
 static double i8_colscale(const dfb_kernel_desc& desc) {
   int e = 0;
   frexp(desc.kss * (1.0 + 1e-9), &e);
@@ -318,11 +337,11 @@ static double i8_sigma2_bound(const dfb_handle* h, const dfb_kernel_desc& desc) 
   return 8.0 * h->i8_rowscale_max * sqrt((double)h->n) * i8_colscale(desc) *
          ldexp(1.0, h->i8_radix256 ? -40 : -43) * sqrt(desc.kss);
 }
-static const double I8_BOUND_LIMIT = 5e-9;     // half of the 1e-8 sigma^2 contract, times max(1, k(x,x))
+static const double I8_BOUND_LIMIT = 5e-9;     // absolute: half of the 1e-8 sigma^2 contract
 static bool i8_usable(const dfb_handle* h, const dfb_kernel_desc& desc) {
   if (!h->i8_ready || !(desc.kss > 0.0)) return false;
-  const double b = i8_sigma2_bound(h, desc);
-  return b <= I8_BOUND_LIMIT * (desc.kss > 1.0 ? desc.kss : 1.0);
+  if (h->i8_unguarded) return true;                 // diagnostics only (tools/sweep_i8_bound.py)
+  return i8_sigma2_bound(h, desc) <= I8_BOUND_LIMIT;
 }
 
 // Digit planes of W = L^-1 for the tcgen05 path + the tensor maps of both operands.
@@ -339,8 +358,7 @@ static int prepare_i8(dfb_handle* h) {
   if (h->i8_impl == 2 && h->i8_radix_opt != 0 && npad <= 24576) {
     h->i8_radix256 = 1;
     const dfb_kernel_desc& dtr = h->desc_tr;
-    if (h->i8_radix_opt < 0 && dtr.kss > 0.0 &&
-        i8_sigma2_bound(h, dtr) > I8_BOUND_LIMIT * (dtr.kss > 1.0 ? dtr.kss : 1.0))
+    if (h->i8_radix_opt < 0 && dtr.kss > 0.0 && i8_sigma2_bound(h, dtr) > I8_BOUND_LIMIT)
       h->i8_radix256 = 0;
   }
   // pair-interleaved digit planes: 3 planes of rows x (2 * npad) bytes
@@ -469,10 +487,18 @@ struct ChunkMode {
   bool want_std, do_argmax;
   bool use_i8;                 // int8-slice tcgen05 contraction instead of fp64 DMMA
   bool collect;                // gather the shortlist for the exact re-score
-  double margin, sd_min;       // shortlist thresholds
+  I8ErrModel em;               // int8 error model (collect): bound on |d sigma^2|, score sensitivity
+  double pad;                  // extra slack of the shortlist test
   const int64_t* idx_map;      // global index of each row (re-score pass), NULL = c0 + i
   bool allow_small;            // dfb_eval of <= SMALL_EVAL_M points: row-streaming kernel instead of the tile GEMM
+  bool keep_scores;            // leave the scores of a single-chunk pass in h->score (self-check of the shortlist)
 };
+static ChunkMode chunk_mode(bool want_std, bool do_argmax, bool use_i8, const int64_t* idx_map = nullptr) {
+  ChunkMode md;
+  memset(&md, 0, sizeof(md));
+  md.want_std = want_std; md.do_argmax = do_argmax; md.use_i8 = use_i8; md.idx_map = idx_map;
+  return md;
+}
 constexpr int64_t SMALL_EVAL_M = 16;
 
 static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, int64_t m, int32_t dc,
@@ -513,13 +539,14 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : h->mu;
     double* sd_dev = (space == DFB_DEVICE && out.sd) ? out.sd + c0 : h->sd;
     double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0
-                                                         : ((out.score || md.collect) ? h->score : nullptr);
+                                                         : ((out.score || md.collect || md.keep_scores) ? h->score : nullptr);
+    const int* abort_count = md.collect ? h->list_count : nullptr;
     DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
     int fused_digits = 0;
     if (want_std && md.use_i8 && h->i8_fuse)
       DFB_TRY(launch_kstar_i8(h, d_desc, desc, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows, h->n, npad,
                               mean_const, mu_dev, h->kssv, h->Ki8, 2 * h->chunk * npad, 2 * npad,
-                              1.0 / i8_colscale(desc), &fused_digits));
+                              1.0 / i8_colscale(desc), &fused_digits, abort_count));
     if (!fused_digits)
       DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
                            h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
@@ -547,7 +574,7 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
                                   2 * h->chunk * npad, 2 * npad));
         if (h->i8_impl == 2)
           DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmW1c, h->tmK2h, h->tmK3h, h->tmK1c, nb, (int)(m_rows / TILE), (int)npad,
-                                         h->partial, Mc, h->rowscale, colscale));
+                                         h->partial, Mc, h->rowscale, colscale, abort_count));
         else if (h->i8_impl == 1)
           DFB_TRY(launch_score_i8x2_args(h, h->tmW2, h->tmW3, h->tmK2, h->tmK3, nb, (int)(m_rows / TILE), (int)npad,
                                          h->partial, Mc, h->rowscale, colscale));
@@ -567,10 +594,10 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     if (want_std || do_argmax || sc_dev != nullptr) {
       DFB_TRY(prof_begin(h, DFB_PROF_ACQ));
       DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, small ? SMALL_EVAL_M : Mc, small ? small_warps : nb, h->kssv, mc, c0,
-                         want_std ? 1 : 0, want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map));
+                         want_std ? 1 : 0, want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map,
+                         md.collect ? &md.em : nullptr));
       if (md.collect)
-        DFB_TRY(launch_collect_shortlist(h, sc_dev, sd_dev, mc, c0, md.margin, md.sd_min, xc_dev, dc,
-                                         h->list_idx, h->list_X, h->list_count, SHORTLIST_CAP));
+        DFB_TRY(launch_collect_shortlist(h, sc_dev, sd_dev, mc, c0, md.em, md.pad, xc_dev, dc));
       DFB_TRY(prof_end(h, DFB_PROF_ACQ, (double)mc));
     }
     if (space == DFB_HOST) {
@@ -873,7 +900,7 @@ int dfb_eval(dfb_handle* h, const double* Xc, int64_t m, int32_t dc, int32_t spa
   acq.kind = DFB_ACQ_MEAN;
   ChunkOut out = {mu, sd, nullptr};
   const dfb_kernel_desc& desc = h->have_test_kernel ? h->desc_te : h->desc_tr;
-  ChunkMode md = {sd != nullptr, false, false, false, 0.0, 0.0, nullptr};
+  ChunkMode md = chunk_mode(sd != nullptr, false, false);
   md.use_i8 = (sd != nullptr) && (h->score_impl == 1) && i8_usable(h, desc);
   md.allow_small = h->small_eval != 0;
   h->last_used_i8 = md.use_i8 ? 1 : 0;
@@ -897,49 +924,54 @@ int dfb_score_argmax(dfb_handle* h, const dfb_acq_desc* acq, const double* Xc, i
   // only guarantees the arg-max, so the int8 pass is reserved for arg-max-only calls unless forced.
   const bool fast = want_std && h->score_impl != 0 && i8_usable(h, desc) &&
                     (scores == nullptr || h->score_impl == 1);
-  ChunkMode md = {want_std, true, fast, false, 0.0, 0.0, nullptr};
+  ChunkMode md = chunk_mode(want_std, true, fast);
   h->last_used_i8 = fast ? 1 : 0;
   h->last_shortlist = 0;
+  h->last_selfcheck_violations = 0;
+  h->last_selfcheck_ratio = 0.0;
   double bs = 0.0;
   int64_t bi = -1;
   bool need_exact_pass = !fast;
   if (fast) {
-    // Pass 1: int8-slice scoring of everything, collecting the shortlist of candidates that could be
-    // the exact arg-max.  Natural score scale: UCB |mu| + beta sigma ~ (1 + beta) sqrt(kss); EI/TTEI
-    // <= sigma ~ sqrt(kss); PI <= 1.  The shortlist margin is the larger of 1e-6 of that scale and the
-    // a-priori score error of the int8 pass (below).
+    // Pass 1: int8-slice scoring of everything, collecting the shortlist of candidates whose fp64 score could be
+    // the maximum under the error model (kernels.cu: i8_score_err / collect_shortlist_kernel).  The pass is void
+    // -- and its remaining launches return at once -- as soon as the shortlist overflows (masses of exact ties).
     const double sk = sqrt(desc.kss);
-    double scale = sk;
+    double scale = sk;                    // natural score scale, for the slack only
     if (acq->kind == DFB_ACQ_UCB) scale = (1.0 + fabs(acq->beta)) * sk + fabs(mean_const);
     else if (acq->kind == DFB_ACQ_PI) scale = 1.0;
     md.collect = true;
-    md.sd_min = sqrt(1e-3 * desc.kss);
-    // every candidate with sigma >= sd_min has |score_int8 - score_fp64| <= sens * B2 / (2 sd_min), where
-    // sens bounds |d score / d sigma|: UCB |beta|; EI, TTEI <= 1 (phi(z) <= 0.4); PI |z phi(z)| / sigma
-    // <= 0.25 / sd_min.  Both the leader and a challenger can be off by that much, hence the factor 2.
-    double sens = 1.0;
-    if (acq->kind == DFB_ACQ_UCB) sens = fabs(acq->beta);
-    else if (acq->kind == DFB_ACQ_PI) sens = 0.25 / md.sd_min;
-    const double rigorous = 2.0 * sens * i8_sigma2_bound(h, desc) / (2.0 * md.sd_min);
-    md.margin = 1e-6 * scale > rigorous ? 1e-6 * scale : rigorous;
+    md.em.b2 = i8_sigma2_bound(h, desc);
+    md.em.kind = acq->kind;
+    md.em.sens = (acq->kind == DFB_ACQ_UCB) ? fabs(acq->beta) : (acq->kind == DFB_ACQ_PI ? 0.25 : 0.4);
+    md.pad = 1e-9 * scale;
     DFB_CUDA_OK(cudaMemsetAsync(h->list_count, 0, sizeof(int) * 4, h->stream));
     DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, md));
     int count = 0;
     DFB_CUDA_OK(cudaMemcpyAsync(&count, h->list_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
     if (count > SHORTLIST_CAP || count > h->chunk) {
-      h->last_shortlist = -1;          // too many near-ties / suspects: exact pass over everything
+      h->last_shortlist = -1;          // too many candidates within reach of the maximum: exact pass over everything
       need_exact_pass = true;
     } else {
-      // Pass 2: exact fp64 (DMMA) re-score of the shortlist; indices map back to the caller's rows.
+      // Pass 2: exact fp64 (DMMA) re-score of the shortlist; indices map back to the caller's rows.  Then the
+      // self-check: int8 vs fp64 score of every listed candidate against its allowance.
       h->last_shortlist = count;
-      ChunkMode ex = {want_std, true, false, false, 0.0, 0.0, h->list_idx};
+      ChunkMode ex = chunk_mode(want_std, true, false, h->list_idx);
+      ex.keep_scores = true;
       ChunkOut none = {nullptr, nullptr, nullptr};
       DFB_TRY(run_chunks(h, *acq, h->list_X, count, dc, DFB_DEVICE, mean_const, none, ex));
+      DFB_TRY(launch_selfcheck(h, h->score, count));
+      int chk[2] = {0, 0};
+      DFB_CUDA_OK(cudaMemcpyAsync(chk, h->list_count + 1, sizeof(chk), cudaMemcpyDeviceToHost, h->stream));
+      DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+      h->last_selfcheck_violations = chk[0];
+      h->last_selfcheck_ratio = (double)chk[1] * 1e-6;
+      if (chk[0] > 0) need_exact_pass = true;      // the error model failed on a candidate that matters: fp64
     }
   }
   if (need_exact_pass) {
-    ChunkMode ex = {want_std, true, false, false, 0.0, 0.0, nullptr};
+    ChunkMode ex = chunk_mode(want_std, true, false);
     DFB_TRY(run_chunks(h, *acq, Xc, m, dc, space, mean_const, out, ex));
   }
   DFB_CUDA_OK(cudaMemcpyAsync(&bs, h->best_score, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1104,6 +1136,17 @@ int dfb_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int32_t S, int64_t 
   return launch_fill_rng(h, seed, col0, S, m, what, out_dev);
 }
 
+int dfb_fill_candidates(dfb_handle* h, uint64_t seed, int64_t row0, int64_t m, int32_t d, const double* lo_host,
+                        const double* hi_host, double* out_dev) {
+  DFB_TRY(need(h, false, false, false, false, false));
+  if (out_dev == nullptr || lo_host == nullptr || hi_host == nullptr || m < 1 || row0 < 0 || d < 1 || d > DFB_MAX_SLOTS) {
+    set_error("bad fill_candidates arguments (m = %lld, d = %d)", (long long)m, d);
+    return -1;
+  }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  return launch_fill_candidates(h, seed, row0, m, d, lo_host, hi_host, out_dev);
+}
+
 int dfb_ts_argmax(dfb_handle* h, const double* samples_dev, int64_t ld, int32_t S, int64_t m, int64_t idx_base,
                   int32_t reset, double* best_dev, int64_t* index_dev) {
   DFB_TRY(need(h, false, false, false, false, false));
@@ -1121,6 +1164,11 @@ int dfb_query(dfb_handle* h, const char* name, double* out) {
   if (strcmp(name, "i8_sigma2_bound") == 0) { *out = h->i8_ready ? i8_sigma2_bound(h, desc) : -1.0; return 0; }
   if (strcmp(name, "last_used_i8") == 0) { *out = (double)h->last_used_i8; return 0; }
   if (strcmp(name, "last_shortlist") == 0) { *out = (double)h->last_shortlist; return 0; }
+  if (strcmp(name, "last_selfcheck_violations") == 0) { *out = (double)h->last_selfcheck_violations; return 0; }
+  if (strcmp(name, "last_selfcheck_ratio") == 0) { *out = h->last_selfcheck_ratio; return 0; }
+  if (strcmp(name, "chunk") == 0) { *out = (double)h->chunk; return 0; }
+  if (strcmp(name, "i8_bound_limit") == 0) { *out = I8_BOUND_LIMIT; return 0; }
+  if (strcmp(name, "score_impl") == 0) { *out = (double)h->score_impl; return 0; }
   if (strcmp(name, "i8_ready") == 0) { *out = h->i8_ready ? 1.0 : 0.0; return 0; }
   if (strcmp(name, "i8_impl") == 0) { *out = (double)h->i8_impl; return 0; }
   if (strcmp(name, "i8_radix256") == 0) { *out = (double)h->i8_radix256; return 0; }
@@ -1148,6 +1196,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "small_eval") == 0) { h->small_eval = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
+  if (strcmp(name, "i8_unguarded") == 0) { h->i8_unguarded = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {
     if (value < 0 || value > 2) { set_error("i8_impl must be 0 (N=64, one pass), 1 (N=128, two passes) or 2 (CTA pairs)"); return -1; }
     h->i8_impl = (int)value;

@@ -123,10 +123,17 @@ struct dfb_handle {
   double i8_rowscale_max = 0.0;   // max_i 2^E_i of the current posterior
   int64_t* list_idx = nullptr;    // shortlist (cap entries)
   double* list_X = nullptr;       // cap x DFB_MAX_SLOTS
-  int* list_count = nullptr;
+  int* list_count = nullptr;      // [0] entries wanted (> cap = overflow), [1] self-check violations, [2] max ratio x 1e6
+  double* list_s8 = nullptr;      // int8-pass score of each shortlist entry
+  double* list_err = nullptr;     // its error allowance E_i (< 0: none -- suspect / NaN)
+  double* blk_lb = nullptr;       // per-block max of (score - E): certain lower bounds of the fp64 maximum
+  double* best_lb = nullptr;      // running maximum of those
+  int64_t last_selfcheck_violations = 0;
+  double last_selfcheck_ratio = 0.0;   // max |s_int8 - s_fp64| / E_i over the last shortlist
   int64_t last_shortlist = 0;     // diagnostics: size of the last shortlist, -1 = overflow -> exact pass
   int last_used_i8 = 0;
   bool i8_ready = false;
+  int i8_unguarded = 0;       // diagnostics: use the int8 path even when its a-priori bound exceeds the limit (the error sweep)
   int i8_fuse = 1;            // K_* kernel emits the digit planes itself (no fp64 K_* round trip)
   int i8_ts = 0;              // 1 = A digits staged in tensor memory (tcgen05.cp + TS-form MMA)
   int8_t* Wi8 = nullptr;      // [6][npad][npad]

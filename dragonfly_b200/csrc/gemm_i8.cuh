@@ -57,6 +57,8 @@ struct ScoreI8Args {
   const double* rowscale;   // 2^E_i per row of W
   double colscale;          // 2^F
   unsigned long long* timing;   // diagnostics (DFB200_I8_TIMING): per-CTA clocks the MMA thread spent waiting; else NULL
+  const int* abort_count;       // CTA-pair kernel: the launch is a no-op once *abort_count > abort_cap (the arg-max
+  int abort_cap;                // shortlist overflowed, so this int8 pass will be discarded for an fp64 one); may be NULL
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,

@@ -131,6 +131,8 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                   const __grid_constant__ CUtensorMap tmA1c, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmB1c,
                   const ScoreI8Args g) {
+  // uniform over the grid: the counter is only written by earlier kernels of the same stream
+  if (g.abort_count != nullptr && *g.abort_count > g.abort_cap) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);

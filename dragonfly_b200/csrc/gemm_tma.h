@@ -26,7 +26,8 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale);
 int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3, const CUtensorMap& tmA1c,
                            const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, const CUtensorMap& tmB1c, int n_rb, int n_cb, int K,
-                           double* partial, int64_t ld_partial, const double* rowscale, double colscale);
+                           double* partial, int64_t ld_partial, const double* rowscale, double colscale,
+                           const int* abort_count = nullptr);
 int launch_row_exponent(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,
                         double* rowscale, double* rowinv);
 int launch_slice_i8(dfb_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols,

@@ -298,6 +298,8 @@ struct KstarI8Out {
   double inv_colscale;    // 2^-F
   int kb;                 // k-values per interleave block (64 or 32)
   int radix256;           // 1: five radix-256 digits (digits_radix256), 0: six radix-128 digits
+  const int* abort_count; // the launch is a no-op once *abort_count > abort_cap (shortlist overflow); may be NULL
+  int abort_cap;
 };
 
 template <int KIND, int P, int D, bool I8OUT>
@@ -308,6 +310,7 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
                   int64_t m_rows, double* __restrict__ Ks, int64_t ldk, int64_t n_valid, int64_t n_write,
                   double mean_const, double* __restrict__ mu, double* __restrict__ kss_out,
                   const KstarI8Out i8o) {
+  if (I8OUT && i8o.abort_count != nullptr && *i8o.abort_count > i8o.abort_cap) return;
   __shared__ dfb_factor_desc fsh;
   __shared__ int coord_sh[8];
   __shared__ double bw_sh[8];
@@ -736,14 +739,35 @@ __device__ __forceinline__ bool better(double sa, int64_t ia, double sb, int64_t
   return ia < ib;
 }
 
+// Error model of the int8-slice scoring pass (api.cu: i8_sigma2_bound): |sigma^2_int8 - sigma^2_fp64| <= b2 for
+// every candidate.  mu is computed in fp64 by both passes, so a score differs only through sigma:
+//   |sd_64 - sd_i8| <= min(b2 / sd_i8, sqrt(b2))          (|sqrt a - sqrt b| <= |a - b| / (sqrt a + sqrt b) <= sqrt|a - b|)
+//   UCB:  |d score| <= |beta| e;   EI, TTEI: d/d sigma = phi(z) [x sigma / sigma_c] <= 0.4, so <= 0.4 e;
+//   PI:   d/d sigma = -z phi(z) / sigma, |z phi(z)| <= 0.242: <= 0.25 e / (sd_i8 - e), capped at 1.
+// `sens` carries |beta| / 0.4 / 0.25.  Returns < 0 for a candidate whose fp64 variance may be negative (NaN score,
+// which np.argmax treats as the maximum): sd_i8 <= sqrt(b2) or NaN -- such candidates are always re-scored.
+__device__ __forceinline__ double i8_score_err(const I8ErrModel& em, double sd) {
+  const double root = sqrt(em.b2);
+  if (!(sd > root)) return -1.0;
+  const double e = em.b2 / sd;
+  if (em.kind == DFB_ACQ_PI) {
+    const double lo = sd - e;
+    return (lo > 0.0) ? fmin(1.0, em.sens * e / lo) : 1.0;
+  }
+  return em.sens * e;
+}
+
 __global__ void __launch_bounds__(256)
 acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* __restrict__ partial,
            int64_t ld_partial, int nrb, const double* __restrict__ kss, int64_t m, int64_t idx_base,
            int want_std, double* __restrict__ sd_out, double* __restrict__ score_out, double* blk_score,
-           int64_t* blk_index, const int64_t* __restrict__ idx_map) {
+           int64_t* blk_index, const int64_t* __restrict__ idx_map, const I8ErrModel em, double* blk_lb,
+           const int* __restrict__ abort_count, int abort_cap) {
+  if (abort_count != nullptr && *abort_count > abort_cap) return;     // shortlist overflowed: this pass is void
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double score = 0.0;
   int64_t index = -1;
+  double lb = -__longlong_as_double(0x7ff0000000000000ll);     // -inf
   if (i < m) {
     const double mean = mu[i];
     double sd = 0.0;
@@ -776,6 +800,11 @@ acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* 
     }
     if (score_out != nullptr) score_out[i] = score;
     index = (idx_map != nullptr) ? idx_map[i] : idx_base + i;
+    if (blk_lb != nullptr) {
+      // a certain lower bound of this candidate's fp64 score (none for suspects / NaN)
+      const double e = i8_score_err(em, sd);
+      if (e >= 0.0 && !isnan(score)) lb = score - e;
+    }
   }
   if (blk_score == nullptr) return;
   // block arg-max
@@ -783,44 +812,60 @@ acq_kernel(const dfb_acq_desc acq, const double* __restrict__ mu, const double* 
     const double so = __shfl_xor_sync(0xffffffffu, score, o);
     const int64_t io = __shfl_xor_sync(0xffffffffu, index, o);
     if (better(so, io, score, index)) { score = so; index = io; }
+    lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
   }
   __shared__ double ss[8];
   __shared__ int64_t si[8];
+  __shared__ double sl[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { ss[warp] = score; si[warp] = index; }
+  if (lane == 0) { ss[warp] = score; si[warp] = index; sl[warp] = lb; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; w++)
+    for (int w = 1; w < 8; w++) {
       if (better(ss[w], si[w], score, index)) { score = ss[w]; index = si[w]; }
+      lb = fmax(lb, sl[w]);
+    }
     blk_score[blockIdx.x] = score;
     blk_index[blockIdx.x] = index;
+    if (blk_lb != nullptr) blk_lb[blockIdx.x] = lb;
   }
 }
 
 // Folds the per-block winners of one chunk into the running (score, index) of the whole call.
+// blk_lb / best_lb (optional): the running maximum of the candidates' certain lower bounds (int8 pass).
 __global__ void __launch_bounds__(256)
 argmax_merge_kernel(const double* __restrict__ blk_score, const int64_t* __restrict__ blk_index,
-                    int nblk, double* best_score, int64_t* best_index) {
+                    int nblk, double* best_score, int64_t* best_index, const double* __restrict__ blk_lb,
+                    double* best_lb, const int* __restrict__ abort_count, int abort_cap) {
+  if (abort_count != nullptr && *abort_count > abort_cap) return;
   double score = 0.0;
   int64_t index = -1;
-  if (threadIdx.x == 0) { score = *best_score; index = *best_index; }
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+  double lb = -__longlong_as_double(0x7ff0000000000000ll);
+  if (threadIdx.x == 0) { score = *best_score; index = *best_index; if (best_lb != nullptr) lb = *best_lb; }
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
     if (better(blk_score[b], blk_index[b], score, index)) { score = blk_score[b]; index = blk_index[b]; }
+    if (blk_lb != nullptr) lb = fmax(lb, blk_lb[b]);
+  }
   for (int o = 16; o > 0; o >>= 1) {
     const double so = __shfl_xor_sync(0xffffffffu, score, o);
     const int64_t io = __shfl_xor_sync(0xffffffffu, index, o);
     if (better(so, io, score, index)) { score = so; index = io; }
+    lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
   }
   __shared__ double ss[8];
   __shared__ int64_t si[8];
+  __shared__ double sl[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { ss[warp] = score; si[warp] = index; }
+  if (lane == 0) { ss[warp] = score; si[warp] = index; sl[warp] = lb; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; w++)
+    for (int w = 1; w < 8; w++) {
       if (better(ss[w], si[w], score, index)) { score = ss[w]; index = si[w]; }
+      lb = fmax(lb, sl[w]);
+    }
     *best_score = score;
     *best_index = index;
+    if (best_lb != nullptr) *best_lb = lb;
   }
 }
 
@@ -923,6 +968,28 @@ __global__ void fill_rng_kernel(uint64_t seed, int64_t col0, int S, int64_t m, i
   out[idx] = sqrt(-2.0 * log(u1)) * cs;
 }
 
+// Candidate generation on the device: random_sample + map_to_bounds (oper_utils.py:59-67, general_utils.py:25-27) with
+// the same counter-based uniforms as fill_rng_kernel -- coordinate s of candidate row a is
+// lo[s] + u(seed, row0 + a, s) * (hi[s] - lo[s]), u = the DFB_RNG_UNIFORM element (s, row0 + a): it depends on the GLOBAL
+// row index only, so any rank can generate exactly its shard, and the winning row can be regenerated on its own.
+// Output row-major m x d (what dfb_score_argmax takes).
+struct CandBounds {
+  double lo[DFB_MAX_SLOTS];
+  double width[DFB_MAX_SLOTS];     // hi - lo, formed on the host like map_to_bounds does
+};
+__global__ void fill_candidates_kernel(uint64_t seed, int64_t row0, int64_t m, int d, const CandBounds b,
+                                       double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * d) return;
+  const int64_t a = idx / d;
+  const int s = (int)(idx - a * d);
+  const uint64_t col = (uint64_t)(row0 + a);
+  uint32_t r[4];
+  philox4x32_10((uint32_t)col, (uint32_t)(col >> 32), (uint32_t)s, (uint32_t)DFB_RNG_UNIFORM, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  out[idx] = __dadd_rn(__dmul_rn(u53(r[0], r[1]), b.width[s]), b.lo[s]);      // pts * (hi - lo) + lo
+}
+
 // running arg-max per draw: row s of samples (S x ld) over columns [0, m) -> (best[s], index[s]) in np.argmax order
 __global__ void __launch_bounds__(256)
 ts_argmax_kernel(const double* __restrict__ samples, int64_t ld, int64_t m, int64_t idx_base, int reset,
@@ -953,9 +1020,10 @@ ts_argmax_kernel(const double* __restrict__ samples, int64_t ld, int64_t m, int6
   }
 }
 
-__global__ void reset_best_kernel(double* best_score, int64_t* best_index) {
+__global__ void reset_best_kernel(double* best_score, int64_t* best_index, double* best_lb) {
   *best_score = 0.0;
   *best_index = -1;
+  *best_lb = -__longlong_as_double(0x7ff0000000000000ll);
 }
 
 // samples[s][a] += mu[a]   (draw_gaussian_samples: L.dot(U).T + mu, general_utils.py:231)
@@ -978,26 +1046,48 @@ __global__ void set_diag_kernel(double* M, int64_t ld, int64_t from, int64_t to,
   if (i < to) M[i * ld + i] = add ? (M[i * ld + i] + v) : v;
 }
 
-// Shortlist for the exact re-score that follows a fast (int8-slice) scoring pass: every candidate whose
-// fast score is within `margin` of the running best (a superset of those within `margin` of the final
-// best, since the running best only grows), every NaN, and every candidate whose sigma is small enough
-// for the fast path's absolute sigma^2 error to matter.  Rows are gathered so host-staged chunks can be
-// re-scored later.
+// Shortlist for the exact re-score that follows a fast (int8-slice) scoring pass.  With the error model above,
+// candidate i's fp64 score lies in [s_i - E_i, s_i + E_i]; LB = max_j (s_j - E_j) over the candidates seen so far
+// (best_lb: includes this chunk, folded by argmax_merge_kernel) is a certain lower bound of the final fp64 maximum.
+// Kept: every candidate with s_i + E_i >= LB - pad (a superset of what the final LB would keep, since LB only
+// grows) -- the fp64 arg-max and all its exact ties are among them --, every NaN, and every suspect (fp64 variance
+// possibly negative).  Rows are gathered so that host-staged chunks can be re-scored later; the int8 score and its
+// error allowance are kept for the self-check of the error model after the exact pass (selfcheck_kernel).
 __global__ void collect_shortlist_kernel(const double* __restrict__ score, const double* __restrict__ sd,
-                                         int64_t mc, int64_t idx_base, const double* best_score,
-                                         const int64_t* best_index, double margin, double sd_min,
+                                         int64_t mc, int64_t idx_base, const double* best_lb,
+                                         const I8ErrModel em, double pad,
                                          const double* __restrict__ Xc, int dc, int64_t* list_idx,
-                                         double* list_X, int* list_count, int cap) {
+                                         double* list_X, double* list_s8, double* list_err, int* list_count, int cap) {
+  if (*list_count > cap) return;                       // already overflowed: the whole pass is void
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mc) return;
-  const double s = score[i], b = *best_score;
-  const double sg = sd[i];
-  const bool keep = (*best_index < 0) || isnan(s) || isnan(b) || s >= b - margin || !(sg >= sd_min);
+  const double s = score[i];
+  const double e = i8_score_err(em, sd[i]);
+  const bool keep = isnan(s) || e < 0.0 || s + e >= *best_lb - pad;
   if (!keep) return;
   const int pos = atomicAdd(list_count, 1);
   if (pos >= cap) return;
   list_idx[pos] = idx_base + i;
+  list_s8[pos] = s;
+  list_err[pos] = isnan(s) ? -1.0 : e;
   for (int q = 0; q < dc; q++) list_X[(int64_t)pos * dc + q] = Xc[i * dc + q];
+}
+
+// After the exact fp64 re-score of the shortlist: every listed candidate with a defined allowance must satisfy
+// |s_int8 - s_fp64| <= E_i -- a live check of the a-priori error model on exactly the candidates that matter.
+// out[0] = number of violations, out[1] = max over the list of |s_int8 - s_fp64| / E_i scaled by 1e6 (diagnostic).
+__global__ void selfcheck_kernel(const double* __restrict__ s8, const double* __restrict__ err,
+                                 const double* __restrict__ s64, int count, int* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double e = err[i];
+  if (e < 0.0) return;
+  const double d = fabs(s8[i] - s64[i]);
+  if (isnan(s64[i]) || d > e) atomicAdd(out, 1);
+  if (e > 0.0) {
+    const double r = fmin(d / e, 1000.0) * 1e6;
+    atomicMax(out + 1, (int)r);
+  }
 }
 
 __global__ void vec_max_kernel(const double* __restrict__ v, int64_t n, double* out) {
@@ -1303,6 +1393,7 @@ int launch_score_i8(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tm
 int launch_score_i8_args(dfb_handle* h, const CUtensorMap& tmA, const CUtensorMap& tmB, int n_rb, int n_cb,
                          int K, double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
   ScoreI8Args g;
+  memset(&g, 0, sizeof(g));
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = h->i8_cb_group;
@@ -1315,6 +1406,7 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
                            const CUtensorMap& tmB2, const CUtensorMap& tmB3, int n_rb, int n_cb, int K,
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
   ScoreI8Args g;
+  memset(&g, 0, sizeof(g));
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = 0;                                   // unused: the persistent kernel deals tiles itself
@@ -1339,11 +1431,14 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
 static bool g_i8c2_attr = false;
 int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3, const CUtensorMap& tmA1c,
                            const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, const CUtensorMap& tmB1c, int n_rb, int n_cb, int K,
-                           double* partial, int64_t ld_partial, const double* rowscale, double colscale) {
+                           double* partial, int64_t ld_partial, const double* rowscale, double colscale,
+                           const int* abort_count) {
   ScoreI8Args g;
+  memset(&g, 0, sizeof(g));
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
   g.cb_group = 0;
+  g.abort_count = abort_count; g.abort_cap = SHORTLIST_CAP;
   const int n_tiles = ((n_rb + 1) / 2) * n_cb;      // row-block pairs x candidate tiles
   if (n_tiles <= 0) return 0;
   static int n_sm[64] = {0};
@@ -1469,7 +1564,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
                     const double* xsT, const double* nrmT, int64_t npad_tr, const double* alpha,
                     const double* Xc, int64_t m, int dc, int64_t m_rows, int64_t n_valid, int64_t n_write,
                     double mean_const, double* mu, double* kss_out, void* planes, int64_t plane_bytes,
-                    int64_t row_bytes, double inv_colscale, int* emitted_i8) {
+                    int64_t row_bytes, double inv_colscale, int* emitted_i8, const int* abort_count) {
   *emitted_i8 = 0;
   if (m_rows <= 0) return 0;
   if (!(h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
@@ -1481,6 +1576,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
   o.inv_colscale = inv_colscale;
   o.kb = (h->i8_impl >= 1) ? 32 : 64;
   o.radix256 = h->i8_radix256;
+  o.abort_count = abort_count; o.abort_cap = SHORTLIST_CAP;
   const unsigned fblocks = (unsigned)((m_rows + KF_CANDS - 1) / KF_CANDS);
   const int d = desc.factors[0].n_dims;
   bool ok = false;
@@ -1605,18 +1701,26 @@ int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* d
 
 int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
                int64_t ld_partial, int nrb, const double* kss, int64_t m, int64_t idx_base, int want_std,
-               double* sd_out, double* score_out, bool do_argmax, const int64_t* idx_map) {
+               double* sd_out, double* score_out, bool do_argmax, const int64_t* idx_map,
+               const I8ErrModel* em) {
   if (m <= 0) return 0;
   const unsigned blocks = (unsigned)((m + 255) / 256);
+  I8ErrModel none;
+  none.b2 = 0.0; none.sens = 0.0; none.kind = 0;
+  const bool track = do_argmax && em != nullptr && em->b2 > 0.0;
+  const int* abort_count = track ? h->list_count : nullptr;     // int8 pass: void once the shortlist overflowed
   acq_kernel<<<blocks, 256, 0, h->stream>>>(acq, mu, partial, ld_partial, nrb, kss, m, idx_base,
                                             want_std, sd_out, score_out,
                                             do_argmax ? h->blk_score : nullptr,
-                                            do_argmax ? h->blk_index : nullptr, idx_map);
+                                            do_argmax ? h->blk_index : nullptr, idx_map,
+                                            track ? *em : none, track ? h->blk_lb : nullptr, abort_count,
+                                            SHORTLIST_CAP);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   if (do_argmax) {
     argmax_merge_kernel<<<1, 256, 0, h->stream>>>(h->blk_score, h->blk_index, (int)blocks,
-                                                  h->best_score, h->best_index);
+                                                  h->best_score, h->best_index, track ? h->blk_lb : nullptr,
+                                                  track ? h->best_lb : nullptr, abort_count, SHORTLIST_CAP);
     h->launches++;
     DFB_CUDA_OK(cudaGetLastError());
   }
@@ -1640,7 +1744,7 @@ int launch_moo(dfb_handle* h, const dfb_moo_desc& d, const double* const* a, con
     h->launches++;
     DFB_CUDA_OK(cudaGetLastError());
     argmax_merge_kernel<<<1, 256, 0, h->stream>>>(h->blk_score, h->blk_index, (int)blocks, h->best_score,
-                                                  h->best_index);
+                                                  h->best_index, nullptr, nullptr, nullptr, 0);
     h->launches++;
     DFB_CUDA_OK(cudaGetLastError());
   }
@@ -1656,6 +1760,18 @@ int launch_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int S, int64_t m
   return 0;
 }
 
+int launch_fill_candidates(dfb_handle* h, uint64_t seed, int64_t row0, int64_t m, int d, const double* lo,
+                           const double* hi, double* out) {
+  if (m * d <= 0) return 0;
+  CandBounds b;
+  memset(&b, 0, sizeof(b));
+  for (int s = 0; s < d; s++) { b.lo[s] = lo[s]; b.width[s] = hi[s] - lo[s]; }
+  fill_candidates_kernel<<<(unsigned)((m * d + 255) / 256), 256, 0, h->stream>>>(seed, row0, m, d, b, out);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_ts_argmax(dfb_handle* h, const double* samples, int64_t ld, int S, int64_t m, int64_t idx_base, int reset,
                      double* best, int64_t* index) {
   if (S <= 0) return 0;
@@ -1666,7 +1782,7 @@ int launch_ts_argmax(dfb_handle* h, const double* samples, int64_t ld, int S, in
 }
 
 int launch_reset_best(dfb_handle* h) {
-  reset_best_kernel<<<1, 1, 0, h->stream>>>(h->best_score, h->best_index);
+  reset_best_kernel<<<1, 1, 0, h->stream>>>(h->best_score, h->best_index, h->best_lb);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1683,12 +1799,21 @@ int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, in
 }
 
 int launch_collect_shortlist(dfb_handle* h, const double* score, const double* sd, int64_t mc,
-                             int64_t idx_base, double margin, double sd_min, const double* Xc, int dc,
-                             int64_t* list_idx, double* list_X, int* list_count, int cap) {
+                             int64_t idx_base, const I8ErrModel& em, double pad, const double* Xc, int dc) {
   if (mc <= 0) return 0;
   collect_shortlist_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, h->stream>>>(
-      score, sd, mc, idx_base, h->best_score, h->best_index, margin, sd_min, Xc, dc, list_idx, list_X,
-      list_count, cap);
+      score, sd, mc, idx_base, h->best_lb, em, pad, Xc, dc, h->list_idx, h->list_X, h->list_s8, h->list_err,
+      h->list_count, SHORTLIST_CAP);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// compares the int8 scores of the shortlist with the exact ones (s64: the re-score pass's output, same order)
+int launch_selfcheck(dfb_handle* h, const double* s64, int count) {
+  if (count <= 0) return 0;
+  selfcheck_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->list_s8, h->list_err, s64, count,
+                                                                         h->list_count + 1);
   h->launches++;
   DFB_CUDA_OK(cudaGetLastError());
   return 0;

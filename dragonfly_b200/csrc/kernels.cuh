@@ -16,7 +16,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
                     const double* xsT, const double* nrmT, int64_t npad_tr, const double* alpha,
                     const double* Xc, int64_t m, int dc, int64_t m_rows, int64_t n_valid, int64_t n_write,
                     double mean_const, double* mu, double* kss_out, void* planes, int64_t plane_bytes,
-                    int64_t row_bytes, double inv_colscale, int* emitted_i8);
+                    int64_t row_bytes, double inv_colscale, int* emitted_i8, const int* abort_count = nullptr);
 int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double diag_add,
                      const double* yc, int with_bottom);
 int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info);
@@ -29,16 +29,26 @@ int launch_extract_lower(dfb_handle* h, const double* T, int64_t npad, double* L
 int launch_copy_pad(dfb_handle* h, const double* src, int64_t n_src, double* dst, int64_t n_dst);
 int launch_copy_rows(dfb_handle* h, const double* src, int64_t ld_src, double* dst, int64_t ld_dst,
                      int64_t rows, int64_t cols);
+// Error model of the int8-slice scoring pass handed to the acquisition / shortlist kernels (kernels.cu:
+// i8_score_err): |sigma^2_int8 - sigma^2_fp64| <= b2; sens = |beta| (UCB), 0.4 (EI, TTEI), 0.25 (PI).
+struct I8ErrModel {
+  double b2;       // a-priori bound on |d sigma^2|; 0 = no int8 pass (no lower-bound tracking)
+  double sens;
+  int kind;        // DFB_ACQ_*
+};
+constexpr int SHORTLIST_CAP = 4096;
 int launch_acq(dfb_handle* h, const dfb_acq_desc& acq, const double* mu, const double* partial,
                int64_t ld_partial, int nrb, const double* kss, int64_t m, int64_t idx_base,
                int want_std, double* sd_out, double* score_out, bool do_argmax,
-               const int64_t* idx_map = nullptr);
+               const int64_t* idx_map = nullptr, const I8ErrModel* em = nullptr);
 int launch_collect_shortlist(dfb_handle* h, const double* score, const double* sd, int64_t mc,
-                             int64_t idx_base, double margin, double sd_min, const double* Xc, int dc,
-                             int64_t* list_idx, double* list_X, int* list_count, int cap);
+                             int64_t idx_base, const I8ErrModel& em, double pad, const double* Xc, int dc);
+int launch_selfcheck(dfb_handle* h, const double* s64, int count);
 int launch_vec_max(dfb_handle* h, const double* v, int64_t n, double* out);
 int launch_reset_best(dfb_handle* h);
 int launch_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int S, int64_t m, int what, double* out);
+int launch_fill_candidates(dfb_handle* h, uint64_t seed, int64_t row0, int64_t m, int d, const double* lo,
+                           const double* hi, double* out);
 int launch_ts_argmax(dfb_handle* h, const double* samples, int64_t ld, int S, int64_t m, int64_t idx_base, int reset,
                      double* best, int64_t* index);
 int launch_small_sumsq(dfb_handle* h, const double* W, int64_t ldw, const double* Ks, int64_t ldk, int64_t n_rows,

@@ -4,6 +4,7 @@ torch-owned workspace it computes in.  PyTorch appears here only as the allocato
 and the owner of CUDA streams; every numeric result comes from libdfb200's CUDA kernels.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -82,6 +83,9 @@ class DevicePosterior(object):
     self.n = 0
     self.dim = 0
     self.lml = None
+    self._owners = weakref.WeakSet()      # GP objects using this posterior (gp_core.GP._post_is_shared)
+    # joint-posterior blocks (covariance / Thompson draws) must fit the handle's scoring chunk
+    self.TS_BLOCK = min(DevicePosterior.TS_BLOCK, int(self.query('chunk')))
     for _name, _value in DEFAULT_OPTIONS.items():
       self.set_option(_name, _value)
     self._keep = []      # tensors that must outlive asynchronous use
@@ -293,6 +297,20 @@ class DevicePosterior(object):
                                      int(what), C.c_void_p(out.data_ptr())), 'dfb_fill_rng')
     return out
 
+  def fill_candidates(self, seed, row0, m, bounds, out=None):
+    """ dfb_fill_candidates: rows row0 .. row0+m-1 of the device-generated candidate matrix (m x d CUDA tensor);
+        bounds: (d, 2) array-like of [lo, hi]. """
+    b = np.ascontiguousarray(np.asarray(bounds, dtype=np.float64))
+    d = int(b.shape[0])
+    lo = np.ascontiguousarray(b[:, 0]); hi = np.ascontiguousarray(b[:, 1])
+    if out is None:
+      out = torch.empty((int(m), d), dtype=torch.float64, device=self.device)
+    _lib.check(self.lib.dfb_fill_candidates(self.h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), int(row0), int(m), d,
+                                            lo.ctypes.data_as(C.POINTER(C.c_double)),
+                                            hi.ctypes.data_as(C.POINTER(C.c_double)),
+                                            C.c_void_p(out.data_ptr())), 'dfb_fill_candidates')
+    return out
+
   def ts_argmax(self, samples, idx_base, best, index, reset):
     """ dfb_ts_argmax: fold one block of draws (S x m CUDA tensor) into the running per-draw arg-max. """
     S, m = int(samples.shape[0]), int(samples.shape[1])
@@ -320,6 +338,15 @@ class DevicePosterior(object):
     _lib.check(self.lib.dfb_profile_read(self.h, int(cls), C.byref(ms), C.byref(n), C.byref(u)),
                'dfb_profile_read')
     return ms.value, n.value, u.value
+
+
+def measure_peak(what, device=None):
+  """ dfb_measure_peak: 'i8' -> tcgen05 kind::i8 issue rate (int8 TOP/s), 'f64' -> DMMA issue rate (TFLOP/s). """
+  dev = _require_cuda(device)
+  out = C.c_double(0.0)
+  code = {'i8': _lib.DFB_PEAK_TCGEN05_I8, 'f64': _lib.DFB_PEAK_DMMA_F64}[what]
+  _lib.check(_lib.load().dfb_measure_peak(dev.index, code, C.byref(out)), 'dfb_measure_peak')
+  return out.value
 
 
 _KM_CACHE = {}

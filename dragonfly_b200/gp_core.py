@@ -33,19 +33,31 @@ def _as_2d(X):
   return np.ascontiguousarray(arr)
 
 
-def _constant_mean_value(mean_func, dim):
-  """ Returns c if mean_func is constant on a few probe points (the only kind GPFitter produces),
-      else None.  Objects may also advertise it via a `const_value` attribute. """
+def _constant_mean_value(mean_func, X_train):
+  """ (c, trusted).  A mean function that ADVERTISES its constant (`const_value`: ConstantMean below, what the
+      fitter path builds) is folded into the device call as is: trusted.  Any other callable -- e.g. the plain
+      lambda of the reference's GPFitter.build_gp (gp_core.py:527-530) -- is a candidate constant only if it is
+      constant on the actual training inputs, and is then RE-CHECKED on the actual candidates of every call
+      (GP._mean_const_for) before the constant is used; it is never inferred from probe points. """
   if hasattr(mean_func, 'const_value'):
-    return float(mean_func.const_value)
+    return float(mean_func.const_value), True
   try:
-    probe = np.array([[0.0] * dim, [0.5] * dim, [0.123456789] * dim, [1.0] * dim])
-    vals = np.asarray(mean_func(probe), dtype=np.float64).reshape(-1)
+    vals = np.asarray(mean_func(X_train), dtype=np.float64).reshape(-1)
   except Exception:  # pylint: disable=broad-except
-    return None
-  if vals.shape[0] == 4 and np.all(vals == vals[0]):
-    return float(vals[0])
-  return None
+    return None, False
+  if vals.shape[0] == len(X_train) and vals.shape[0] > 0 and np.all(vals == vals[0]):
+    return float(vals[0]), False
+  return None, False
+
+
+def _owners_of(post):
+  """ The WeakSet of GP objects that use a device posterior (created on first use). """
+  import weakref
+  owners = getattr(post, '_owners', None)
+  if owners is None:
+    owners = weakref.WeakSet()
+    post._owners = owners
+  return owners
 
 
 class ConstantMean(object):
@@ -150,7 +162,24 @@ class GP(object):
         self.build_posterior()
 
   def _posterior_token(self):
-    return (id(self.kernel), id(self.mean_func), float(self.noise_var), self.handle_non_psd_kernels)
+    """ What the built device posterior depends on besides the data: the kernel's hyper-parameters BY VALUE (the
+        bytes of its device descriptor, so an in-place set_hyperparams / change_smoothness invalidates the
+        posterior), the mean function, the noise and the PSD handling. """
+    try:
+      dim = self._post.dim if getattr(self, '_post', None) is not None else self._train_matrix().shape[1]
+      kern_fp = bytes(build_descriptor(self.kernel, train_dim=dim, cand_dim=dim))
+    except Exception:  # pylint: disable=broad-except
+      kern_fp = id(self.kernel)
+    return (kern_fp, id(self.mean_func), getattr(self.mean_func, 'const_value', None), float(self.noise_var),
+            self.handle_non_psd_kernels)
+
+  def _post_is_shared(self):
+    """ True while another live GP object (a copy() / deepcopy() of this one) uses the same device posterior. """
+    post = getattr(self, '_post', None)
+    if post is None:
+      return False
+    owners = _owners_of(post)
+    return len([o for o in owners if o is not self and getattr(o, '_post', None) is post]) > 0
 
   def _rows_as_train_matrix(self, rows):
     """ `rows` (a list in the format of self.X) as rows of the matrix the kernel sees. """
@@ -174,7 +203,7 @@ class GP(object):
         of this GP, a jitter ladder in play, kernel / noise / mean changed since the build, padded
         size exceeded, or the extended matrix not positive definite at jitter 0). """
     post = getattr(self, '_post', None)
-    if (not self._can_extend_in_place(q) or getattr(self, '_post_shared', False) or
+    if (not self._can_extend_in_place(q) or self._post_is_shared() or
         post.n + q != self.num_tr_data):
       return False
     y_new = (np.asarray(self.Y[-q:], dtype=np.float64) -
@@ -237,9 +266,9 @@ class GP(object):
     self._y_centred = y_centred
     self._post, self._lml, self.jitter_power = self._build_on_device(X_mat, y_centred,
                                                                      _lib.DFB_BUILD_FULL)
+    _owners_of(self._post).add(self)
     self._post_token = self._posterior_token()
-    self._post_shared = False
-    self._mean_const = _constant_mean_value(self.mean_func, X_mat.shape[1])
+    self._mean_const, self._mean_trusted = _constant_mean_value(self.mean_func, self.X)
 
   def _state(self, name):
     if not hasattr(self, '_cache'):
@@ -304,11 +333,28 @@ class GP(object):
       return X_test
     return _as_2d(X_test)
 
+  def _mean_const_for(self, X_test):
+    """ The constant to fold into the device call for these candidates, or None.  An advertised constant is used as
+        is; an inferred one only after mean_func has been evaluated on the ACTUAL candidates (what the reference
+        does anyway, gp_core.py:172) and found equal to it everywhere. """
+    import torch
+    c = getattr(self, '_mean_const', None)
+    if c is None or getattr(self, '_mean_trusted', False):
+      return c
+    if isinstance(X_test, torch.Tensor):
+      return None
+    try:
+      vals = np.asarray(self.mean_func(X_test), dtype=np.float64).reshape(-1)
+    except Exception:  # pylint: disable=broad-except
+      return None
+    return c if (vals.shape[0] == len(X_test) and np.all(vals == c)) else None
+
   def _eval_on(self, post, X_test, want_std):
     import torch
     Xm = self._test_matrix(X_test)
-    if self._mean_const is not None:
-      return post.eval(Xm, mean_const=self._mean_const, want_std=want_std)
+    mc = self._mean_const_for(X_test)
+    if mc is not None:
+      return post.eval(Xm, mean_const=mc, want_std=want_std)
     if isinstance(Xm, torch.Tensor):
       raise NotImplementedError('A non-constant mean_func needs host candidates (it is a Python '
                                 'callable, gp_core.py:172).')
@@ -334,8 +380,9 @@ class GP(object):
     if len(Xm) > post.TS_BLOCK:
       raise NotImplementedError('uncert_form="covar" materialises an M x M matrix; M = %d exceeds '
                                 'the device block of %d.' % (len(Xm), post.TS_BLOCK))
-    if self._mean_const is not None:
-      return post.eval_covar(Xm, mean_const=self._mean_const)
+    mc = self._mean_const_for(X_test)
+    if mc is not None:
+      return post.eval_covar(Xm, mean_const=mc)
     mu, cov = post.eval_covar(Xm, mean_const=0.0)
     return np.asarray(self.mean_func(X_test)) + mu, cov
 
@@ -400,10 +447,11 @@ class GP(object):
   def _fused_score(self, acq, pts, halluc=None, test_desc=None, mean_const=None,
                    want_scores=False):
     """ One dfb_score_argmax call: returns (best_score, best_index, scores or None). """
-    mc = self._mean_const if mean_const is None else mean_const
+    mc = self._mean_const_for(pts) if mean_const is None else mean_const
     if mc is None:
-      raise NotImplementedError('Fused acquisition scoring needs a constant mean function '
-                                '(what GPFitter.build_gp produces, gp_core.py:527-530).')
+      raise NotImplementedError('Fused acquisition scoring needs a mean function that is constant on the '
+                                'candidates (what GPFitter.build_gp produces, gp_core.py:527-530); device-tensor '
+                                'candidates need it advertised through a `const_value` attribute (ConstantMean).')
     with self._hallucinated([] if halluc is None else halluc) as post:
       if test_desc is not None:
         post.set_test_kernel(test_desc)
@@ -427,9 +475,13 @@ class GP(object):
     """ draw_gaussian_samples (general_utils.py:224-232) per block of <= TS_BLOCK candidates:
         L = stable_cholesky(covar) with the same jitter ladder, U = np.random.normal(size=(M, S))
         drawn ONCE from the global RNG exactly like the reference, samples = (L U)^T + mu.
-        Blocks are sampled independently of each other: exact for M <= TS_BLOCK. """
+        DEVIATION from the reference for M > TS_BLOCK (min(4096, the handle's scoring chunk)): blocks are
+        sampled INDEPENDENTLY of each other -- the reference's single joint draw needs the M x M covariance
+        (8 TB at M = 10^6) -- so cross-block correlations are dropped and the sample matrix is not the one
+        the reference's RNG stream would give.  Exact, and seed-identical, for M <= TS_BLOCK. """
     Xm = self._test_matrix(X_test)
-    if self._mean_const is None:
+    mean_c = self._mean_const_for(X_test)
+    if mean_c is None:
       raise NotImplementedError('Thompson sampling on device needs a constant mean function.')
     M = len(Xm)
     U = np.random.normal(size=(M, int(num_samples)))
@@ -446,11 +498,11 @@ class GP(object):
       for s_lo in range(0, int(num_samples), 256):
         s_hi = min(int(num_samples), s_lo + 256)
         Ut = np.ascontiguousarray(U[lo:hi, s_lo:s_hi].T)
-        info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=0.0)
+        info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=mean_c, jitter=0.0)
         power = -11
         while info != 0:
           jitter = (10 ** power) * max_diag
-          info, smp, _ = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=jitter)
+          info, smp, _ = post.ts_draws(xb, Ut, mean_const=mean_c, jitter=jitter)
           if info != 0:
             power += 1
             if power >= 5:
@@ -472,8 +524,10 @@ class GP(object):
     import torch
     from . import dist as dfb_dist
     from .gpb_acquisitions import _shard_info
-    if self._mean_const is None:
-      raise NotImplementedError('Thompson sampling on device needs a constant mean function.')
+    mean_c = self._mean_const_for(X_test)
+    if mean_c is None:
+      raise NotImplementedError('Thompson sampling on device needs a constant mean function (advertised through '
+                                '`const_value` for device-tensor candidates).')
     S = int(num_samples)
     with self._hallucinated([] if X_halluc is None else X_halluc) as post:
       Xm = self._test_matrix(X_test)
@@ -491,11 +545,11 @@ class GP(object):
         for s_lo in range(0, S, 256):
           s_hi = min(S, s_lo + 256)
           Ut = post.fill_rng(seed, lo, S, hi - lo)[s_lo:s_hi] if S > 256 else post.fill_rng(seed, lo, S, hi - lo)
-          info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=0.0)
+          info, smp, max_diag = post.ts_draws(xb, Ut, mean_const=mean_c, jitter=0.0)
           power = -11
           while info != 0:                                    # stable_cholesky's ladder, per block
             jitter = (10 ** power) * max_diag
-            info, smp, _ = post.ts_draws(xb, Ut, mean_const=self._mean_const, jitter=jitter)
+            info, smp, _ = post.ts_draws(xb, Ut, mean_const=mean_c, jitter=jitter)
             if info != 0:
               power += 1
               if power >= 5:
@@ -528,15 +582,16 @@ class GP(object):
   def _child_str(self):
     return 'B200-GP %s' % (str(self.kernel))
 
-  # Copies share the device posterior; a shared posterior is never extended for good (add_data on
-  # either copy rebuilds into a fresh one), only temporarily for hallucinations (restored on exit).
+  # Copies share the device posterior; while another live copy uses it a posterior is never extended for good
+  # (add_data on either copy rebuilds into a fresh one), only temporarily for hallucinations (restored on exit).
+  # Sharing is tracked with a WeakSet of owners on the DevicePosterior, so it ends with the copy's lifetime (the
+  # syn_* wrappers copy the GP on every call, gpb_acquisitions.py:104).
   def __copy__(self):
     cls = self.__class__
     new = cls.__new__(cls)
     new.__dict__.update(self.__dict__)
     if getattr(self, '_post', None) is not None:
-      self._post_shared = True
-      new._post_shared = True
+      _owners_of(self._post).add(new)    # weak: the share ends when the copy is garbage-collected
     return new
 
   def __deepcopy__(self, memo):
@@ -552,6 +607,5 @@ class GP(object):
       else:
         new.__dict__[k] = _copy.deepcopy(v, memo)
     if getattr(self, '_post', None) is not None:
-      self._post_shared = True
-      new._post_shared = True
+      _owners_of(self._post).add(new)
     return new

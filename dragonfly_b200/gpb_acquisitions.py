@@ -154,7 +154,8 @@ def _get_gp_eval_for_parallel_strategy(gp, anc_data, uncert_form='std'):
 
 
 def _get_syn_recommendations_from_asy(asy_acq, num_workers, list_of_gps, anc_datas):
-  """ :90-115 -- worker k sees the previous k-1 picks as hallucinations. """
+  """ Transcribed from the reference's :90-115 (host glue, kept as is) -- worker k sees the previous k-1 picks as
+      hallucinations. """
   def _next(objs):
     ret = objs.pop(0)
     return ret, objs + [ret]
@@ -179,6 +180,7 @@ def _get_syn_recommendations_from_asy(asy_acq, num_workers, list_of_gps, anc_dat
 # UCB (:202-227)
 # ---------------------------------------------------------------------------------------------
 def _get_gp_ucb_dim(gp):
+  """ transcribed from the reference's :202-209 """
   if hasattr(gp, 'ucb_dim') and gp.ucb_dim is not None:
     return gp.ucb_dim
   elif hasattr(gp.kernel, 'dim'):
@@ -187,6 +189,7 @@ def _get_gp_ucb_dim(gp):
 
 
 def _get_ucb_beta_th(dim, time_step):
+  """ transcribed from the reference's :211-213 """
   return np.sqrt(0.5 * dim * np.log(2 * dim * time_step + 1))
 
 
@@ -395,7 +398,12 @@ def syn_ts(num_workers, list_of_gps, anc_datas):
 # Random (:300-311)
 # ---------------------------------------------------------------------------------------------
 def asy_rand(_, anc_data):
-  """ :301-307 -- the vectorised objective returns ONE uniform, so arg-max is candidate 0. """
+  """ :301-307 -- the objective is np.random.random((1,)) whatever its argument.  With the `rand` maximiser the
+      vectorised objective returns ONE uniform for the whole candidate matrix, so the arg-max is candidate 0;
+      the sequential maximisers call it point by point (one uniform per evaluation), so they run as in the
+      reference and consume the global RNG like it. """
+  if not _check_rand_euclidean(anc_data):
+    return _delegate_to_reference_maximiser(lambda x: np.random.random((1,)), anc_data)
   rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
   np.random.random((1,))
   return rand_pts[0]

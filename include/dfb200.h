@@ -234,6 +234,14 @@ int dfb_moo_score_argmax(dfb_handle* h, const dfb_moo_desc* desc, const double* 
 int dfb_fill_rng(dfb_handle* h, uint64_t seed, int64_t col0, int32_t S, int64_t m, int32_t what, double* out_dev);
 int dfb_ts_argmax(dfb_handle* h, const double* samples_dev, int64_t ld, int32_t S, int64_t m, int64_t idx_base,
                   int32_t reset, double* best_dev, int64_t* index_dev);
+/* random_sample + map_to_bounds (oper_utils.py:59-67, general_utils.py:25-27) on the device: rows row0 .. row0+m-1 of
+ * the candidate matrix, row-major m x d, coordinate s of global row a = lo[s] + u * (hi[s] - lo[s]) with u the
+ * DFB_RNG_UNIFORM element (s, a) of dfb_fill_rng for the same seed.  A row depends on (seed, its global index) only:
+ * every rank generates just its shard, nobody holds the M x d matrix on the host, and the winning row is
+ * regenerated from its index.  (np.random's MT19937 stream cannot be reproduced this way: the operators keep the
+ * reference's host generation for seeded parity and use this in their throughput mode.)  lo / hi: HOST arrays of d.  */
+int dfb_fill_candidates(dfb_handle* h, uint64_t seed, int64_t row0, int64_t m, int32_t d, const double* lo_host,
+                        const double* hi_host, double* out_dev);
 
 /* Kernel.__call__(X1, X2) (kernel.py:72-83): the n1 x n2 Gram matrix, device pointers. */
 int dfb_kernel_matrix(dfb_handle* h, const dfb_kernel_desc* desc, const double* X1_dev, int64_t n1,
@@ -256,16 +264,22 @@ int64_t dfb_launch_count(dfb_handle* h);
 /* Tuning switches.
  *  "gemm_impl"  : 0 = cp.async-ring DMMA kernel, 1 = TMA + mbarrier warp-specialised DMMA kernel for the
  *                 fp64 scoring contraction (env DFB200_GEMM=v1|tma at dfb_create; default tma).
- *  "score_impl" : how |L^-1 k_*|^2 is contracted (env DFB200_SCORE=fp64|i8|auto; default auto):
- *                 0 = fp64 DMMA everywhere;
- *                 1 = int8-slice tcgen05 path (exact digit expansion of both fp64 operands, int32
- *                     accumulation in tensor memory; measured |d sigma^2| <= 4e-10 at N = 5000, a-priori
- *                     estimate: query "i8_sigma2_bound") everywhere;
- *                 2 = auto: dfb_eval stays fp64; dfb_score_argmax scores with the int8 path, then re-scores
- *                     in fp64 the shortlist of candidates that could be the arg-max, so the returned index
- *                     and score are the fp64 ones.  The int8 path is skipped when its a-priori error bound
- *                     (query "i8_sigma2_bound") exceeds 5e-9 max(1, k(x,x)) -- half the 1e-8 contract --
- *                     or n < 1024.
+ *  "score_impl" : how |L^-1 k_*|^2 is contracted (env DFB200_SCORE=fp64|i8|auto at dfb_create; default auto;
+ *                 readable back through dfb_query "score_impl").  ONE switch -- score_impl = 0 -- puts every call
+ *                 on the pure fp64 DMMA path:
+ *                 0 = fp64 DMMA everywhere (no reduced-precision arithmetic anywhere; 1.2 M candidates/s at N = 5000);
+ *                 1 = int8-slice tcgen05 path everywhere, sigma vectors included (exact digit expansion of both fp64
+ *                     operands, int32 accumulation in tensor memory; a-priori bound: query "i8_sigma2_bound");
+ *                 2 = auto: dfb_eval stays fp64; dfb_score_argmax screens with the int8 path, re-scores in fp64
+ *                     every candidate whose int8 score -- widened by the error allowance that follows from the
+ *                     bound -- could reach the fp64 maximum, returns the fp64 arg-max (index and score) of those,
+ *                     and finally checks the int8 scores of that shortlist against the fp64 ones: a candidate
+ *                     outside its allowance voids the screen and the call is redone in fp64 (queries
+ *                     "last_selfcheck_violations", "last_selfcheck_ratio").  The bound (api.cu: i8_sigma2_bound) is
+ *                     a sqrt(n) rounding-error model with a 9x margin over every measured maximum
+ *                     (profiles/r02_i8_bound_sweep.json), not a worst-case bound.  The screen is skipped when the
+ *                     bound exceeds 5e-9 ABSOLUTE (half the 1e-8 sigma^2 contract, whatever the kernel scale;
+ *                     query "i8_bound_limit") or n < 1024.
  *  "i8_impl"    : which tcgen05 kernel the int8 path uses (switching re-slices W: layouts differ):
  *                 2 (default) = persistent CTA-pair kernel: tcgen05.mma.cta_group::2 M256 N128 K32, two passes
  *                     per 256 x 128 tile (gemm_i8c2.cuh);
@@ -274,8 +288,10 @@ int64_t dfb_launch_count(dfb_handle* h);
  *  "i8_radix"   : digit scheme of the CTA-pair kernel: 1 = five radix-256 digits, 15 products (measured
  *                 |d sigma^2| 3.6e-10 at N = 5000); 0 = six radix-128 digits, 21 products (3e-11), the scheme
  *                 of i8_impl 0 and 1; -1 (default) = radix 256 whenever its a-priori bound is below
- *                 5e-9 max(1, k(x,x)) for the training kernel, else radix 128.
+ *                 5e-9 (absolute) for the training kernel, else radix 128.
  *  "i8_fuse"    : 1 (default) = the K_* kernel emits the int8 digit planes directly, 0 = via an fp64 K_* buffer.
+ *  "i8_unguarded": diagnostics only (tools/sweep_i8_bound.py): 1 = run the int8 path even when its a-priori bound exceeds
+ *                 the limit, so that the bound can be compared with the measured error where it would refuse.
  *  "i8_ts"      : i8_impl 0 only: 1 = stage W's digits in tensor memory (tcgen05.cp), default 0.
  *  "lookahead"  : 1 (default) = look-ahead schedule of the blocked factorisation (next panel's column updated first,
  *                 chol_diag + panel solve of step k+1 overlap the bulk trailing update of step k on a second stream;
@@ -284,8 +300,10 @@ int64_t dfb_launch_count(dfb_handle* h);
  *                 warp per row, HBM-bound) instead of spending 128-wide DMMA tiles on them; 0 = tile kernels always.
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
-/* Diagnostics: "i8_sigma2_bound", "i8_ready", "i8_impl", "i8_radix256", "last_used_i8", "last_shortlist"
- * (-1 = overflow -> fp64 pass). */
+/* Diagnostics: "i8_sigma2_bound", "i8_bound_limit", "i8_ready", "i8_impl", "i8_radix256", "score_impl",
+ * "last_used_i8", "last_shortlist" (-1 = overflow -> fp64 pass), "last_selfcheck_violations" (> 0: the int8 screen
+ * was voided and the call redone in fp64), "last_selfcheck_ratio" (max |s_int8 - s_fp64| / allowance over the last
+ * shortlist; the model's margin is its inverse). */
 int dfb_query(dfb_handle* h, const char* name, double* out);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
@@ -298,6 +316,14 @@ int dfb_query(dfb_handle* h, const char* name, double* out);
 #define DFB_PROF_BUILD 3
 int dfb_profile_enable(dfb_handle* h, int on);
 int dfb_profile_read(dfb_handle* h, int cls, double* ms_total, int64_t* launches, double* units);
+
+/* Live roofline denominators for bench.py, measured on `device` in the calling process (best of 3 short launches):
+ * DFB_PEAK_TCGEN05_I8 -> issue rate of tcgen05.mma kind::i8 M128 N256 K32 in int8 TOP/s (2 per MAC), the peak the
+ * int8-slice contraction is quoted against; DFB_PEAK_DMMA_F64 -> fp64 DMMA.8x8x4 issue rate in TFLOP/s.
+ * MEASURED_PEAKS.json carries neither.  Not on the product path; replaces nothing in the reference.  */
+#define DFB_PEAK_TCGEN05_I8 0
+#define DFB_PEAK_DMMA_F64   1
+int dfb_measure_peak(int device, int what, double* out_host);
 
 #ifdef __cplusplus
 }
