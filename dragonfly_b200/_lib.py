@@ -74,6 +74,7 @@ PROTOTYPES = {
   'dfb_extend_posterior': (C.c_int, [_P, _P, _I64, _P, _I32, C.POINTER(_D)]),
   'dfb_restore_posterior': (C.c_int, [_P]),
   'dfb_get_max_diag': (C.c_int, [_P, C.POINTER(_D)]),
+  'dfb_lml_gradients': (C.c_int, [_P, C.POINTER(_D), _I32]),
   'dfb_get_state': (C.c_int, [_P, _P, _P, _P]),
   'dfb_set_alpha': (C.c_int, [_P, _P, _I64]),
   'dfb_eval': (C.c_int, [_P, _P, _I64, _I32, _I32, _D, _P, _P]),

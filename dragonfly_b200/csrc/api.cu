@@ -862,6 +862,50 @@ int dfb_restore_posterior(dfb_handle* h) {
   return 0;
 }
 
+int dfb_lml_gradients(dfb_handle* h, double* out_host, int32_t n_out) {
+  DFB_TRY(need(h, true, true, true, true, true));
+  const dfb_kernel_desc& desc = h->desc_tr;
+  if (desc.n_terms != 1 || desc.n_factors != 1) {
+    // the reference's composite kernels inherit Kernel._child_gradient, which raises (kernel.py:123-125)
+    set_error("LML gradients are defined for plain SE / Matern kernels only (kernel has %d terms, %d factors)",
+              desc.n_terms, desc.n_factors);
+    return -3;
+  }
+  const int D = desc.factors[0].n_dims;
+  const int P = 4 + D;
+  if (out_host == nullptr || n_out < P) { set_error("lml_gradients: out needs 4 + d = %d entries", P); return -1; }
+  DFB_CUDA_OK(cudaSetDevice(h->device));
+  const int64_t npad = h->npad;
+  const int nb = (int)(npad / TILE);
+  const int64_t n_tiles = (int64_t)nb * (nb + 1) / 2;
+  if (n_tiles * P > (int64_t)nb * h->chunk || P > h->chunk) {
+    set_error("lml_gradients: scoring chunk %lld too small for %lld tile partials", (long long)h->chunk, (long long)n_tiles);
+    return -1;
+  }
+  DFB_TRY(ensure_train_scaled(h));
+  // K^-1 = W^T W row-block stripe by stripe into the K_* chunk buffer (chunk rows x npad), each followed by the
+  // fused reduction against the kernel derivatives.  L^-T sits in the middle block of the tall matrix.
+  const double* Wt = h->T + (size_t)npad * npad;
+  const int stripe = (int)((h->chunk / TILE) < nb ? (h->chunk / TILE) : nb);
+  for (int rb0 = 0; rb0 < nb; rb0 += stripe) {
+    const int R = (nb - rb0 < stripe) ? nb - rb0 : stripe;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = Wt + (int64_t)rb0 * TILE * npad; g.lda = npad; g.B = Wt; g.ldb = npad; g.D = h->Ks; g.ldd = npad;
+    g.alpha = 1.0; g.mode = MODE_GENERIC; g.n_rb = R; g.n_cb = nb; g.K = (int)npad; g.tri = 3; g.lower_only = 1;
+    g.rb0 = rb0;
+    DFB_TRY(launch_gemm(h, g, EPI_STORE, R * nb));
+    DFB_TRY(launch_lml_grad_tiles(h, h->d_desc_tr, h->tr.xs, h->tr.nrm, npad, h->alpha, h->Ks, npad, rb0, R, nb, h->n, P,
+                                  h->partial));
+  }
+  DFB_TRY(launch_lml_grad_reduce(h, h->partial, n_tiles, P, P, h->alpha, h->n, h->score));
+  DFB_CUDA_OK(cudaMemcpyAsync(out_host, h->score, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  // 1/2 tr(.) (gp_core.py:240); slot 1 still lacks the factor noise_var, slot 2 is sum(alpha) as is
+  for (int p = 0; p < P; p++) if (p != 2) out_host[p] *= 0.5;
+  return 0;
+}
+
 int dfb_get_max_diag(dfb_handle* h, double* out_host) {
   DFB_TRY(need(h, true, true, true, false, false));
   if (out_host == nullptr) { set_error("out is NULL"); return -1; }

@@ -39,8 +39,11 @@ struct GemmArgs {
   int mode;
   int n_rb, n_cb;                   // SCORE / GENERIC: tile grid
   int K;                            // k extent (multiple of 16)
-  int tri;                          // GENERIC: 0 full K, 1 A lower-tri (k < (rb+1)*128), 2 B lower-tri
+  int tri;                          // GENERIC: 0 full K, 1 A lower-tri (k < (rb+1)*128), 2 B lower-tri,
+                                    //   3 both operands UPPER-tri (k >= max(rb, cb)*128): W^T W from L^-T
   int lower_only;                   // GENERIC: skip tiles with cb > rb
+  int rb0;                          // GENERIC: global index of row block 0 (A / C / D already point at it): the
+                                    //   triangular ranges and lower_only refer to rb0 + rb
   int step, nb;                     // PANEL / TRAIL: factorisation step and #top row blocks
   int skip_bottom;                  // PANEL / TRAIL: the L^-T rows are absent (LML-only build)
   int tr_j0, tr_nc;                 // TRAIL: column blocks step+1+tr_j0 .. +tr_nc-1 only (tr_nc = 0: all of them) --
@@ -113,11 +116,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tn_kernel(const GemmArgs
     const int tile = bid / ks, slice = bid - tile * ks;
     rb = tile / g.n_cb;
     cb = tile % g.n_cb;
-    if (g.lower_only && cb > rb) return;
+    const int rbg = rb + g.rb0;
+    if (g.lower_only && cb > rbg) return;
     A = g.A + (int64_t)rb * TILE * g.lda;
     B = g.B + (int64_t)cb * TILE * g.ldb;
-    if (g.tri == 1) k_hi = min(g.K, (rb + 1) * TILE);
+    if (g.tri == 1) k_hi = min(g.K, (rbg + 1) * TILE);
     else if (g.tri == 2) k_hi = min(g.K, (cb + 1) * TILE);
+    else if (g.tri == 3 && ks == 1) { k_lo = min(g.K, max(rbg, cb) * TILE); A += k_lo; B += k_lo; }
     if (ks > 1) {
       // slice `slice` of this tile's k-range, in multiples of the pipeline stage; empty slices store zeros
       const int chunk = ((k_hi + ks - 1) / ks + GEMM_BK - 1) / GEMM_BK * GEMM_BK;

@@ -1849,4 +1849,147 @@ int launch_set_diag(dfb_handle* h, double* M, int64_t ld, int64_t from, int64_t 
   return 0;
 }
 
+// ================================================================================================
+// Log-marginal-likelihood gradients.
+//   GP.compute_grad_log_marginal_likelihood (gp_core.py:229-240):  1/2 tr((alpha alpha^T - K^-1) G),
+//   G = Kernel.gradient(param, X, X) (kernel.py:202-217 SE, 301-322 Matern).
+// K^-1 = W^T W comes from one triangular DMMA product of L^-T with itself (gemm.cuh, tri = 3); this kernel then
+// walks the lower 128 x 128 tiles, re-derives every G entry from the scaled coordinates (dK/dparam is never
+// materialised) and reduces M_ij G_ij for ALL parameters of the kernel in one pass:
+//   slot 0 'scale'                G = K itself
+//   slot 1 trace part of 'noise_var'  sum_i M_ii          (host multiplies by noise_var)
+//   slot 3 'same_dim_bandwidths'  SE: K D2 / bw_0          Matern: T1 (-r / bw_0)
+//   slot 4+q 'dim_bandwidths', q  SE: K d2_q / bw_q        Matern: T1 (-(d2_q / bw_q) / r), 0 on the diagonal
+// with D2 the scaled squared distance, d2_q its one-coordinate version (dist_squared on a column, as the
+// reference forms it), r = sqrt(D2) and T1 = scale c w (u' - s2 u) in the notation of kernel.py:272-290.
+// Symmetric: off-diagonal entries of the lower triangle count twice.  Per-warp slots in shared memory and a
+// fixed-order final sum keep the result deterministic.
+// ================================================================================================
+constexpr int GRAD_FIXED = 4;
+
+__global__ void __launch_bounds__(256)
+lml_grad_tile_kernel(const dfb_kernel_desc* __restrict__ desc_g, const double* __restrict__ xs,
+                     const double* __restrict__ nrm, int64_t npad, const double* __restrict__ alpha,
+                     const double* __restrict__ Kinv, int64_t ldk, int rb0, int nb, int64_t n, int pstride,
+                     double* __restrict__ partial) {
+  const int rb = rb0 + (int)blockIdx.x / nb, cb = (int)blockIdx.x % nb;
+  if (cb > rb) return;
+  __shared__ dfb_factor_desc fsh;
+  __shared__ double bw_sh[DFB_MAX_SLOTS];
+  __shared__ double red[GRAD_FIXED + DFB_MAX_SLOTS][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = desc_g->factors[0].n_dims;
+  if (tid == 0) fsh = desc_g->factors[0];
+  for (int q = tid; q < D; q += 256) bw_sh[q] = desc_g->slot_bandwidth[q];
+  for (int idx = tid; idx < (GRAD_FIXED + D) * 8; idx += 256) (&red[0][0])[idx] = 0.0;
+  __syncthreads();
+  const dfb_factor_desc f = fsh;
+  const bool se = (f.kind == DFB_BASE_SE);
+  const double bw0 = bw_sh[0];
+  const int64_t j = (int64_t)cb * TILE + (tid & 127);
+  const int half = tid >> 7;
+  const bool jvalid = j < n;
+  const double aj = alpha[j], nj = nrm[j];
+  double acc_scale = 0.0, acc_tr = 0.0, acc_same = 0.0;
+  for (int pass = 0; pass < 4; pass++) {
+    const int64_t i0 = (int64_t)rb * TILE + half * 64 + pass * 16;
+    double t1m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int64_t i = i0 + k;
+      double wgt = 0.0;
+      if (jvalid && i < n) wgt = (rb != cb || j < i) ? 2.0 : (j == i ? 1.0 : 0.0);
+      double dot = 0.0;
+      for (int q = 0; q < D; q++) dot = fma(xs[(int64_t)q * npad + i], xs[(int64_t)q * npad + j], dot);
+      double d2 = __dadd_rn(__dadd_rn(nj, nrm[i]), -2.0 * dot);
+      d2 = fmax(d2, 0.0);
+      const double M = wgt * (alpha[i] * aj - Kinv[(i - (int64_t)rb0 * TILE) * ldk + j]);
+      if (i == j && jvalid) acc_tr += M;
+      if (se) {
+        const double base = f.scale * dfb_exp_nonpos(d2 * -0.5);
+        acc_scale = fma(M, base, acc_scale);
+        acc_same = fma(M, base * (d2 / bw0), acc_same);
+        t1m[k] = M * base;
+      } else {
+        const double dist = sqrt(d2);
+        const double mult = f.s8 * dist;
+        double u = 0.0, up = 0.0;
+        for (int t = 0; t <= f.p; t++) {
+          const int e = f.p - t;
+          double pw = 1.0, pw1 = 1.0;                      // mult^e, mult^(e-1)
+          for (int r = 0; r < e; r++) { pw1 = pw; pw *= mult; }
+          u += f.coeffs[t] * pw;
+          if (e > 0) up += f.s8 * (double)e * f.coeffs[t] * pw1;
+        }
+        const double w = f.gamma_ratio * dfb_exp_nonpos(-f.s2 * dist);
+        acc_scale = fma(M, f.scale * (u * w), acc_scale);
+        const double T1 = f.scale * w * (up - f.s2 * u);
+        acc_same = fma(M, T1 * (-(dist / bw0)), acc_same);
+        // the reference zeroes the diagonal distances (np.fill_diagonal) before the per-dimension gradient
+        t1m[k] = (i == j || wgt == 0.0) ? 0.0 : M * T1 * (-1.0 / dist);     // wgt 0: padding / upper half of a diagonal tile
+      }
+    }
+    for (int q = 0; q < D; q++) {
+      const double xj = xs[(int64_t)q * npad + j];
+      const double xj2 = xj * xj, ibw = bw_sh[q];
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const double xi = xs[(int64_t)q * npad + i0 + k];
+        double dsq = __dadd_rn(__dadd_rn(xj2, __dmul_rn(xi, xi)), -2.0 * __dmul_rn(xi, xj));
+        dsq = fmax(dsq, 0.0);
+        if (t1m[k] != 0.0) sacc = fma(t1m[k], dsq / ibw, sacc);
+      }
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[GRAD_FIXED + q][warp] += sacc;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_scale += __shfl_xor_sync(0xffffffffu, acc_scale, o);
+    acc_tr += __shfl_xor_sync(0xffffffffu, acc_tr, o);
+    acc_same += __shfl_xor_sync(0xffffffffu, acc_same, o);
+  }
+  if (lane == 0) { red[0][warp] = acc_scale; red[1][warp] = acc_tr; red[3][warp] = acc_same; }
+  __syncthreads();
+  if (tid < GRAD_FIXED + D) {
+    double s = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) s += red[tid][w8];
+    const int64_t t = (int64_t)rb * (rb + 1) / 2 + cb;
+    partial[t * pstride + tid] = s;
+  }
+}
+
+// out[p] = sum over the lower tiles, in tile order; out[2] = sum(alpha) ('noise_mean', gp_core.py:234-235)
+__global__ void lml_grad_reduce_kernel(const double* __restrict__ partial, int64_t n_tiles, int pstride, int n_out,
+                                       const double* __restrict__ alpha, int64_t n, double* __restrict__ out) {
+  const int p = threadIdx.x;
+  if (p >= n_out) return;
+  double s = 0.0;
+  if (p == 2) {
+    for (int64_t i = 0; i < n; i++) s += alpha[i];
+  } else {
+    for (int64_t t = 0; t < n_tiles; t++) s += partial[t * pstride + p];
+  }
+  out[p] = s;
+}
+
+int launch_lml_grad_tiles(dfb_handle* h, const dfb_kernel_desc* d_desc, const double* xs, const double* nrm, int64_t npad,
+                          const double* alpha, const double* Kinv, int64_t ldk, int rb0, int n_rb, int nb, int64_t n,
+                          int pstride, double* partial) {
+  lml_grad_tile_kernel<<<(unsigned)(n_rb * nb), 256, 0, h->stream>>>(d_desc, xs, nrm, npad, alpha, Kinv, ldk, rb0, nb, n,
+                                                                    pstride, partial);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_lml_grad_reduce(dfb_handle* h, const double* partial, int64_t n_tiles, int pstride, int n_out,
+                           const double* alpha, int64_t n, double* out) {
+  lml_grad_reduce_kernel<<<1, 256, 0, h->stream>>>(partial, n_tiles, pstride, n_out, alpha, n, out);
+  h->launches++;
+  DFB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace dfb

@@ -158,6 +158,15 @@ class DevicePosterior(object):
     _lib.check(self.lib.dfb_restore_posterior(self.h), 'dfb_restore_posterior')
     self.n = int(n_before)
 
+  def lml_gradients(self, dim):
+    """ dfb_lml_gradients: [scale, noise_var / noise_var, noise_mean, same_dim_bandwidths, dim_bandwidths[0..d)]. """
+    out = (C.c_double * (4 + int(dim)))()
+    st = self.lib.dfb_lml_gradients(self.h, out, 4 + int(dim))
+    if st == -3:
+      raise NotImplementedError(_lib.last_error())
+    _lib.check(st, 'dfb_lml_gradients')
+    return np.array(out[:], dtype=np.float64)
+
   def max_diag(self):
     out = C.c_double(0.0)
     _lib.check(self.lib.dfb_get_max_diag(self.h, C.byref(out)), 'dfb_get_max_diag')

@@ -62,6 +62,31 @@ def all_reduce_argmax(score, global_index, device=None, group=None):
   return reduce_pairs(scores, stacked[:, 1])
 
 
+def all_reduce_argmax_point(score, global_index, point, dim, device=None, group=None):
+  """ all_reduce_argmax with the winner's coordinates riding along: still ONE all-gather, of (2 + dim) 8-byte
+      words per rank, so that a rank need not hold (or re-draw) candidate rows outside its own shard.  `point` may
+      be None on a rank without candidates (index < 0).  Returns (score, index, point (dim,) ndarray). """
+  if not (dist.is_available() and dist.is_initialized()):
+    return float(score), int(global_index), point
+  world = dist.get_world_size(group)
+  dev = torch.device('cpu') if device is None else device
+  words = np.zeros(2 + int(dim), dtype=np.int64)
+  words[0] = int(np.float64(score).view(np.int64))
+  words[1] = int(global_index)
+  if point is not None:
+    words[2:] = np.ascontiguousarray(np.asarray(point, dtype=np.float64)).view(np.int64)
+  mine = torch.from_numpy(words).to(dev)
+  gathered = [torch.empty_like(mine) for _ in range(world)]
+  dist.all_gather(gathered, mine, group=group)
+  stacked = torch.stack(gathered).cpu().numpy()
+  scores = stacked[:, 0].copy().view(np.float64)
+  best_s, best_i = reduce_pairs(scores, stacked[:, 1])
+  if best_i < 0:
+    return best_s, best_i, None
+  row = int(np.nonzero(stacked[:, 1] == best_i)[0][0])
+  return best_s, best_i, stacked[row, 2:].copy().view(np.float64)
+
+
 def all_reduce_argmax_many(scores, global_indices, device=None, group=None):
   """ K independent arg-maxes at once (Add-UCB groups, Thompson draws): one all-gather of K packed
       (score bits, index) pairs per rank, K local reductions.  Returns (scores (K,), indices (K,)). """

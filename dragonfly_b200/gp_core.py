@@ -60,6 +60,10 @@ def _owners_of(post):
   return owners
 
 
+# Scoring chunk (candidate rows per device pass) of new posteriors; 0 = the library default (~256 MB of K_* rows).
+DEFAULT_CHUNK = [0]
+
+
 class ConstantMean(object):
   """ lambda x: np.array([c] * len(x)) with the constant advertised (gp_core.py:527-530). """
 
@@ -96,6 +100,48 @@ def stable_cholesky_on_device(post, noise_var, add_to_diag_till_psd=True, flags=
       raise ValueError(('Could not compute Cholesky decomposition despite adding %0.4f to the '
                         'diagonal. This is likely because the M is not positive semi-definite or '
                         'has infinities/nans.') % (diag_noise))
+
+
+# What INTEGRATION.md's recipe copies onto the reference's own dragonfly.gp.gp_core.GP (setattr by name): the
+# public methods the device path replaces plus the private helpers they call.
+# Kept by the reference class: its constructor / set-up, data bookkeeping and printing.
+_REBIND_KEEPS_REFERENCE = ('__init__', '_set_up', '_write_message', 'set_data', 'add_data_single', '__str__',
+                           '_child_str', '_get_training_kernel_matrix')
+
+
+def _rebind_methods():
+  """ Every plain method / class attribute of the device-backed GP except the ones the reference keeps: derived from
+      the class itself so that the recipe cannot fall behind the implementation. """
+  names = []
+  for name, val in vars(GP).items():
+    if name in _REBIND_KEEPS_REFERENCE or name in REBIND_PROPERTIES or isinstance(val, property):
+      continue
+    if callable(val) or name == 'incremental_updates':
+      names.append(name)
+  return names
+
+
+REBIND_PROPERTIES = ['L', 'alpha', 'K_trtr_wo_noise']
+
+
+class _FusedSession(object):
+  """ See GP._fused_session. """
+
+  def __init__(self, gp, post, acq, mean_const):
+    self.gp, self.post, self.acq, self.mean_const = gp, post, acq, mean_const
+
+  def score(self, pts, want_scores=False):
+    """ dfb_score_argmax over one slab: (best_score, best_index within the slab, scores or None). """
+    mc = self.gp._mean_const_for(pts) if self.mean_const is None else self.mean_const
+    if mc is None:
+      raise NotImplementedError('Fused acquisition scoring needs a mean function that is constant on the '
+                                'candidates (what GPFitter.build_gp produces, gp_core.py:527-530).')
+    return self.post.score_argmax(self.acq, self.gp._test_matrix(pts), mean_const=mc, want_scores=want_scores)
+
+  def slab_rows(self, target):
+    """ Rows per streamed slab: a whole number of the handle's scoring chunks (no ragged chunk inside a slab). """
+    chunk = int(self.post.query('chunk'))
+    return max(1, int(target) // chunk) * chunk
 
 
 class GP(object):
@@ -232,7 +278,7 @@ class GP(object):
 
   def _new_device_posterior(self, n_max):
     from .device import DevicePosterior
-    return DevicePosterior(n_max, device=getattr(self, '_device', None))
+    return DevicePosterior(n_max, device=getattr(self, '_device', None), chunk=DEFAULT_CHUNK[0])
 
   def _build_on_device(self, X_mat, y_centred, flags):
     if self.handle_non_psd_kernels not in ('guaranteed_psd', 'try_before_project', 'project_first'):
@@ -326,6 +372,38 @@ class GP(object):
       raise RuntimeError('Posterior has not been built.')
     return self._lml
 
+  def compute_grad_log_marginal_likelihood(self, param, *args):
+    """ gp_core.py:229-240: 1/2 tr((alpha alpha^T - K^-1) dK/dparam) for param in 'noise_var', 'noise_mean' and the
+        kernel's own 'scale', 'same_dim_bandwidths' and (any other name, param_num) = bandwidth of one dimension
+        (kernel.py:202-217, 301-322).  One device call (dfb_lml_gradients) yields the gradients w.r.t. ALL of them
+        -- K^-1 from one triangular product of L^-T with itself, dK/dparam re-derived entry by entry, never
+        stored -- and is cached for the posterior, so looping over the parameters as the reference's samplers do
+        (gp_core.py:571) costs one pass.  The reference indexes dim_bandwidths[0, j], which only works for kernels
+        that were given a (d, 1) bandwidth column; the values here are those it returns in that case. """
+    if self._post is None or self.num_tr_data == 0:
+      raise RuntimeError('Posterior has not been built.')
+    if param == 'noise_mean':
+      return float(self._lml_gradient_vector()[2])
+    if param == 'noise_var':
+      return float(self.noise_var * self._lml_gradient_vector()[1])
+    if param == 'scale':
+      return float(self._lml_gradient_vector()[0])
+    if param == 'same_dim_bandwidths':
+      return float(self._lml_gradient_vector()[3])
+    param_num = args[0] if len(args) > 0 else None
+    if param_num is None or not 0 <= int(param_num) < self.kernel.dim:
+      raise IndexError('param_num %s is not a dimension of the kernel.' % (param_num,))
+    return float(self._lml_gradient_vector()[4 + int(param_num)])
+
+  def _lml_gradient_vector(self):
+    if getattr(self, '_cache', None) is None:
+      self._cache = {}
+    key = ('lml_grad', id(self._post), self._post.n)
+    if self._cache.get('lml_grad_key') != key:
+      self._cache['lml_grad'] = self._post.lml_gradients(self.kernel.dim)
+      self._cache['lml_grad_key'] = key
+    return self._cache['lml_grad']
+
   # -- prediction --------------------------------------------------------------------------------------
   def _test_matrix(self, X_test):
     import torch
@@ -342,7 +420,9 @@ class GP(object):
     if c is None or getattr(self, '_mean_trusted', False):
       return c
     if isinstance(X_test, torch.Tensor):
-      return None
+      # a Python callable can only see host rows: the check costs one device->host copy of the candidates
+      # (advertise the constant with ConstantMean to avoid it)
+      X_test = X_test.detach().cpu().numpy()
     try:
       vals = np.asarray(self.mean_func(X_test), dtype=np.float64).reshape(-1)
     except Exception:  # pylint: disable=broad-except
@@ -355,10 +435,11 @@ class GP(object):
     mc = self._mean_const_for(X_test)
     if mc is not None:
       return post.eval(Xm, mean_const=mc, want_std=want_std)
-    if isinstance(Xm, torch.Tensor):
-      raise NotImplementedError('A non-constant mean_func needs host candidates (it is a Python '
-                                'callable, gp_core.py:172).')
     mu, sd = post.eval(Xm, mean_const=0.0, want_std=want_std)
+    if isinstance(Xm, torch.Tensor):
+      # non-constant Python mean on device candidates: evaluated on a host copy of the rows (gp_core.py:172)
+      mvals = np.asarray(self.mean_func(Xm.detach().cpu().numpy()), dtype=np.float64).reshape(-1)
+      return torch.from_numpy(mvals).to(mu.device) + mu, sd
     return np.asarray(self.mean_func(X_test)) + mu, sd
 
   def eval(self, X_test, uncert_form='none'):
@@ -444,22 +525,26 @@ class GP(object):
       return self._post
     return self._augmented_posterior(halluc)
 
-  def _fused_score(self, acq, pts, halluc=None, test_desc=None, mean_const=None,
-                   want_scores=False):
-    """ One dfb_score_argmax call: returns (best_score, best_index, scores or None). """
-    mc = self._mean_const_for(pts) if mean_const is None else mean_const
-    if mc is None:
-      raise NotImplementedError('Fused acquisition scoring needs a mean function that is constant on the '
-                                'candidates (what GPFitter.build_gp produces, gp_core.py:527-530); device-tensor '
-                                'candidates need it advertised through a `const_value` attribute (ConstantMean).')
+  @contextmanager
+  def _fused_session(self, acq, halluc=None, test_desc=None, mean_const=None):
+    """ One acquisition-maximisation session on the device posterior: the evaluations in progress are appended
+        ONCE (in place when possible, gp_core.py:200-217) and the group's test kernel bound once, however many
+        slabs of candidates are then scored through `session.score(pts)` (gpb_acquisitions._fused_maximise streams
+        the candidates in slabs so that drawing them overlaps with scoring them). """
     with self._hallucinated([] if halluc is None else halluc) as post:
       if test_desc is not None:
         post.set_test_kernel(test_desc)
       try:
-        return post.score_argmax(acq, self._test_matrix(pts), mean_const=mc, want_scores=want_scores)
+        yield _FusedSession(self, post, acq, mean_const)
       finally:
         if test_desc is not None:
           post.set_test_kernel(None)
+
+  def _fused_score(self, acq, pts, halluc=None, test_desc=None, mean_const=None,
+                   want_scores=False):
+    """ One dfb_score_argmax call: returns (best_score, best_index, scores or None). """
+    with self._fused_session(acq, halluc, test_desc, mean_const) as session:
+      return session.score(pts, want_scores=want_scores)
 
   def _group_test_descriptor(self, add_kernel, kernel_j, group_j, train_dim):
     """ K_*j = scale * k_j(X*_j, X[:, g_j]) (gpb_acquisitions.py:166-170): candidates have d_j
@@ -609,3 +694,6 @@ class GP(object):
     if getattr(self, '_post', None) is not None:
       _owners_of(self._post).add(new)
     return new
+
+
+REBIND_METHODS = _rebind_methods()

@@ -13,6 +13,7 @@ importable they are delegated to its own maximise_with_method with the device-ba
 the objective, otherwise they raise.
 """
 from argparse import Namespace
+from contextlib import contextmanager
 from copy import copy
 
 import numpy as np
@@ -81,13 +82,117 @@ def _sharded_argmax(scorer, n_rows, align=1):
   return int(gidx)
 
 
-def _fused_maximise(scorer, anc_data, bounds=None):
-  """ maximise_acquisition (:23-40) for the `rand` method: draw candidates, one device call (per rank),
-      return the arg-max point. """
+# Candidate source of the `rand` maximiser.
+#   'numpy'  (default, parity mode): np.random.random((max_evals, d)) from the GLOBAL MT19937 stream, exactly the
+#            rows the reference draws (oper_utils.py:59-67) -- every rank consumes the whole stream, in slabs, on a
+#            producer thread that overlaps with the device scoring of the previous slab; a rank uploads and keeps only
+#            the rows of its own shard.
+#   'device' (throughput mode): a counter-based Philox4x32-10 stream keyed by (seed, GLOBAL row index, coordinate)
+#            generated on the GPU (dfb_fill_candidates): no host RNG, no host->device copy, nothing proportional to
+#            max_evals on the host, and a rank generates its own shard only; the seed is two draws from the global
+#            NumPy stream, so seeded runs are reproducible and every rank agrees.  Different candidates than the
+#            reference's, same distribution.  Select per call with anc_data.candidate_rng or module-wide here.
+CANDIDATE_RNG = 'numpy'
+STREAM_SLAB_ROWS = 1 << 17
+
+
+def _maximise_streamed(score, bounds, max_evals, slab):
+  """ random_maximise (oper_utils.py:70-80) with the candidate draw pipelined against the scoring.
+      score(pts) -> (best_score, best_index_within_pts, ...).  np.random.random((M, d)) and consecutive
+      np.random.random((m_k, d)) slabs consume the MT19937 stream identically (row-major fill), so the candidates
+      -- and the state the global RNG is left in -- are the reference's. """
+  import queue
+  import threading
+  from . import dist as dfb_dist
+  M, dim = int(max_evals), len(bounds)
+  rank, world, dev = _shard_info()
+  lo_r, hi_r = dfb_dist.shard_bounds(M, rank, world) if world > 1 else (0, M)
+  starts = list(range(0, M, slab)) if M > 0 else []
+  q = queue.Queue(maxsize=2)
+
+  def _producer():
+    try:
+      for r0 in starts:
+        q.put((r0, draw_candidates(bounds, min(slab, M - r0))))
+    except BaseException as exc:  # pylint: disable=broad-except
+      q.put(exc)
+
+  if len(starts) > 1:
+    th = threading.Thread(target=_producer, daemon=True)
+    th.start()
+  else:
+    th = None
+    _producer()
+  best_s, best_i, best_pt, err = 0.0, -1, None, None
+  for _ in starts:
+    item = q.get()
+    if isinstance(item, BaseException):
+      err = item
+      break
+    if err is not None:
+      continue            # keep draining: the global RNG must end where the reference leaves it
+    r0, pts = item
+    a, b = max(lo_r, r0), min(hi_r, r0 + len(pts))
+    if b <= a:
+      continue
+    try:
+      res = score(pts[a - r0:b - r0])
+    except BaseException as exc:  # pylint: disable=broad-except
+      err = exc
+      continue
+    s, gi = float(res[0]), a + int(res[1])
+    if dfb_dist.better(s, gi, best_s, best_i):
+      best_s, best_i, best_pt = s, gi, np.array(pts[gi - r0], dtype=np.float64)
+  if th is not None:
+    th.join()
+  if err is not None:
+    raise err
+  if world > 1:
+    best_s, best_i, best_pt = dfb_dist.all_reduce_argmax_point(best_s, best_i, best_pt, dim, device=dev)
+  return best_pt
+
+
+def _maximise_device_candidates(session, bounds, max_evals):
+  """ Throughput mode of the `rand` maximiser: candidates generated on the device by global row index. """
+  from . import dist as dfb_dist
+  M = int(max_evals)
+  seed = (int(np.random.randint(0, 2 ** 31 - 1)) << 31) | int(np.random.randint(0, 2 ** 31 - 1))
+  rank, world, dev = _shard_info()
+  lo_r, hi_r = dfb_dist.shard_bounds(M, rank, world) if world > 1 else (0, M)
+  slab = session.slab_rows(2 * STREAM_SLAB_ROWS)
+  best_s, best_i, buf = 0.0, -1, None
+  for r0 in range(lo_r, hi_r, slab):
+    m = min(slab, hi_r - r0)
+    if buf is None:
+      buf = session.post.fill_candidates(seed, r0, m, bounds)
+      pts = buf
+    else:
+      pts = session.post.fill_candidates(seed, r0, m, bounds, out=buf[:m])
+    res = session.score(pts)
+    s, gi = float(res[0]), r0 + int(res[1])
+    if dfb_dist.better(s, gi, best_s, best_i):
+      best_s, best_i = s, gi
+  if world > 1:
+    best_s, best_i = dfb_dist.all_reduce_argmax(best_s, best_i, device=dev)
+  return session.post.fill_candidates(seed, int(best_i), 1, bounds).cpu().numpy()[0]
+
+
+def _fused_maximise(scorer, anc_data, bounds=None, session=None):
+  """ maximise_acquisition (:23-40) for the `rand` method: candidates scored slab by slab through fused device
+      calls (per rank), the arg-max point returned.  `session` (a context-manager factory, GP._fused_session) binds
+      hallucinations / test kernel once for all slabs; a plain `scorer(pts)` callable works too. """
   bounds = anc_data.domain.bounds if bounds is None else bounds
-  rand_pts = draw_candidates(bounds, anc_data.max_evals)
-  idx = _sharded_argmax(lambda lo, hi: scorer(rand_pts[lo:hi]), len(rand_pts))
-  return rand_pts[idx]
+  mode = getattr(anc_data, 'candidate_rng', None) or CANDIDATE_RNG
+  if session is None:
+    if mode == 'device':
+      raise NotImplementedError('device candidate generation needs a GP session')
+    return _maximise_streamed(scorer, bounds, anc_data.max_evals, STREAM_SLAB_ROWS)
+  with session() as sess:
+    if mode == 'device':
+      return _maximise_device_candidates(sess, bounds, anc_data.max_evals)
+    if mode != 'numpy':
+      raise ValueError("candidate_rng should be 'numpy' or 'device'.")
+    return _maximise_streamed(sess.score, bounds, anc_data.max_evals, sess.slab_rows(STREAM_SLAB_ROWS))
 
 
 def _reference_fortran_direct_available():
@@ -197,7 +302,7 @@ def asy_ucb(gp, anc_data):
   beta_th = _get_ucb_beta_th(_get_gp_ucb_dim(gp), anc_data.t)
   if _check_rand_euclidean(anc_data):
     acq = make_acq_desc('ucb', beta=beta_th)
-    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+    return _fused_maximise(None, anc_data, session=lambda: gp._fused_session(acq, _halluc_points(anc_data)))
   gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
   def _ucb_acq(x):
     mu, sigma = gp_eval(x)
@@ -216,7 +321,7 @@ def asy_pi(gp, anc_data):
   curr_best = anc_data.curr_max_val
   if _check_rand_euclidean(anc_data):
     acq = make_acq_desc('pi', best=curr_best)
-    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+    return _fused_maximise(None, anc_data, session=lambda: gp._fused_session(acq, _halluc_points(anc_data)))
   from scipy.stats import norm as normal_distro
   gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
   def _pi_acq(x):
@@ -233,7 +338,7 @@ def asy_ei(gp, anc_data):
   curr_best = anc_data.curr_max_val
   if _check_rand_euclidean(anc_data):
     acq = make_acq_desc('ei', best=curr_best)
-    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+    return _fused_maximise(None, anc_data, session=lambda: gp._fused_session(acq, _halluc_points(anc_data)))
   from scipy.stats import norm as normal_distro
   gp_eval = _get_gp_eval_for_parallel_strategy(gp, anc_data, 'std')
   def _ei_acq(x):
@@ -255,7 +360,7 @@ def _ttei(gp, anc_data, ref_point):
   ref_std = float(ref_std[0])
   if _check_rand_euclidean(anc_data):
     acq = make_acq_desc('ttei', ref_mean=ref_mean, ref_std=ref_std)
-    return _fused_maximise(lambda pts: gp._fused_score(acq, pts, _halluc_points(anc_data)), anc_data)
+    return _fused_maximise(None, anc_data, session=lambda: gp._fused_session(acq, _halluc_points(anc_data)))
   from scipy.stats import norm as normal_distro
   def _tt_ei_acq(x):
     mu, sigma = gp_eval(x)
@@ -310,9 +415,8 @@ def _add_ucb(gp, add_kernel, mean_funcs, anc_data):
     acq = make_acq_desc('ucb', beta=betath_j)
     anc_data_j = copy(anc_data)
     anc_data_j.domain = EuclideanDomain(domain_bounds[group_j])
-    scorer = lambda pts, _d=desc_j, _a=acq: gp._fused_score(_a, pts, [], test_desc=_d,
-                                                            mean_const=0.0)
-    point_j = _fused_maximise(scorer, anc_data_j)
+    point_j = _fused_maximise(None, anc_data_j, session=lambda _d=desc_j, _a=acq: gp._fused_session(
+        _a, [], test_desc=_d, mean_const=0.0))
     group_points.append(point_j)
     num_coordinates += len(point_j)
   anc_data.max_evals = total_max_evals
@@ -445,8 +549,38 @@ class _FidelToOptGP(object):
     return self.mfgp.draw_samples_with_hallucinated_observations(n, self._zx(x), halluc_fidel_pts,
                                                                  *args, **kwargs)
 
+  def _zx_any(self, x):
+    """ _zx for host rows or a CUDA tensor of rows (device-generated candidates). """
+    try:
+      import torch
+    except ImportError:
+      torch = None
+    if torch is not None and isinstance(x, torch.Tensor):
+      z = torch.as_tensor(self.fidel_to_opt, dtype=x.dtype, device=x.device).reshape(1, -1).expand(len(x), -1)
+      ordering = np.argsort(list(self.mfgp.fidel_coords) + list(self.mfgp.domain_coords))
+      return torch.cat((z, x), dim=1)[:, torch.as_tensor(ordering, device=x.device)].contiguous()
+    return self._zx(x)
+
   def _fused_score(self, acq, pts, halluc, **kwargs):
     return self.mfgp._fused_score(acq, self._zx(pts), halluc, **kwargs)
+
+  @contextmanager
+  def _fused_session(self, acq, halluc=None, **kwargs):
+    with self.mfgp._fused_session(acq, halluc, **kwargs) as sess:
+      yield _PrefixedSession(sess, self._zx_any)
+
+
+class _PrefixedSession(object):
+  """ A GP._fused_session whose candidate rows get the fidel_to_opt prefix before they are scored. """
+
+  def __init__(self, sess, prefix):
+    self.sess, self.prefix, self.post = sess, prefix, sess.post
+
+  def score(self, pts, want_scores=False):
+    return self.sess.score(self.prefix(pts), want_scores=want_scores)
+
+  def slab_rows(self, target):
+    return self.sess.slab_rows(target)
 
 
 def _get_fidel_to_opt_gp(mfgp, fidel_to_opt):

@@ -178,6 +178,20 @@ int dfb_build_posterior(dfb_handle* h, double noise_var, double jitter, int32_t 
 int dfb_extend_posterior(dfb_handle* h, const double* X_new_dev, int64_t q, const double* y_centred_new_dev,
                          int32_t flags, double* lml_out_host);
 int dfb_restore_posterior(dfb_handle* h);
+/* Gradients of the log marginal likelihood w.r.t. every hyper-parameter of a plain SE / Matern kernel, in one call:
+ *     1/2 tr((alpha alpha^T - K^-1) dK/dparam)          GP.compute_grad_log_marginal_likelihood, gp_core.py:229-240
+ * with dK/dparam = Kernel.gradient(param, X, X) (kernel.py:202-217 SE, 301-322 Matern) re-derived entry by entry
+ * on the device (never materialised) and K^-1 = L^-T L^-1 from one triangular DMMA product.
+ *   out_host[0]     'scale'
+ *   out_host[1]     'noise_var' WITHOUT its factor noise_var: 1/2 (alpha.alpha - tr K^-1); the reference's value is
+ *                   noise_var * out[1] (gp_core.py:232-233)
+ *   out_host[2]     'noise_mean' = sum(alpha)                                                  gp_core.py:234-235
+ *   out_host[3]     'same_dim_bandwidths'
+ *   out_host[4 + j] 'dim_bandwidths', param_num = j  (j < d)
+ * n_out >= 4 + d.  Needs a full posterior (DFB_BUILD_FULL).  Returns -3 for composite kernels (the reference raises
+ * NotImplementedError there, kernel.py:123-125).  Uses the K_* chunk buffer as scratch. */
+int dfb_lml_gradients(dfb_handle* h, double* out_host, int32_t n_out);
+
 /* max(diag K) of the last build -- the jitter ladder's scale (general_utils.py:183-189). */
 int dfb_get_max_diag(dfb_handle* h, double* out_host);
 /* Copies of gp.L (n x n lower), gp.alpha (n), gp.K_trtr_wo_noise (n x n); any may be NULL.

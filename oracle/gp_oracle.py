@@ -115,6 +115,25 @@ class OSEKernel(OKernel):
     d2 = dist_squared(X1 / bw, X2 / bw)
     return self.hyperparams['scale'] * np.exp(-d2 / 2)
 
+  def gradient(self, param, X1, X2=None, param_num=None):
+    """ dK/d(param), kernel.py:116-121, 202-217.  The reference indexes the bandwidth vector as
+        hyperparams['dim_bandwidths'][0, j], which only works when the kernel was given its bandwidths as a
+        (d, 1) column (set_dim_bandwidths transposes it to (1, d)); that is the configuration the goldens of
+        tests/golden/make_golden_grad.py pin.  Here bw[j] is the same number. """
+    X2 = X1 if X2 is None else X2
+    if len(X1) == 0 or len(X2) == 0:
+      return np.zeros((len(X1), len(X2)))
+    X1 = np.asarray(X1, dtype=np.float64); X2 = np.asarray(X2, dtype=np.float64)
+    bw = self.hyperparams['dim_bandwidths']
+    s1, s2 = X1 / bw, X2 / bw
+    d2 = dist_squared(s1, s2)
+    if param == 'scale':
+      return self.hyperparams['scale'] * np.exp(-d2 / 2)
+    if param == 'same_dim_bandwidths':
+      return self.hyperparams['scale'] * np.multiply(d2 / bw[0], np.exp(-d2 / 2))
+    dim_sq = dist_squared(s1[:, [param_num]], s2[:, [param_num]]) / bw[param_num]
+    return self.hyperparams['scale'] * np.multiply(dim_sq, np.exp(-d2 / 2))
+
 
 def matern_constants(nu):
   """ The scalar constants of the half-integer Matern kernel exactly as the reference forms them
@@ -161,6 +180,41 @@ class OMaternKernel(OKernel):
     bw = self.hyperparams['dim_bandwidths']
     dist = np.sqrt(dist_squared(X1 / bw, X2 / bw))
     return self.hyperparams['scale'] * self.norm_constant * self._unnormalised(dist)
+
+  def _grad_unnormalised(self, dist, dist_dv):
+    """ kernel.py:272-290 """
+    c = self.consts
+    u = np.zeros(dist.shape)
+    u_dv = np.zeros(dist_dv.shape)
+    for i in range(self.p + 1):
+      mult = c['s8'] * dist
+      u += c['coeffs'][i] * mult ** (self.p - i)
+      if self.p - i > 0:
+        u_dv += c['s8'] * (self.p - i) * c['coeffs'][i] * (mult ** (self.p - i - 1)) * dist_dv
+    u_dv *= (c['gamma_ratio'] * np.exp(-c['s2'] * dist))
+    u *= (c['gamma_ratio'] * np.exp(-c['s2'] * dist) * (-c['s2'] * dist_dv))
+    return u + u_dv
+
+  def gradient(self, param, X1, X2=None, param_num=None):
+    """ dK/d(param), kernel.py:116-121, 301-322 (see OSEKernel.gradient for the bandwidth indexing). """
+    X2 = X1 if X2 is None else X2
+    if len(X1) == 0 or len(X2) == 0:
+      return np.zeros((len(X1), len(X2)))
+    X1 = np.asarray(X1, dtype=np.float64); X2 = np.asarray(X2, dtype=np.float64)
+    bw = self.hyperparams['dim_bandwidths']
+    s1, s2 = X1 / bw, X2 / bw
+    dist = np.sqrt(dist_squared(s1, s2))
+    sc = self.hyperparams['scale'] * self.norm_constant
+    if param == 'scale':
+      return sc * self._unnormalised(dist)
+    if param == 'same_dim_bandwidths':
+      return sc * self._grad_unnormalised(dist, -(dist / bw[0]))
+    np.fill_diagonal(dist, 1.0)
+    dist_dv = 1 / dist
+    np.fill_diagonal(dist, 0.0)
+    dim_sq = dist_squared(s1[:, [param_num]], s2[:, [param_num]])
+    dist_dv *= -(dim_sq / bw[param_num])
+    return sc * self._grad_unnormalised(dist, dist_dv)
 
 
 class OAdditiveKernel(OKernel):
@@ -261,6 +315,18 @@ class OGP(object):
     Yc = np.asarray(self.Y) - self.mean_func(self.X)
     return (-0.5 * Yc.T.dot(self.alpha) - np.log(np.diag(self.L)).sum()
             - 0.5 * self.num_tr_data * np.log(2 * np.pi))
+
+  def compute_grad_log_marginal_likelihood(self, param, *args):    # gp_core.py:229-240
+    alpha = np.expand_dims(self.alpha, axis=0)
+    if param == 'noise_var':
+      grad_m = self.noise_var * np.identity(len(self.X))
+    elif param == 'noise_mean':
+      return np.matmul(alpha, np.ones((len(self.Y), 1))).item()
+    else:
+      grad_m = self.kernel.gradient(param, self.X, self.X, *args)
+    grad_m = np.matmul(alpha.T, np.matmul(alpha, grad_m)) - \
+             solve_upper_triangular(self.L.T, solve_lower_triangular(self.L, grad_m))
+    return 0.5 * np.trace(grad_m)
 
   def eval(self, X_test, uncert_form='none'):             # gp_core.py:165-190
     """ NOTE: like the reference this materialises K(X_test, X_test) and V^T V in full. """

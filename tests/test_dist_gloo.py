@@ -124,14 +124,16 @@ def _acq_worker(rank, world, port, out_dir):
     return vals[i], i, None
   anc = Namespace(domain=EuclideanDomain([[0, 1], [-1, 2]]), max_evals=1001)
   np.random.seed(3)
+  A.STREAM_SLAB_ROWS = 300          # four streamed slabs, the shard boundary (row 500) inside the second one
   pt = A._fused_maximise(scorer, anc)
+  after = np.random.random()        # the global stream must be where one np.random.random((1001, 2)) leaves it
   # a sample vector with this rank's blocks filled in and the others at -inf (asy_ts)
   full = np.random.RandomState(5).standard_normal(10000)
   blk = 4096
   lo, hi = [(0, 8192), (8192, 10000)][rank] if world == 2 else (0, 10000)
   mine = np.full(10000, -np.inf); mine[lo:hi] = full[lo:hi]
   ts_idx = A._argmax_of_sharded_sample(mine)
-  np.save(os.path.join(out_dir, 'acq_%d.npy' % rank), np.concatenate((pt, [calls[0], ts_idx])))
+  np.save(os.path.join(out_dir, 'acq_%d.npy' % rank), np.concatenate((pt, [sum(calls), ts_idx, after])))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -151,12 +153,17 @@ def test_two_rank_fused_maximise_equals_single_process(tmp_path):
     vals = np.sin(7.0 * pts[:, 0]) + pts[:, 1] ** 2
     i = int(np.argmax(vals))
     return vals[i], i, None
-  want = A._fused_maximise(scorer, anc)               # not distributed here: scores all 1001 rows
+  want = A._fused_maximise(scorer, anc)               # not distributed here: scores all 1001 rows, one slab
+  want_after = np.random.random()
+  np.random.seed(3)
+  pts = A.draw_candidates(anc.domain.bounds, 1001)    # the reference's single draw (oper_utils.py:59-67)
+  assert (want == pts[int(np.argmax(np.sin(7.0 * pts[:, 0]) + pts[:, 1] ** 2))]).all()
   want_ts = int(np.argmax(np.random.RandomState(5).standard_normal(10000)))
   sizes = []
   for r in range(2):
     got = np.load(os.path.join(str(tmp_path), 'acq_%d.npy' % r))
     assert (got[:2] == want).all()
     assert int(got[3]) == want_ts
+    assert got[4] == want_after
     sizes.append(int(got[2]))
   assert sorted(sizes) == [500, 501]                  # each rank scored only its shard

@@ -656,6 +656,7 @@ def test_auto_mode_with_group_test_kernel_and_mf(B):
   rs = np.random.RandomState(11)
   n, d = 1100, 10
   X = rs.random_sample((n, d)); Y = synth_data.tiled(synth_data.park1, 4, X)
+  Y = Y / Y.std()       # unit scale: the int8 screen's ABSOLUTE 5e-9 guard (api.cu: I8_BOUND_LIMIT) admits the path
   groups = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
   sub = [B.kernel.MaternKernel(4, 2.5, 1.0, 0.5), B.kernel.SEKernel(4, 1.0, 0.5), B.kernel.MaternKernel(2, 1.5, 1.0, 0.4)]
   kern = B.kernel.AdditiveKernel(float(Y.var()) / 3, sub, groups)

@@ -31,11 +31,18 @@ def run_all(counts=None):
   gp = gp_core.GP(X, Y, kernel.MaternKernel(6, 2.5, k['scale'], k['dim_bandwidths']),
                   gp_core.ConstantMean(w['mean_const']), w['noise_var'])
   if counts is not None:
-    orig = gp._fused_score
-    def counting(acq, pts, *a, **kw):
-      counts.append(len(pts))
-      return orig(acq, pts, *a, **kw)
-    gp._fused_score = counting
+    from contextlib import contextmanager
+    orig = gp._fused_session
+    @contextmanager
+    def counting(*a, **kw):
+      with orig(*a, **kw) as sess:
+        inner = sess.score
+        def score(pts, **k2):
+          counts.append(len(pts))
+          return inner(pts, **k2)
+        sess.score = score
+        yield sess
+    gp._fused_session = counting
   dom = domains.EuclideanDomain([[0, 1]] * 6)
 
   def anc(name, max_evals, in_progress=()):

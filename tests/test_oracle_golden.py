@@ -347,3 +347,21 @@ def test_stable_cholesky_and_gaussian_draws_like_the_reference_tests():
   sample_covar = centred.T.dot(centred) / num_samples
   assert np.linalg.norm(mu - sample_mean) < 4 * np.linalg.norm(mu) / np.sqrt(num_samples)
   assert np.linalg.norm(K - sample_covar) < 4 * np.linalg.norm(K) / np.sqrt(num_samples)
+
+
+# ---- LML gradients: the oracle's restatement against the unmodified reference ------------
+@pytest.mark.parametrize('name', ['se3', 'm25_6', 'm15_2', 'm05_4'])
+def test_lml_gradients_match_reference(name):
+  """ gp_core.py:229-240 + kernel.py:202-217, 301-322; goldens: tests/golden/make_golden_grad.py. """
+  g = load_golden('grad')
+  X, Y, bw = g[name + '_X'], g[name + '_Y'], g[name + '_bw']
+  scale, nv, mc, nu = [float(v) for v in g[name + '_meta']]
+  d = X.shape[1]
+  kern = O.OSEKernel(d, scale, bw) if nu < 0 else O.OMaternKernel(d, nu, scale, bw)
+  gp = O.OGP(X, Y, kern, lambda x: np.array([mc] * len(x)), nv)
+  params = [('scale', ()), ('noise_var', ()), ('noise_mean', ()), ('same_dim_bandwidths', ())] + \
+           [('dim_bandwidths', (j,)) for j in range(d)]
+  got = np.array([gp.compute_grad_log_marginal_likelihood(p, *a) for p, a in params])
+  np.testing.assert_allclose(got, g[name + '_grads'], rtol=1e-10)
+  np.testing.assert_allclose(kern.gradient('same_dim_bandwidths', X[:8], X), g[name + '_G_same'], rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(kern.gradient('dim_bandwidths', X, X, 1)[:8], g[name + '_G_dim1'], rtol=1e-12, atol=1e-14)
