@@ -59,6 +59,11 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   // three pair-interleaved digit planes (2 bytes per entry each) + one compact plane of the leading digit
   int8_t* Wi8 = c.take<int8_t>((size_t)7 * npad * npad);
   int8_t* Ki8 = c.take<int8_t>((size_t)7 * chunk * npad);
+  int8_t* Ki8b = c.take<int8_t>((size_t)7 * chunk * npad);
+  double* mu_b = c.take<double>((size_t)chunk);
+  double* kssv_b = c.take<double>((size_t)chunk);
+  double* cprep = c.take<double>((size_t)chunk * 10);
+  double* mu_part = c.take<double>((size_t)(npad / 64 + 2) * chunk);      // per 64-point block partial sums of mu
   double* rowscale = c.take<double>((size_t)npad);
   double* rowinv = c.take<double>((size_t)npad);
   int64_t* list_idx = c.take<int64_t>((size_t)SHORTLIST_CAP);
@@ -88,6 +93,7 @@ static size_t carve(dfb_handle* h, char* base, int64_t n_max, int64_t chunk) {
   double* ext_save = c.take<double>((size_t)(2 * TILE + 1) * npad + TILE);
   if (h != nullptr && base != nullptr) {
     h->ext_save = ext_save;
+    h->Ki8b = Ki8b; h->mu_b = mu_b; h->kssv_b = kssv_b; h->cprep = cprep; h->mu_part = mu_part;
     h->T = T; h->W = W; h->Dinv = Dinv; h->X = X; h->yc = yc; h->alpha = alpha;
     h->tr.xs = tr_xs; h->tr.nrm = tr_nrm; h->te.xs = te_xs; h->te.nrm = te_nrm;
     h->Ks = Ks; h->Wi8 = Wi8; h->Ki8 = Ki8; h->rowscale = rowscale; h->rowinv = rowinv; h->list_idx = list_idx; h->list_X = list_X; h->list_count = list_count; h->list_s8 = list_s8; h->list_err = list_err; h->blk_lb = blk_lb; h->best_lb = best_lb; h->partial = partial; h->mu = mu; h->sd = sd; h->score = score; h->kssv = kssv; h->stage = stage;
@@ -369,6 +375,9 @@ static int prepare_i8(dfb_handle* h) {
     // compact plane of the leading digit (row-major rows of npad bytes, SWIZZLE_128B boxes of 128 k-values)
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW1c, h->Wi8 + 6 * npad * npad, npad, npad, 1, npad, npad * npad, 128, 128, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK1c, h->Ki8 + 6 * h->chunk * npad, npad, h->chunk, 1, npad, h->chunk * npad, 128, 64, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK2h_b, h->Ki8b, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 1));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK3h_b, h->Ki8b, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 64, 3));
+    DFB_TRY(make_tensor_map_3d_u8(&h->tmK1c_b, h->Ki8b + 6 * h->chunk * npad, npad, h->chunk, 1, npad, h->chunk * npad, 128, 64, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW2, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 1));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmW3, h->Wi8, 2 * npad, npad, 3, 2 * npad, 2 * npad * npad, 64, 128, 3));
     DFB_TRY(make_tensor_map_3d_u8(&h->tmK2, h->Ki8, 2 * npad, h->chunk, 3, 2 * npad, 2 * h->chunk * npad, 64, 128, 1));
@@ -501,6 +510,29 @@ static ChunkMode chunk_mode(bool want_std, bool do_argmax, bool use_i8, const in
 }
 constexpr int64_t SMALL_EVAL_M = 16;
 
+static int ensure_ks_stream(dfb_handle* h) {
+  if (h->ks_stream != nullptr) return 0;
+  int lo = 0, hi = 0;
+  DFB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority: the contraction's CTAs go first
+  DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->ks_stream, cudaStreamNonBlocking, lo));
+  DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->gs_stream, cudaStreamNonBlocking, hi));
+  DFB_CUDA_OK(cudaEventCreateWithFlags(&h->ks_fork, cudaEventDisableTiming));
+  DFB_CUDA_OK(cudaEventCreateWithFlags(&h->ks_join, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    DFB_CUDA_OK(cudaEventCreateWithFlags(&h->ks_k[i], cudaEventDisableTiming));
+    DFB_CUDA_OK(cudaEventCreateWithFlags(&h->ks_g[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+// Per chunk two stages:
+//   K: (host candidates: staging copy) K_* rows / digit planes + mu + k(x*,x*)      fp64 pipe
+//   G: the contraction |L^-1 k_*|^2 -> sd / acquisition / arg-max / shortlist       tensor pipe (int8) or DMMA
+// With the CTA-pair int8 contraction the stages of consecutive chunks are software-pipelined over two streams: K(c+1)
+// runs on h->ks_stream into the second digit buffer while G(c) runs on the caller's stream (the lean K_* kernel
+// co-resides with the persistent tcgen05 kernel: 88 registers x 128 threads and < 1 KB of shared memory per CTA).
+// Events carry the two dependencies per buffer: K(c) -> G(c) and G(c) -> K(c+2).  Everything else is unchanged: the
+// arithmetic per chunk, the order of the arg-max folds (G stages stay in stream order) and therefore every result.
 static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, int64_t m, int32_t dc,
                       int32_t space, double mean_const, ChunkOut out, const ChunkMode& md) {
   const bool want_std = md.want_std, do_argmax = md.do_argmax;
@@ -517,40 +549,88 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
   const int64_t npad = h->npad, Mc = h->chunk;
   const int nb = (int)(npad / TILE);
   if (do_argmax) DFB_TRY(launch_reset_best(h));
+  const bool i8 = want_std && md.use_i8;
+  const bool seg_ok = i8 && h->i8_fuse && h->kstar_fast && h->kstar_seg && h->i8_impl == 2 && h->i8_radix256;
+  const bool pipelined = i8 && h->i8_impl == 2 && h->kstar_overlap && m > Mc;
+  StreamSwap guard(h);
+  cudaStream_t s_user = guard.user, s_k = s_user, s_g = s_user;
+  if (pipelined) {
+    DFB_TRY(ensure_ks_stream(h));
+    s_k = h->ks_stream;
+    s_g = h->gs_stream;
+    DFB_CUDA_OK(cudaEventRecord(h->ks_fork, s_user));
+    DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->ks_fork, 0));
+    DFB_CUDA_OK(cudaStreamWaitEvent(s_g, h->ks_fork, 0));
+  }
   // host candidates are staged in batches of as many whole chunks as the staging buffer holds
   // (chunk x DFB_MAX_SLOTS doubles), so a 6-column candidate matrix needs 1 copy per ~21 chunks
   const int64_t stage_rows = (Mc * DFB_MAX_SLOTS / dc) / Mc * Mc;
   int64_t staged_lo = 0, staged_hi = 0;
-  for (int64_t c0 = 0; c0 < m; c0 += Mc) {
+  const int64_t n_chunks = (m + Mc - 1) / Mc;
+  const double* xc_of[2] = {nullptr, nullptr};
+
+  auto stage_k = [&](int64_t ci) -> int {
+    const int b = pipelined ? (int)(ci & 1) : 0;
+    const int64_t c0 = ci * Mc;
     const int64_t mc = (m - c0 < Mc) ? (m - c0) : Mc;
     const int64_t m_rows = round_up(mc, TILE);
+    h->stream = s_k;
+    if (pipelined && ci >= 2) DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->ks_g[b], 0));     // G(ci-2) is done with buffer b
     const double* xc_dev;
     if (space == DFB_HOST) {
       if (c0 >= staged_hi) {
+        // the shortlist collection of earlier chunks reads the staged rows: wait for the latest G stage
+        if (pipelined && ci >= 1) DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->ks_g[(ci - 1) & 1], 0));
         staged_lo = c0;
         staged_hi = (m - c0 < stage_rows) ? m : c0 + stage_rows;
         DFB_CUDA_OK(cudaMemcpyAsync(h->stage, Xc + staged_lo * dc, sizeof(double) * (staged_hi - staged_lo) * dc,
-                                    cudaMemcpyHostToDevice, h->stream));
+                                    cudaMemcpyHostToDevice, s_k));
       }
       xc_dev = h->stage + (c0 - staged_lo) * dc;
     } else {
       xc_dev = Xc + c0 * dc;
     }
-    double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : h->mu;
+    xc_of[b] = xc_dev;
+    double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : (b ? h->mu_b : h->mu);
+    double* kss_dev = b ? h->kssv_b : h->kssv;
+    int8_t* planes = b ? h->Ki8b : h->Ki8;
+    const int* abort_count = md.collect ? h->list_count : nullptr;
+    DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
+    int fused_digits = 0;
+    if (seg_ok)
+      DFB_TRY(launch_kstar_seg(h, d_desc, desc, ss.xs, ss.nrm, npad, h->alpha, h->n, xc_dev, mc, dc, m_rows, npad, mean_const,
+                               mu_dev, kss_dev, planes, 2 * h->chunk * npad, 2 * npad, 1.0 / i8_colscale(desc), h->cprep,
+                               h->mu_part, Mc, &fused_digits, abort_count));
+    if (!fused_digits && i8 && h->i8_fuse)
+      DFB_TRY(launch_kstar_i8(h, d_desc, desc, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows, h->n, npad,
+                              mean_const, mu_dev, kss_dev, planes, 2 * h->chunk * npad, 2 * npad,
+                              1.0 / i8_colscale(desc), &fused_digits, abort_count));
+    if (!fused_digits) {
+      DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
+                           h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? kss_dev : nullptr));
+      if (i8)     // K_* = 2^F * digits: |K_*| <= k(x,x) for every supported (stationary, non-negative) kernel
+        DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / i8_colscale(desc), planes,
+                                2 * h->chunk * npad, 2 * npad));
+    }
+    DFB_TRY(prof_end(h, DFB_PROF_KSTAR, (double)mc));
+    if (pipelined) DFB_CUDA_OK(cudaEventRecord(h->ks_k[b], s_k));
+    return 0;
+  };
+
+  auto stage_g = [&](int64_t ci) -> int {
+    const int b = pipelined ? (int)(ci & 1) : 0;
+    const int64_t c0 = ci * Mc;
+    const int64_t mc = (m - c0 < Mc) ? (m - c0) : Mc;
+    const int64_t m_rows = round_up(mc, TILE);
+    h->stream = s_g;
+    if (pipelined) DFB_CUDA_OK(cudaStreamWaitEvent(s_g, h->ks_k[b], 0));
+    const double* xc_dev = xc_of[b];
+    double* mu_dev = (space == DFB_DEVICE && out.mu) ? out.mu + c0 : (b ? h->mu_b : h->mu);
+    double* kss_dev = b ? h->kssv_b : h->kssv;
     double* sd_dev = (space == DFB_DEVICE && out.sd) ? out.sd + c0 : h->sd;
     double* sc_dev = (space == DFB_DEVICE && out.score) ? out.score + c0
                                                          : ((out.score || md.collect || md.keep_scores) ? h->score : nullptr);
     const int* abort_count = md.collect ? h->list_count : nullptr;
-    DFB_TRY(prof_begin(h, DFB_PROF_KSTAR));
-    int fused_digits = 0;
-    if (want_std && md.use_i8 && h->i8_fuse)
-      DFB_TRY(launch_kstar_i8(h, d_desc, desc, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows, h->n, npad,
-                              mean_const, mu_dev, h->kssv, h->Ki8, 2 * h->chunk * npad, 2 * npad,
-                              1.0 / i8_colscale(desc), &fused_digits, abort_count));
-    if (!fused_digits)
-      DFB_TRY(launch_kstar(h, d_desc, desc, 0, ss.xs, ss.nrm, npad, h->alpha, xc_dev, mc, dc, m_rows,
-                           h->Ks, npad, h->n, npad, mean_const, mu_dev, want_std ? h->kssv : nullptr));
-    DFB_TRY(prof_end(h, DFB_PROF_KSTAR, (double)mc));
     int small_warps = 0;
     const bool small = want_std && md.allow_small && !md.use_i8 && m <= SMALL_EVAL_M &&
                        (int64_t)((h->n + 7) / 8 * 8) * SMALL_EVAL_M <= (int64_t)nb * Mc;
@@ -567,13 +647,10 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
       g.partial = h->partial; g.ld_partial = Mc;
       DFB_TRY(prof_begin(h, DFB_PROF_GEMM));
       if (md.use_i8) {
-        // K_* = 2^F * digits: |K_*| <= k(x,x) for every supported (stationary, non-negative) kernel
         const double colscale = i8_colscale(desc);
-        if (!fused_digits)
-          DFB_TRY(launch_slice_i8(h, h->Ks, npad, m_rows, npad, nullptr, 1.0 / colscale, h->Ki8,
-                                  2 * h->chunk * npad, 2 * npad));
         if (h->i8_impl == 2)
-          DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmW1c, h->tmK2h, h->tmK3h, h->tmK1c, nb, (int)(m_rows / TILE), (int)npad,
+          DFB_TRY(launch_score_i8c2_args(h, h->tmW2, h->tmW3, h->tmW1c, b ? h->tmK2h_b : h->tmK2h, b ? h->tmK3h_b : h->tmK3h,
+                                         b ? h->tmK1c_b : h->tmK1c, nb, (int)(m_rows / TILE), (int)npad,
                                          h->partial, Mc, h->rowscale, colscale, abort_count));
         else if (h->i8_impl == 1)
           DFB_TRY(launch_score_i8x2_args(h, h->tmW2, h->tmW3, h->tmK2, h->tmK3, nb, (int)(m_rows / TILE), (int)npad,
@@ -593,7 +670,7 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     }
     if (want_std || do_argmax || sc_dev != nullptr) {
       DFB_TRY(prof_begin(h, DFB_PROF_ACQ));
-      DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, small ? SMALL_EVAL_M : Mc, small ? small_warps : nb, h->kssv, mc, c0,
+      DFB_TRY(launch_acq(h, acq, mu_dev, h->partial, small ? SMALL_EVAL_M : Mc, small ? small_warps : nb, kss_dev, mc, c0,
                          want_std ? 1 : 0, want_std ? sd_dev : nullptr, sc_dev, do_argmax, md.idx_map,
                          md.collect ? &md.em : nullptr));
       if (md.collect)
@@ -602,12 +679,32 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     }
     if (space == DFB_HOST) {
       if (out.mu)
-        DFB_CUDA_OK(cudaMemcpyAsync(out.mu + c0, mu_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+        DFB_CUDA_OK(cudaMemcpyAsync(out.mu + c0, mu_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, s_g));
       if (out.sd && want_std)
-        DFB_CUDA_OK(cudaMemcpyAsync(out.sd + c0, sd_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+        DFB_CUDA_OK(cudaMemcpyAsync(out.sd + c0, sd_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, s_g));
       if (out.score)
-        DFB_CUDA_OK(cudaMemcpyAsync(out.score + c0, sc_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, h->stream));
+        DFB_CUDA_OK(cudaMemcpyAsync(out.score + c0, sc_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, s_g));
     }
+    if (pipelined) DFB_CUDA_OK(cudaEventRecord(h->ks_g[b], s_g));
+    return 0;
+  };
+
+  if (!pipelined) {
+    for (int64_t ci = 0; ci < n_chunks; ci++) {
+      DFB_TRY(stage_k(ci));
+      DFB_TRY(stage_g(ci));
+    }
+  } else {
+    // issue order: the contraction of chunk c is enqueued BEFORE the K_* of chunk c+1, so that the block scheduler
+    // places the persistent kernel's CTAs first and the K_* CTAs fill the registers / shared memory left over
+    DFB_TRY(stage_k(0));
+    for (int64_t ci = 0; ci < n_chunks; ci++) {
+      DFB_TRY(stage_g(ci));
+      if (ci + 1 < n_chunks) DFB_TRY(stage_k(ci + 1));
+    }
+    DFB_CUDA_OK(cudaEventRecord(h->ks_join, s_g));          // every K stage precedes a G stage: joining G joins both
+    DFB_CUDA_OK(cudaStreamWaitEvent(s_user, h->ks_join, 0));
+    h->last_overlapped = n_chunks;
   }
   return 0;
 }
@@ -659,6 +756,10 @@ void dfb_destroy(dfb_handle* h) {
     cudaStreamDestroy(h->fs_hi); cudaStreamDestroy(h->fs_lo);
     cudaEventDestroy(h->fe_fork); cudaEventDestroy(h->fe_panel); cudaEventDestroy(h->fe_rest);
     cudaEventDestroy(h->fe_join_hi); cudaEventDestroy(h->fe_join_lo);
+  }
+  if (h->ks_stream != nullptr) {
+    cudaStreamDestroy(h->ks_stream); cudaStreamDestroy(h->gs_stream); cudaEventDestroy(h->ks_fork); cudaEventDestroy(h->ks_join);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ks_k[i]); cudaEventDestroy(h->ks_g[i]); }
   }
   if (h->prof != nullptr) {
     for (int c = 0; c < PROF_CLASSES; c++)
@@ -1201,6 +1302,8 @@ int dfb_ts_argmax(dfb_handle* h, const double* samples_dev, int64_t ld, int32_t 
 
 int64_t dfb_launch_count(dfb_handle* h) { return h ? h->launches : 0; }
 
+int dfb_debug_trace(void* buf_dev, int64_t cap_records) { return debug_set_trace(buf_dev, (long long)cap_records); }
+
 int dfb_query(dfb_handle* h, const char* name, double* out) {
   DFB_TRY(need(h, false, false, false, false, false));
   if (name == nullptr || out == nullptr) { set_error("bad query arguments"); return -1; }
@@ -1211,6 +1314,7 @@ int dfb_query(dfb_handle* h, const char* name, double* out) {
   if (strcmp(name, "last_selfcheck_violations") == 0) { *out = (double)h->last_selfcheck_violations; return 0; }
   if (strcmp(name, "last_selfcheck_ratio") == 0) { *out = h->last_selfcheck_ratio; return 0; }
   if (strcmp(name, "chunk") == 0) { *out = (double)h->chunk; return 0; }
+  if (strcmp(name, "last_overlapped") == 0) { *out = (double)h->last_overlapped; return 0; }     // chunks of the last PIPELINED pass
   if (strcmp(name, "i8_bound_limit") == 0) { *out = I8_BOUND_LIMIT; return 0; }
   if (strcmp(name, "score_impl") == 0) { *out = (double)h->score_impl; return 0; }
   if (strcmp(name, "i8_ready") == 0) { *out = h->i8_ready ? 1.0 : 0.0; return 0; }
@@ -1240,6 +1344,8 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "small_eval") == 0) { h->small_eval = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
+  if (strcmp(name, "kstar_seg") == 0) { h->kstar_seg = value ? 1 : 0; return 0; }
+  if (strcmp(name, "kstar_overlap") == 0) { h->kstar_overlap = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_unguarded") == 0) { h->i8_unguarded = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {
     if (value < 0 || value > 2) { set_error("i8_impl must be 0 (N=64, one pass), 1 (N=128, two passes) or 2 (CTA pairs)"); return -1; }

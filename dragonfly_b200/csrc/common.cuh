@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include "../../include/dfb200.h"
 
@@ -135,9 +136,24 @@ struct dfb_handle {
   bool i8_ready = false;
   int i8_unguarded = 0;       // diagnostics: use the int8 path even when its a-priori bound exceeds the limit (the error sweep)
   int i8_fuse = 1;            // K_* kernel emits the digit planes itself (no fp64 K_* round trip)
+  int kstar_seg = 1;          // second-generation digit kernel (kstar_seg_kernel) where it applies
+  int kstar_overlap = 0;      // option: chunk c+1's K_* on a second stream while chunk c is contracted (api.cu: run_chunks)
   int i8_ts = 0;              // 1 = A digits staged in tensor memory (tcgen05.cp + TS-form MMA)
   int8_t* Wi8 = nullptr;      // [6][npad][npad]
   int8_t* Ki8 = nullptr;      // [6][chunk][npad]
+  // K_* / contraction overlap (api.cu: run_chunks): second buffer of everything the K_* stage hands to the
+  // contraction stage, the scratch of the second-generation K_* kernel, the second stream and its events
+  int8_t* Ki8b = nullptr;
+  double* mu_b = nullptr;
+  double* kssv_b = nullptr;
+  double* cprep = nullptr;    // chunk x 10 scaled candidate rows (cand_prep_kernel)
+  double* mu_part = nullptr;  // (npad / 64 + 2) x chunk
+  cudaStream_t ks_stream = nullptr;   // K stage (least priority)
+  cudaStream_t gs_stream = nullptr;   // G stage (greatest priority: the persistent kernel's CTAs are placed first)
+  cudaEvent_t ks_join = nullptr;
+  cudaEvent_t ks_fork = nullptr, ks_k[2] = {nullptr, nullptr}, ks_g[2] = {nullptr, nullptr};
+  CUtensorMap tmK2h_b, tmK3h_b, tmK1c_b;   // maps of the second digit buffer
+  int64_t last_overlapped = 0;             // diagnostics: chunks of the last call that went through the two-stream pipeline
   double* rowscale = nullptr; // npad  2^E_i
   double* rowinv = nullptr;   // npad  2^-E_i
   CUtensorMap tmWi8, tmKi8;

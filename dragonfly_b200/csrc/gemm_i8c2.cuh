@@ -43,7 +43,18 @@ constexpr int C2_B_SUB = (X2_BN / 2) * 2 * X2_BK;       // 4096 B:  64 rows x 64
 constexpr int C2_STAGE_BYTES = 3 * C2_A_SUB + 3 * C2_B_SUB;          // 36864 per CTA
 constexpr int C2_PB_A_BYTES = X2_BM * 128;              // pass B, radix 256: 128 rows x 128 k-values of the leading digit
 constexpr int C2_PB_BYTES = C2_PB_A_BYTES + (X2_BN / 2) * 128;       // + 64 candidate rows: 24576 per CTA
-constexpr int C2_THREADS = 320;
+// Warp roles: 0..7 epilogue (two per TMEM lane quarter), 8 TMA producer, 9 MMA issuer (+ TMEM allocation), 10..11 idle.
+// Register budget: the kernel is LAUNCHED with C2_LAUNCH_REGS = 136 registers per thread (52224 per CTA, 13056 per SM
+// sub-partition: the register file is partitioned 4 x 16384 and warp w lives on partition w % 4).  Right after
+// set-up the light warpgroup (8..11) drops to C2_LIGHT_REGS = 56 (setmaxnreg.dec: 10240 registers into the CTA's
+// pool) and the two epilogue warpgroups rise to C2_EPI_REGS = 168 (setmaxnreg.inc: 8192 out of it) -- deallocated
+// registers only ever return to the CTA's own pool, so what a co-resident kernel can use is fixed by the launch
+// count: 16384 - 13056 = 3328 registers per partition, room for one 88-register warp of the K_* kernel
+// (kernels.cu: kstar_seg_kernel, four warps per CTA, one per partition).
+constexpr int C2_THREADS = 384;
+constexpr int C2_LAUNCH_REGS = 136;
+constexpr int C2_LIGHT_REGS = 56;
+constexpr int C2_EPI_REGS = 168;
 constexpr size_t C2_SMEM_BYTES = (size_t)C2_STAGES * C2_STAGE_BYTES + 1024 + 2 * 4 * X2_BN * sizeof(double) +
                                  (2 * C2_STAGES + 4) * 8 + 64;
 // M=256 (pair), N=128, A/B = signed int8 K-major, D = int32
@@ -54,6 +65,24 @@ __device__ __forceinline__ unsigned c2_cta_rank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+// Waiting without occupying issue slots: mbarrier.try_wait with a suspend-time hint parks the warp in hardware until the
+// phase completes (or the hint expires) instead of returning after the short default limit.  The per-CTA trace
+// (tools/trace_overlap.py) showed the co-resident K_* warps running at a sixth of their stand-alone rate while this
+// kernel's five or six waiting warps per CTA polled with the default limit.
+__device__ __forceinline__ void c2_wait(void* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000000u)
+        : "memory");
+  } while (!ok);
 }
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
@@ -126,7 +155,7 @@ __device__ __forceinline__ bool c2_tile(const ScoreI8Args& g, int j, int& rp, in
 }
 
 template <bool R256>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(C2_LAUNCH_REGS)
 score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA3,
                   const __grid_constant__ CUtensorMap tmA1c, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmB1c,
@@ -146,6 +175,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = c2_cta_rank();
+  const unsigned long long t_begin = (tid == 0 && g_trace != nullptr) ? trace_now() : 0ull;
 
   if (tid == 0) {
     for (int s = 0; s < C2_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -155,7 +185,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     mbar_init(epi_bar, 16);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(512)
@@ -168,7 +198,11 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const unsigned tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  // the light warpgroup: nothing below this point of the branch may need more than C2_LIGHT_REGS registers (the
+  // epilogue sits on the other side of the branch so that ptxas does not apply the cap to it)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C2_LIGHT_REGS));
+  if (warp == 8) {
     // ---------------- TMA producer (both CTAs): own A tile + own half of B --------------------------------
     if (lane == 0) {
       unsigned git = 0;
@@ -179,7 +213,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int n_it = nk + c2_pass_b_stages<R256>(nk);
         for (int it = 0; it < n_it; it++, git++) {
           const unsigned s = git % C2_STAGES, n = git / C2_STAGES;
-          mbar_wait(&empty_bar[s], (n & 1u) ^ 1u);
+          c2_wait(&empty_bar[s], (n & 1u) ^ 1u);
           unsigned char* dst = tiles + (size_t)s * C2_STAGE_BYTES;
           if (R256 && it >= nk) {
             // pass B, radix 256: 128 k-values of the compact leading-digit planes (A 16 KB, B half 8 KB)
@@ -203,7 +237,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ---------------- MMA issuer: leader CTA only, for the pair -----------------------------------------
     // The whole warp walks the loops in uniform control flow and ONE elected lane issues: descriptors,
     // stage indices and barrier addresses then live in uniform registers, which is what UTCIMMA / UTCBAR
@@ -222,7 +256,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const unsigned tpar = (unsigned)(j & 1);
         if (j > 0) {
           if (timed) t0 = clock64();
-          mbar_wait(epi_bar, tpar ^ 1u);
+          c2_wait(epi_bar, tpar ^ 1u);
           if (timed) t_epi += clock64() - t0;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         }
@@ -231,12 +265,12 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           const bool pb = it >= nk;
           if (it == nk) {
             if (timed) t0 = clock64();
-            mbar_wait(drain_bar, tpar);
+            c2_wait(drain_bar, tpar);
             if (timed) t_drain += clock64() - t0;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           }
           if (timed) t0 = clock64();
-          mbar_wait(&full_bar[s], n & 1u);
+          c2_wait(&full_bar[s], n & 1u);
           if (timed) t_full += clock64() - t0;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const unsigned a0 = smem_u32(tiles + (size_t)s * C2_STAGE_BYTES);
@@ -317,14 +351,16 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         o[3] = (unsigned long long)(clock64() - t_start);
       }
     }
+  }
   } else {
-    // ---------------- epilogue warps 2..9 (both CTAs, own row block) ---------------------------------------
+    // ---------------- epilogue warps 0..7 (both CTAs, own row block) ---------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C2_EPI_REGS));
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     const int row = q * 32 + lane;
     const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16);
     const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
-    const int et = tid - 64;
+    const int et = tid;
     int rp, cb, nk;
     for (int j = 0; c2_tile(g, j, rp, cb, nk); j++) {
       const int rb = 2 * rp + (int)rank;
@@ -334,7 +370,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const double rs = (tmem_base == 0u) ? (real ? g.rowscale[(int64_t)rb * X2_BM + row] * g.colscale : 0.0)
                                           : __longlong_as_double(0x7ff8000000000000ll);
       double v1[64];
-      mbar_wait(acc1_bar, tpar);
+      c2_wait(acc1_bar, tpar);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // tensor-memory loads run one step ahead of the conversions (tcgen05.wait::ld covers all loads
       // issued so far, so the next pair is issued right after the wait and lands during the math)
@@ -372,7 +408,7 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           v1[c0 + j2] += R256 ? fma((double)ra[cur][j2], 0x1p-38, (double)rc[cur][j2] * 0x1p-46)
                               : fma((double)ra[cur][j2], 0x1p-42, (double)rc[cur][j2] * 0x1p-49);
       }
-      mbar_wait(acc2_bar, tpar);
+      c2_wait(acc2_bar, tpar);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       // radix 256: group 2 sits in accumulator 0 alone; radix 128: groups 2, 3 in accumulators 0, 1
       tmem_ld8(lane_addr + (unsigned)(half * 64), ra[0]);
@@ -428,8 +464,9 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
   __syncthreads();
+  if (tid == 0) trace_emit(2u, t_begin);
   c2_cluster_sync();                              // the peer may still be reading / being written to
-  if (warp == 1) {
+  if (warp == 9) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512)
                  : "memory");

@@ -3,6 +3,38 @@
 // sm_100a only.  Reference paths are relative to the reference tree (dragonfly-opt 0.1.7).
 #include "kernels.cuh"
 #include "exp_nonpos.h"
+
+// ---- diagnostics: per-CTA (kind, SM id, start, end) records of the two kernels of the overlapped scoring pipeline ------
+// dfb_debug_trace(buffer, capacity) arms it (buffer[0] = record counter, 4 words per record); NULL disarms.  Used by
+// tools/trace_overlap.py to see whether the K_* CTAs really run beside the persistent contraction CTAs.
+namespace dfb {
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned long long g_trace_cap = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_emit(unsigned kind, unsigned long long t0) {
+  unsigned long long* buf = g_trace;
+  if (buf == nullptr) return;
+  const unsigned long long idx = atomicAdd(buf, 1ull);
+  if (idx >= g_trace_cap) return;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  buf[1 + 4 * idx + 0] = ((unsigned long long)kind << 32) | smid;
+  buf[1 + 4 * idx + 1] = t0;
+  buf[1 + 4 * idx + 2] = trace_now();
+  buf[1 + 4 * idx + 3] = blockIdx.x;
+}
+int debug_set_trace(void* buf, long long cap_records) {
+  unsigned long long* p = static_cast<unsigned long long*>(buf);
+  unsigned long long c = (unsigned long long)(cap_records < 0 ? 0 : cap_records);
+  DFB_CUDA_OK(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+  DFB_CUDA_OK(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
+  return 0;
+}
+}  // namespace dfb
 #include "gemm_tma.cuh"
 #include "gemm_i8.cuh"
 #include "gemm_i8x2.cuh"
@@ -502,6 +534,312 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
       }
     }
   }
+}
+
+// ================================================================================================
+// K_* digit planes for the CTA-pair contraction, second generation (radix 256 only): kstar_seg_kernel.
+//
+// What changed against kstar_fast_kernel<.., I8OUT = true> (which stays as the radix-128 / fallback path):
+//  * TRAINING-STATIONARY loop nest: a warp owns 64 training points -- two per lane, their scaled coordinates, norms
+//    and alpha held in registers for the whole kernel -- and streams candidate rows past them, two rows per iteration
+//    (four independent dependency chains per lane).  The only loads in the loop are the warp-uniform candidate rows
+//    (64 bytes each).  ncu on the first version of this kernel, which re-read its training slice from L1 every row,
+//    showed the fp64 pipe at 47 % with half of all issue slots lost to long-scoreboard stalls
+//    (profiles/r02_kstar_seg_ncu_summary.txt); with nothing left to wait for, a handful of warps per SM is enough;
+//  * which is the point: at <= 104 registers and no shared memory, one 4-warp CTA of it (one warp per SM sub-partition)
+//    co-resides with the persistent tcgen05 kernel (gemm_i8c2.cuh: launched at 136 registers x 12 warps, 225 KB of
+//    shared memory), and api.cu issues chunk c+1's K_* on a second stream while chunk c is being contracted: fp64 pipe
+//    and tensor pipe of the same SM at the same time;
+//  * candidate-side work (x / bw, |x~|^2, k(x*,x*) in the reference's own operation order) is done once per row by
+//    cand_prep_kernel instead of once per (row, training slice);
+//  * the five digits of x = v 2^-F come from ONE fused multiply-add: t = x 2^39 + (1.5 2^52 + 0x80808080) holds
+//    q + bias in its low mantissa bits, and adding 0x80 to every byte position and then flipping that bit IS the
+//    balanced (signed-byte) base-256 expansion -- no integer carry chain;
+//  * the kernel value is formed with fused constants and FMA contraction: v differs from the reference-order value
+//    of kstar_kernel by a few ulp, which is 10^6 times below the int8 screen's own error allowance, and every
+//    candidate that matters is re-scored by the exact-order fp64 path anyway (dfb_score_argmax).  Exception: the
+//    squared distance of Matern-1/2 keeps the reference's rounding order (see the loop);
+//  * padding needs no selects: training points beyond n carry the norm 1e200 (their kernel value underflows to an
+//    exact 0 for SE and Matern alike), candidate rows beyond m likewise;
+//  * mu leaves as per-block partial sums mu_part[block][row] (one packed butterfly per row pair), added in a fixed
+//    order by mu_reduce_kernel.
+// Algorithmic bytes per candidate: 6 npad written (five digit planes + the compact leading plane) + 8 (D+2) read.
+// ================================================================================================
+constexpr int KS_BLK = 64;         // training points per warp (two per lane), register-resident
+constexpr int KS_ROWS = 64;        // candidate rows per CTA
+constexpr int KS_WARPS = 4;        // one warp per SM sub-partition, <= 104 registers: the 3328 registers per partition that
+                                   // the persistent contraction kernel (launched at 136 registers x 12 warps) leaves free
+constexpr double KS_FAR = 1e200;   // squared norm of padding points: exp(-sqrt(1e200) c) == 0, no overflow on the way
+
+template <int KIND, int P, int D>
+__global__ void cand_prep_kernel(const dfb_kernel_desc* __restrict__ desc_g, const double* __restrict__ Xc, int64_t m,
+                                 int dc, int64_t m_rows, double* __restrict__ cprep, double* __restrict__ kss_out) {
+  constexpr int CP = (D + 2) & ~1;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m_rows) return;
+  double xc[D];
+  double nc = KS_FAR;
+#pragma unroll
+  for (int q = 0; q < D; q++) xc[q] = 0.0;
+  if (r < m) {
+#pragma unroll
+    for (int q = 0; q < D; q++) xc[q] = Xc[r * dc + desc_g->slot_cand_coord[q]] / desc_g->slot_bandwidth[q];
+    if (D < 8) {
+      nc = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; q++) nc = __dadd_rn(nc, __dmul_rn(xc[q], xc[q]));
+    } else {
+      nc = numpy_sumsq(D, [&](int q) { return xc[q]; });
+    }
+    if (kss_out != nullptr) {
+      // k(x*, x*) through D2(x, x) = (|x|^2 + |x|^2) - 2 x.x with its rounding noise (gp_core.py:179)
+      const dfb_factor_desc f = desc_g->factors[0];
+      double dot = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; q++) dot = fma(xc[q], xc[q], dot);
+      double d2 = __dadd_rn(__dadd_rn(nc, nc), -2.0 * dot);
+      d2 = fmax(d2, 0.0);
+      const double prod = __dmul_rn(desc_g->term_pre_scale[0], base_value_fast<KIND, P>(f, d2));
+      kss_out[r] = __dmul_rn(desc_g->post_scale, __dadd_rn(0.0, prod));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < D; q++) cprep[r * CP + q] = xc[q];
+  cprep[r * CP + D] = nc;
+  if (CP > D + 1) cprep[r * CP + D + 1] = 0.0;
+}
+
+// constants of the segment kernel as constant-bank operands (literals would be re-materialised with two moves each)
+__constant__ double ks_cd[6] = {1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+                                6755399441055744.0, 6755399441055744.0 + 2155905152.0, 0x1p-960};
+
+// exp(x), x <= 0 (or a rounding residue above 0): dfb_exp_nonpos without the argument clamp -- whatever the polynomial
+// makes of x < -707 is discarded by the final select (no traps on the device); NaN propagates through the arithmetic
+__device__ __forceinline__ double ks_exp(double x) {
+  const double t = fma(x, ks_cd[0], ks_cd[3]);
+  const int n = __double2loint(t);
+  const double tn = t - ks_cd[3];
+  double r = fma(tn, ks_cd[1], x);
+  r = fma(tn, ks_cd[2], r);
+  double p = dfb_exp_cd[0];
+#pragma unroll
+  for (int i = 1; i < 14; i++) p = fma(p, r, dfb_exp_cd[i]);
+  const double out = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  return (x < -707.0) ? 0.0 : out;
+}
+
+// Four of them, stage by stage (see the staging note in kstar_seg_kernel).  The kernel is bound by the LATENCY of
+// dependent fp64 operations (a few warps per SM sub-partition when co-resident), so the degree-13 polynomial is
+// evaluated by Estrin's scheme -- depth 4 instead of Horner's 13, three more multiplications:
+//   p = (a0 + a1 r2) + (a2 + a3 r2) r4 + ((a4 + a5 r2) + a6 r4) r8,   a_k = c_2k + c_2k+1 r
+// (c_i = 1/i! lives in dfb_exp_cd[13 - i]).  Rounding differs from Horner's by an ulp or two.
+__device__ __forceinline__ void ks_exp4(const double (&x)[4], double (&out)[4]) {
+  double t[4], r[4], p[4];
+  int n[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) { t[e] = fma(x[e], ks_cd[0], ks_cd[3]); n[e] = __double2loint(t[e]); t[e] -= ks_cd[3]; }
+#pragma unroll
+  for (int e = 0; e < 4; e++) r[e] = fma(t[e], ks_cd[2], fma(t[e], ks_cd[1], x[e]));
+  double r2[4], r4[4], a[4][7];
+#pragma unroll
+  for (int e = 0; e < 4; e++) r2[e] = r[e] * r[e];
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) a[e][k] = fma(dfb_exp_cd[13 - (2 * k + 1)], r[e], dfb_exp_cd[13 - 2 * k]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) r4[e] = r2[e] * r2[e];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const double b0 = fma(a[e][1], r2[e], a[e][0]);
+    const double b1 = fma(a[e][3], r2[e], a[e][2]);
+    const double b2 = fma(a[e][5], r2[e], a[e][4]);
+    const double e0 = fma(b1, r4[e], b0);
+    const double e1 = fma(a[e][6], r4[e], b2);
+    p[e] = fma(e1, r4[e] * r4[e], e0);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const double o = __hiloint2double(__double2hiint(p[e]) + (n[e] << 20), __double2loint(p[e]));
+    out[e] = (x[e] < -707.0) ? 0.0 : o;
+  }
+}
+
+struct KsegArgs {
+  const double* xsT; const double* nrm; const double* alpha; int64_t npad_tr; int64_t n_valid;
+  const double* cprep; int64_t m_rows; int64_t n_write;
+  uint8_t* planes; int64_t plane_bytes; int64_t row_bytes;
+  double cdig;       // 2^-F 2^39: kernel value -> q
+  double cval;       // post * pre * scale (* Gamma(p+1)/Gamma(2p+1)): the constant factors of the kernel, fused
+  double s8, ms2, c0, c1, c2;         // ms2 = -sqrt(2 nu)
+  double* mu_part; int64_t ld_mu;
+  const int* abort_count; int abort_cap;
+  int debug;         // diagnostics (env DFB200_KSEG_DEBUG): 1 = no digit stores, 2 = candidate rows not re-loaded
+};
+
+template <int KIND, int P, int D>
+__global__ void __maxnreg__(104) kstar_seg_kernel(const KsegArgs g) {
+  if (g.abort_count != nullptr && *g.abort_count > g.abort_cap) return;
+  constexpr int CP = (D + 2) & ~1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long t_begin = (threadIdx.x == 0 && g_trace != nullptr) ? trace_now() : 0ull;
+  const int blk = blockIdx.x * KS_WARPS + warp;                   // this warp's block of 64 training points
+  const int64_t j = (int64_t)blk * KS_BLK + 2 * lane;             // this lane's two points: j, j + 1
+  if (j >= g.n_write) return;                                     // whole warps only (no barriers in this kernel)
+  double xt[D][2], nt2[2], aj[2];
+#pragma unroll
+  for (int q = 0; q < D; q++) {
+    const double2 v = *reinterpret_cast<const double2*>(g.xsT + (int64_t)q * g.npad_tr + j);
+    xt[q][0] = v.x; xt[q][1] = v.y;
+  }
+  {
+    const double2 v = *reinterpret_cast<const double2*>(g.nrm + j);
+    nt2[0] = (j < g.n_valid) ? v.x : KS_FAR;
+    nt2[1] = (j + 1 < g.n_valid) ? v.y : KS_FAR;
+    aj[0] = 0.0; aj[1] = 0.0;
+    if (g.alpha != nullptr) {
+      const double2 a2 = *reinterpret_cast<const double2*>(g.alpha + j);
+      aj[0] = (j < g.n_valid) ? a2.x : 0.0;
+      aj[1] = (j + 1 < g.n_valid) ? a2.y : 0.0;
+    }
+  }
+  const int64_t r_lo = (int64_t)blockIdx.y * KS_ROWS;
+  const int64_t r_hi = (r_lo + KS_ROWS < g.m_rows) ? r_lo + KS_ROWS : g.m_rows;       // m_rows is a multiple of 128
+  // byte offset of this lane's two digits inside a pair-interleaved row: ((j >> 5) << 6) + (j & 31)
+  const unsigned doff = (unsigned)(((j >> 5) << 6) + (j & 31));
+  const bool up = (lane & 16) != 0;
+  for (int64_t r = r_lo; r < r_hi; r += 2) {
+    // Rows r and r + 1 against the lane's two points: four independent dependency chains c = 2 * row + point, advanced
+    // STAGE BY STAGE (every stage an unrolled loop over c) so that all four stay in flight -- a co-resident CTA has one
+    // warp per SM sub-partition, so the parallelism that hides the fp64 latency has to come from inside the warp.
+    double d2[4], v[4];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      double xc[D];
+      const double2* cp = reinterpret_cast<const double2*>(g.cprep + (r + rr) * CP);
+      double nc;
+      if (g.debug & 2) {       // diagnostics: no loads at all in the loop
+#pragma unroll
+        for (int q = 0; q < D; q++) xc[q] = xt[q][0] + 1e-3 * (double)(r + rr);
+        nc = nt2[0];
+      } else {
+#pragma unroll
+      for (int q = 0; q < D; q += 2) {
+        const double2 w2 = cp[q >> 1];
+        xc[q] = w2.x;
+        if (q + 1 < D) xc[q + 1] = w2.y;
+      }
+      nc = g.cprep[(r + rr) * CP + D];
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (KIND == DFB_BASE_MATERN && P == 0) {
+          // Matern-1/2 is not smooth at 0: for a candidate that coincides with a training point d2 is pure rounding
+          // residue and sqrt() turns 1e-16 of it into 1e-8 of the kernel value, so d2 is formed exactly as the
+          // reference-order kernels form it: sequential FMA chain, (|y|^2 + |x|^2) - 2 x.y (general_utils.py:66-69)
+          double dot = 0.0;
+#pragma unroll
+          for (int q = 0; q < D; q++) dot = fma(xc[q], xt[q][e], dot);
+          d2[2 * rr + e] = __dadd_rn(__dadd_rn(nt2[e], nc), -2.0 * dot);
+        } else {
+          // smooth at 0 (SE, Matern-3/2, -5/2: value = 1 - O(d2)): the residue is harmless, so the dot product runs
+          // as two half-length chains and d2 by one fused multiply-add (shorter dependency chain)
+          double p0 = xc[0] * xt[0][e], p1 = (D > 1) ? xc[1] * xt[1][e] : 0.0;
+#pragma unroll
+          for (int q = 2; q < D; q += 2) {
+            p0 = fma(xc[q], xt[q][e], p0);
+            if (q + 1 < D) p1 = fma(xc[q + 1], xt[q + 1][e], p1);
+          }
+          d2[2 * rr + e] = fma(-2.0, p0 + p1, nt2[e] + nc);
+        }
+      }
+    }
+    if (KIND == DFB_BASE_SE) {
+      // d2 < 0 (rounding residue of coincident points) -> exp(+1e-16) = 1: no clip needed
+      double x[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) x[c] = d2[c] * -0.5;
+      ks_exp4(x, v);
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] *= g.cval;
+    } else {
+      // dist = sqrt(max(d2, 0)); d2 below 2^-960 (including the negative rounding residues) gives dist = 0
+      double y[4], ee[4], dist[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[c]) : "d"(d2[c]));
+#pragma unroll
+      for (int c = 0; c < 4; c++) ee[c] = fma(d2[c], -(y[c] * y[c]), 1.0);
+#pragma unroll
+      for (int c = 0; c < 4; c++) y[c] = fma(fma(ee[c], 0.375, 0.5), y[c] * ee[c], y[c]);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        // y ~ d2^-1/2 to 2^-58 after the third-order refinement: d2 y is sqrt(d2) to an ulp (the Markstein
+        // correction of dfb_sqrt_nonneg would add three dependent operations for the last half ulp)
+        const double ss = d2[c] * y[c];
+        dist[c] = (d2[c] < ks_cd[5]) ? 0.0 : ss;             // NaN d2: comparison false, ss = NaN propagates
+      }
+      double x[4], u[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        x[c] = g.ms2 * dist[c];
+        const double mm = g.s8 * dist[c];
+        if (P == 0) u[c] = g.c0;
+        else if (P == 1) u[c] = fma(g.c0, mm, g.c1);
+        else u[c] = fma(fma(g.c0, mm, g.c1), mm, g.c2);
+        u[c] *= g.cval;
+      }
+      ks_exp4(x, v);
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] *= u[c];
+    }
+    // mu partials of the two rows over this warp's 64 points: one packed butterfly (the half-warps swap the row they
+    // do not keep in the first step), lane 0 ends up with row r, lane 16 with row r + 1
+    {
+      const double m0 = fma(v[1], aj[1], v[0] * aj[0]);
+      const double m1 = fma(v[3], aj[1], v[2] * aj[0]);
+      double keep = up ? m1 : m0;
+      const double send = up ? m0 : m1;
+      if (!(g.debug & 4)) {
+      keep += __shfl_xor_sync(0xffffffffu, send, 16);
+      keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+      keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+      keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+      keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+      }
+      if ((lane & 15) == 0 && (!(g.debug & 4) || keep == 0.12345)) g.mu_part[(int64_t)blk * g.ld_mu + r + (lane >> 4)] = keep;
+    }
+    // digits: word of chain c = bytes (a4, a3, a2, a1), a0 in the low byte of the high word; two points per 16-bit store
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const double t0 = fma(v[2 * rr], g.cdig, ks_cd[4]), t1 = fma(v[2 * rr + 1], g.cdig, ks_cd[4]);
+      const unsigned w0 = (unsigned)__double2loint(t0) ^ 0x80808080u, w1 = (unsigned)__double2loint(t1) ^ 0x80808080u;
+      const unsigned short d0 = (unsigned short)__byte_perm((unsigned)__double2hiint(t0), (unsigned)__double2hiint(t1), 0x0040);
+      const unsigned short d1 = (unsigned short)__byte_perm(w0, w1, 0x0073);
+      const unsigned short d2w = (unsigned short)__byte_perm(w0, w1, 0x0062);
+      const unsigned short d3 = (unsigned short)__byte_perm(w0, w1, 0x0051);
+      const unsigned short d4 = (unsigned short)__byte_perm(w0, w1, 0x0040);
+      // pair-interleaved planes: digits (2p, 2p+1) side by side in 32-byte k segments (gemm_i8c2.cuh)
+      uint8_t* dst = g.planes + (r + rr) * g.row_bytes + doff;
+      if ((g.debug & 1) && d0 != 0x7777) continue;
+      *reinterpret_cast<unsigned short*>(dst) = d0;
+      *reinterpret_cast<unsigned short*>(dst + 32) = d1;
+      *reinterpret_cast<unsigned short*>(dst + g.plane_bytes) = d2w;
+      *reinterpret_cast<unsigned short*>(dst + g.plane_bytes + 32) = d3;
+      *reinterpret_cast<unsigned short*>(dst + 2 * g.plane_bytes) = d4;
+      *reinterpret_cast<unsigned short*>(g.planes + 3 * g.plane_bytes + (r + rr) * (g.row_bytes >> 1) + j) = d0;
+    }
+  }
+  if (threadIdx.x == 0) trace_emit(1u, t_begin);       // warp 0 of the CTA: representative (all warps do equal work)
+}
+
+__global__ void mu_reduce_kernel(const double* __restrict__ part, int n_seg, int64_t ld, int64_t m, double mean_const,
+                                 double* __restrict__ mu) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  double s = 0.0;
+  for (int k = 0; k < n_seg; k++) s += part[(int64_t)k * ld + r];
+  mu[r] = mean_const + s;
 }
 
 // ---- tall factorisation matrix set-up -------------------------------------------------------------
@@ -1592,6 +1930,77 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
     DFB_CUDA_OK(cudaGetLastError());
     *emitted_i8 = 1;
   }
+  return 0;
+}
+
+// Second-generation K_* digit path (kstar_seg_kernel): cand_prep -> segments -> mu.  Returns 1 in *emitted when it ran.
+template <int KIND, int P>
+static bool launch_kseg_d(dfb_handle* h, int d, const dfb_kernel_desc* d_desc, const double* Xc, int64_t m, int dc,
+                          int64_t m_rows, double* cprep, double* kss_out, const KsegArgs& a, int n_seg) {
+  const dim3 grid((unsigned)((n_seg + KS_WARPS - 1) / KS_WARPS), (unsigned)((m_rows + KS_ROWS - 1) / KS_ROWS));
+  const unsigned pblocks = (unsigned)((m_rows + 127) / 128);
+  // All kernels of the K stage ask for the maximum shared-memory carve-out -- the configuration the persistent tcgen05
+  // kernel puts the SMs in -- so that their CTAs can be placed beside it instead of waiting for an SM to be re-configured.
+#define DFB_KS_CASE(DD)                                                                                              \
+  case DD: {                                                                                                         \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      cudaFuncSetAttribute(cand_prep_kernel<KIND, P, DD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      \
+      cudaFuncSetAttribute(kstar_seg_kernel<KIND, P, DD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      \
+      cudaFuncSetAttribute(mu_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);                   \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    cand_prep_kernel<KIND, P, DD><<<pblocks, 128, 0, h->stream>>>(d_desc, Xc, m, dc, m_rows, cprep, kss_out);        \
+    kstar_seg_kernel<KIND, P, DD><<<grid, KS_WARPS * 32, 0, h->stream>>>(a);                                         \
+    return true;                                                                                                     \
+  }
+  switch (d) {
+    DFB_KS_CASE(1) DFB_KS_CASE(2) DFB_KS_CASE(3) DFB_KS_CASE(4)
+    DFB_KS_CASE(5) DFB_KS_CASE(6) DFB_KS_CASE(7) DFB_KS_CASE(8)
+    default: return false;
+  }
+#undef DFB_KS_CASE
+}
+
+int launch_kstar_seg(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc, const double* xsT,
+                     const double* nrm, int64_t npad_tr, const double* alpha, int64_t n_valid, const double* Xc, int64_t m, int dc,
+                     int64_t m_rows, int64_t n_write, double mean_const, double* mu, double* kss_out, void* planes,
+                     int64_t plane_bytes, int64_t row_bytes, double inv_colscale, double* cprep, double* mu_part,
+                     int64_t ld_mu, int* emitted, const int* abort_count) {
+  *emitted = 0;
+  if (m_rows <= 0) return 0;
+  const dfb_factor_desc& f = desc.factors[0];
+  if (!(h->kstar_fast && h->kstar_seg && h->i8_impl == 2 && h->i8_radix256 && desc.n_terms == 1 && desc.n_factors == 1 &&
+        f.n_dims <= 8 && f.slot_off == 0 && (f.kind == DFB_BASE_SE || f.p <= 2) && n_write % 128 == 0 && npad_tr % 2 == 0 &&
+        m_rows % 2 == 0))
+    return 0;
+  KsegArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xsT = xsT; a.nrm = nrm; a.alpha = alpha; a.npad_tr = npad_tr; a.n_valid = n_valid; a.cprep = cprep; a.m_rows = m_rows;
+  a.n_write = n_write; a.planes = reinterpret_cast<uint8_t*>(planes); a.plane_bytes = plane_bytes; a.row_bytes = row_bytes;
+  a.cdig = inv_colscale * 0x1p39;
+  a.cval = desc.post_scale * desc.term_pre_scale[0] * f.scale * (f.kind == DFB_BASE_MATERN ? f.gamma_ratio : 1.0);
+  a.s8 = f.s8; a.ms2 = -f.s2; a.c0 = f.coeffs[0]; a.c1 = f.coeffs[1]; a.c2 = f.coeffs[2];
+  a.mu_part = mu_part; a.ld_mu = ld_mu; a.abort_count = abort_count; a.abort_cap = SHORTLIST_CAP;
+  static const int kseg_debug = getenv("DFB200_KSEG_DEBUG") ? atoi(getenv("DFB200_KSEG_DEBUG")) : 0;
+  a.debug = kseg_debug;
+  const int n_seg = (int)(n_write / KS_BLK);             // 64-point blocks, one per warp
+  bool ok = false;
+#define DFB_KS_ARGS h, f.n_dims, d_desc, Xc, m, dc, m_rows, cprep, kss_out, a, n_seg
+  if (f.kind == DFB_BASE_SE) ok = launch_kseg_d<DFB_BASE_SE, 0>(DFB_KS_ARGS);
+  else if (f.p == 0) ok = launch_kseg_d<DFB_BASE_MATERN, 0>(DFB_KS_ARGS);
+  else if (f.p == 1) ok = launch_kseg_d<DFB_BASE_MATERN, 1>(DFB_KS_ARGS);
+  else ok = launch_kseg_d<DFB_BASE_MATERN, 2>(DFB_KS_ARGS);
+#undef DFB_KS_ARGS
+  if (!ok) return 0;
+  h->launches += 2;
+  DFB_CUDA_OK(cudaGetLastError());
+  if (mu != nullptr) {
+    mu_reduce_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(mu_part, n_seg, ld_mu, m, mean_const, mu);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+  }
+  *emitted = 1;
   return 0;
 }
 

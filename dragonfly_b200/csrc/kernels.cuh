@@ -17,6 +17,12 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
                     const double* Xc, int64_t m, int dc, int64_t m_rows, int64_t n_valid, int64_t n_write,
                     double mean_const, double* mu, double* kss_out, void* planes, int64_t plane_bytes,
                     int64_t row_bytes, double inv_colscale, int* emitted_i8, const int* abort_count = nullptr);
+// second-generation digit path (kernels.cu: kstar_seg_kernel)
+int launch_kstar_seg(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc, const double* xsT,
+                     const double* nrm, int64_t npad_tr, const double* alpha, int64_t n_valid, const double* Xc, int64_t m,
+                     int dc, int64_t m_rows, int64_t n_write, double mean_const, double* mu, double* kss_out, void* planes,
+                     int64_t plane_bytes, int64_t row_bytes, double inv_colscale, double* cprep, double* mu_part,
+                     int64_t ld_mu, int* emitted, const int* abort_count = nullptr);
 int launch_init_tall(dfb_handle* h, double* T, int64_t n, int64_t npad, double diag_add,
                      const double* yc, int with_bottom);
 int launch_chol_diag(dfb_handle* h, double* T, int64_t ld, int step, double* Dinv, int* info);
@@ -60,6 +66,7 @@ int launch_add_row_vector(dfb_handle* h, double* M, int64_t ld, int64_t rows, in
 int launch_diag_max(dfb_handle* h, const double* M, int64_t ld, int64_t n, double* out);
 int launch_fill(dfb_handle* h, double* p, int64_t n, double v);
 int launch_set_diag(dfb_handle* h, double* M, int64_t ld, int64_t from, int64_t to, double v, int add);
+int debug_set_trace(void* buf, long long cap_records);
 // LML gradients: reduction of (alpha alpha^T - K^-1) o dK/dparam over lower tiles of row blocks [rb0, rb0 + n_rb)
 int launch_lml_grad_tiles(dfb_handle* h, const dfb_kernel_desc* d_desc, const double* xs, const double* nrm, int64_t npad,
                           const double* alpha, const double* Kinv, int64_t ldk, int rb0, int n_rb, int nb, int64_t n,

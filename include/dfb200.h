@@ -274,6 +274,10 @@ int dfb_ts_draws(dfb_handle* h, const double* Xc_dev, int64_t m, int32_t dc, dou
 
 /* Counters for bench.py: number of kernels this handle has launched. */
 int64_t dfb_launch_count(dfb_handle* h);
+/* Diagnostics: arm (buf_dev = device buffer of 1 + 4 * cap_records 64-bit words, zeroed) or disarm (NULL) the per-CTA
+ * trace of the K_* and contraction kernels of the overlapped scoring pipeline: record = (kind << 32 | SM id, start ns,
+ * end ns, CTA index), buf[0] = number of records wanted.  tools/trace_overlap.py reads it. */
+int dfb_debug_trace(void* buf_dev, int64_t cap_records);
 
 /* Tuning switches.
  *  "gemm_impl"  : 0 = cp.async-ring DMMA kernel, 1 = TMA + mbarrier warp-specialised DMMA kernel for the

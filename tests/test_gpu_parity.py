@@ -574,7 +574,9 @@ def test_i8_sigma2_within_contract(B, name, i8_impl, i8_radix):
     assert i8_radix == 1 and bound > 5e-9
     assert (sd0 == sd1).all()
     return
-  assert (mu0 == mu1).all()
+  # mu of the int8 pass comes from the digit-emitting K_* kernel (fused constants, per-segment partial sums): equal
+  # to the exact-order fp64 path's to rounding, 100x inside the 1e-10 contract
+  close(mu1, mu0, atol=1e-12)
   err = np.abs(sd0 ** 2 - sd1 ** 2).max()
   assert err <= (5e-9 if radix256 else 1e-9), err
   assert err <= bound
