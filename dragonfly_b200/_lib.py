@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdfb200.so')
+LIB_PATH = os.environ.get('DFB200_LIB') or os.path.join(_HERE, 'libdfb200.so')      # DFB200_LIB: A/B builds (tools/)
 
 DFB_MAX_FACTORS = 48
 DFB_MAX_TERMS = 48

@@ -514,6 +514,9 @@ static int ensure_ks_stream(dfb_handle* h) {
   if (h->ks_stream != nullptr) return 0;
   int lo = 0, hi = 0;
   DFB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority: the contraction's CTAs go first
+  if (getenv("DFB200_KS_PRIO") != nullptr) {                    // diagnostics: 0 = equal priorities, 1 = swapped
+    if (atoi(getenv("DFB200_KS_PRIO")) == 0) hi = lo; else { const int t = lo; lo = hi; hi = t; }
+  }
   DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->ks_stream, cudaStreamNonBlocking, lo));
   DFB_CUDA_OK(cudaStreamCreateWithPriority(&h->gs_stream, cudaStreamNonBlocking, hi));
   DFB_CUDA_OK(cudaEventCreateWithFlags(&h->ks_fork, cudaEventDisableTiming));
@@ -1314,6 +1317,7 @@ int dfb_query(dfb_handle* h, const char* name, double* out) {
   if (strcmp(name, "last_selfcheck_violations") == 0) { *out = (double)h->last_selfcheck_violations; return 0; }
   if (strcmp(name, "last_selfcheck_ratio") == 0) { *out = h->last_selfcheck_ratio; return 0; }
   if (strcmp(name, "chunk") == 0) { *out = (double)h->chunk; return 0; }
+  if (strcmp(name, "last_c2_group") == 0) { *out = (double)h->last_c2_group; return 0; }
   if (strcmp(name, "last_overlapped") == 0) { *out = (double)h->last_overlapped; return 0; }     // chunks of the last PIPELINED pass
   if (strcmp(name, "i8_bound_limit") == 0) { *out = I8_BOUND_LIMIT; return 0; }
   if (strcmp(name, "score_impl") == 0) { *out = (double)h->score_impl; return 0; }
@@ -1361,6 +1365,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   }
   if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }
   if (strcmp(name, "i8_cb_group") == 0 && value >= 1) { h->i8_cb_group = (int)value; return 0; }
+  if (strcmp(name, "i8_c2_group") == 0 && value >= 0) { h->i8_c2_group = (int)value; return 0; }
   if (strcmp(name, "score_impl") == 0) {
     if (value < 0 || value > 2) { set_error("score_impl must be 0 (fp64 DMMA), 1 (int8-slice tcgen05) or 2 (auto)"); return -1; }
     h->score_impl = (int)value;

@@ -113,6 +113,8 @@ struct dfb_handle {
   int gemm_impl = 1;          // 0 = v1 cp.async ring, 1 = v2 TMA + mbarrier ring (default)
   int tma_cb_group = 1 << 20;       // candidate tiles per scheduling group (sweep: no gain, see profiles/)
   int i8_cb_group = 12;        // int8 kernel: 12 candidate tiles per group keeps W's digits L2-resident (time-neutral, 9x less DRAM traffic)
+  int i8_c2_group = 0;        // pair kernel: candidate tiles per group of its tile order; 0 = chosen by simulation (kernels.cu)
+  int last_c2_group = 0;
   int kstar_fast = 1;         // specialised K_* kernel for plain SE / Matern on <= 8 dims
   bool tma_ready = false;
   CUtensorMap tmW;            // W  (npad x npad)

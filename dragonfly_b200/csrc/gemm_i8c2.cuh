@@ -142,14 +142,26 @@ __device__ __forceinline__ void c2_commit(void* bar) {
 template <bool R256>
 __device__ __forceinline__ int c2_pass_b_stages(int nk) { return R256 ? (nk + 3) / 4 : (nk + 2) / 3; }
 
-// Tile j of cluster c: serpentine deal of the list (row-block pair descending, cb ascending)
+// Tile j of cluster c: serpentine deal of the tile list.  List order (g.cb_group = G candidate tiles per group):
+// group of G candidate tiles ascending -> row-block pair descending (heaviest first) -> candidate tile within the
+// group.  The clusters work on ~74 consecutive list entries at any time, so with G x 20 row-block pairs per group a
+// group's K_* digit tiles (G x 4.6 MB at N = 5000) are consumed by ALL row-block pairs while they sit in the L2, and
+// only W's digits are re-streamed, once per group: ~(n_cb / G) x |W| + |K_*| bytes from HBM per launch instead of
+// ~n_rp / 2 x |K_*| for the plain row-pair-major order (G = 0 or >= n_cb).
 __device__ __forceinline__ bool c2_tile(const ScoreI8Args& g, int j, int& rp, int& cb, int& nk) {
   const int P = (int)gridDim.x >> 1, c = (int)blockIdx.x >> 1;
   const int n_rp = (g.n_rb + 1) >> 1;
   const int t = j * P + ((j & 1) ? P - 1 - c : c);
   if (t >= n_rp * g.n_cb) return false;
-  rp = n_rp - 1 - t / g.n_cb;
-  cb = t % g.n_cb;
+  const int G = (g.cb_group > 0 && g.cb_group < g.n_cb) ? g.cb_group : g.n_cb;
+  const int per_group = n_rp * G;
+  const int grp = t / per_group;
+  const int cb0 = grp * G;
+  const int width = min(G, g.n_cb - cb0);                 // the last group may be narrower
+  const int u = t - grp * per_group;                      // index inside the group: (rp descending, cb ascending)
+  // groups before the last one have exactly per_group entries; the last one n_rp * width
+  rp = n_rp - 1 - u / width;
+  cb = cb0 + u % width;
   nk = min(g.K, (2 * rp + 2) * TILE) / X2_BK;
   return true;
 }

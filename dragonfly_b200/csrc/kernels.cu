@@ -567,8 +567,14 @@ kstar_fast_kernel(const dfb_kernel_desc* __restrict__ desc_g, int cand_uses_trai
 // ================================================================================================
 constexpr int KS_BLK = 64;         // training points per warp (two per lane), register-resident
 constexpr int KS_ROWS = 64;        // candidate rows per CTA
-constexpr int KS_WARPS = 4;        // one warp per SM sub-partition, <= 104 registers: the 3328 registers per partition that
-                                   // the persistent contraction kernel (launched at 136 registers x 12 warps) leaves free
+constexpr int KS_WARPS = 4;        // one warp per SM sub-partition
+// Register cap.  104 is what fits beside the persistent contraction kernel (3328 registers per sub-partition are left by its
+// 12 warps x 136 registers); stand-alone -- the default, see kstar_overlap in DESIGN.md 5.1 -- 128 is fastest
+// (0.200 ms per 6528 x 5120 chunk against 0.209 / 0.219 / 0.244 at 104 / 88 / 72: profiles/r02_kstar_variants.txt).
+#ifndef DFB_KS_MAXREG
+#define DFB_KS_MAXREG 128
+#endif
+constexpr int KS_MAXREG = DFB_KS_MAXREG;
 constexpr double KS_FAR = 1e200;   // squared norm of padding points: exp(-sqrt(1e200) c) == 0, no overflow on the way
 
 template <int KIND, int P, int D>
@@ -679,7 +685,7 @@ struct KsegArgs {
 };
 
 template <int KIND, int P, int D>
-__global__ void __maxnreg__(104) kstar_seg_kernel(const KsegArgs g) {
+__global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
   if (g.abort_count != nullptr && *g.abort_count > g.abort_cap) return;
   constexpr int CP = (D + 2) & ~1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1767,6 +1773,47 @@ int launch_score_i8x2_args(dfb_handle* h, const CUtensorMap& tmA2, const CUtenso
 }
 
 static bool g_i8c2_attr = false;
+// Candidate tiles per group for the pair kernel's tile order (gemm_i8c2.cuh: c2_tile).  The static serpentine deal is only
+// as balanced as the list order lets it be, so the group width is chosen by simulating the deal: among the widths whose
+// K_* digit group stays L2-resident (<= 64 MB), the one with the least HBM traffic estimate whose heaviest cluster is
+// within 0.5 % of the best balance found (no grouping included).
+static int choose_cb_group(int n_rb, int n_cb, int K, int P) {
+  const int n_rp = (n_rb + 1) / 2;
+  const long long group_bytes_per_cb = 7ll * TILE * K;
+  double best_bal = 1e30;
+  int cand[64], n_cand = 0;
+  double bal_of[64];
+  for (int G = 4; G <= n_cb; G++) {
+    if (G < n_cb && group_bytes_per_cb * G > (64ll << 20)) continue;
+    if (n_cand == 64) break;
+    double load[256];
+    for (int c = 0; c < P && c < 256; c++) load[c] = 0.0;
+    int t = 0;
+    for (int cb0 = 0; cb0 < n_cb; cb0 += G) {
+      const int width = (n_cb - cb0 < G) ? n_cb - cb0 : G;
+      for (int u = 0; u < n_rp * width; u++, t++) {
+        const int rp = n_rp - 1 - u / width;
+        int nk = (2 * rp + 2) * TILE;
+        if (nk > K) nk = K;
+        nk /= 32;
+        const int j = t / P, cc = t % P;
+        load[(j & 1) ? P - 1 - cc : cc] += nk + (nk + 3) / 4;
+      }
+    }
+    double mx = 0.0, sum = 0.0;
+    for (int c = 0; c < P && c < 256; c++) { sum += load[c]; if (load[c] > mx) mx = load[c]; }
+    const double bal = mx / (sum / P);
+    cand[n_cand] = G; bal_of[n_cand] = bal; n_cand++;
+    if (bal < best_bal) best_bal = bal;
+  }
+  int best = n_cb;
+  for (int i = 0; i < n_cand; i++)          // widths ascending: the first acceptable width beyond which traffic only grows
+    if (bal_of[i] <= best_bal * 1.005) {    // least traffic = widest acceptable group below the residency limit
+      if (cand[i] < n_cb) best = cand[i];
+    }
+  return best;
+}
+
 int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtensorMap& tmA3, const CUtensorMap& tmA1c,
                            const CUtensorMap& tmB1h, const CUtensorMap& tmB3h, const CUtensorMap& tmB1c, int n_rb, int n_cb, int K,
                            double* partial, int64_t ld_partial, const double* rowscale, double colscale,
@@ -1775,7 +1822,6 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
   memset(&g, 0, sizeof(g));
   g.n_rb = n_rb; g.n_cb = n_cb; g.K = K; g.partial = partial; g.ld_partial = ld_partial;
   g.rowscale = rowscale; g.colscale = colscale;
-  g.cb_group = 0;
   g.abort_count = abort_count; g.abort_cap = SHORTLIST_CAP;
   const int n_tiles = ((n_rb + 1) / 2) * n_cb;      // row-block pairs x candidate tiles
   if (n_tiles <= 0) return 0;
@@ -1784,6 +1830,19 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
     DFB_CUDA_OK(cudaDeviceGetAttribute(&n_sm[h->device & 63], cudaDevAttrMultiProcessorCount, h->device));
   const int max_clusters = n_sm[h->device & 63] / 2;                 // one CTA per SM, two SMs per cluster
   const int n_clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
+  {
+    // group width of the tile order: option i8_c2_group > 0 forces it, 0 = chosen by simulation (cached per geometry)
+    static int memo_key[4] = {0, 0, 0, 0}, memo_val = 0;
+    if (h->i8_c2_group > 0) g.cb_group = h->i8_c2_group;
+    else {
+      if (memo_key[0] != n_rb || memo_key[1] != n_cb || memo_key[2] != K || memo_key[3] != n_clusters) {
+        memo_val = choose_cb_group(n_rb, n_cb, K, n_clusters);
+        memo_key[0] = n_rb; memo_key[1] = n_cb; memo_key[2] = K; memo_key[3] = n_clusters;
+      }
+      g.cb_group = memo_val;
+    }
+    h->last_c2_group = g.cb_group;
+  }
   if (!g_i8c2_attr) {
     DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C2_SMEM_BYTES));
