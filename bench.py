@@ -368,6 +368,7 @@ class Workload(object):
       if self.cfg == 'c5':
         self.c5_cands = None
     self.d = self.w['dim']
+    self.local_ms = []
 
   # -- model -------------------------------------------------------------------------------------
   def make_gp(self):
@@ -392,9 +393,11 @@ class Workload(object):
   def step_device(self):
     """ Candidates resident in (or generated in) HBM: the `value` leg. """
     from dragonfly_b200 import dist as dfb_dist
+    t0 = time.perf_counter()
     gp = self.make_gp()
     if self.cfg == 'headline':
-      best, idx, _ = gp._fused_score(self.acq, self.cands_dev)
+      best, idx, _ = gp._fused_score(self.acq, self.cands_dev)      # returns after the device is done (16-byte read-back)
+      self.local_ms.append(1e3 * (time.perf_counter() - t0))        # this rank's own work, before the collective
       if self.world > 1:
         dfb_dist.all_reduce_argmax(best, idx + self.rank * self.M, self.dev)
     else:
@@ -490,7 +493,9 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   launches[0] = 0
+  wl.local_ms = []
   t_dev = timed(wl.step_device, args.steps)
+  local_ms = float(np.mean(wl.local_ms)) if wl.local_ms else 0.0
   n_launch = launches[0]
   barrier()
   wl.step_e2e()                                  # warm-up of the host path (pinned staging, thread start)
@@ -583,12 +588,12 @@ def run_ours(args):
       del gp
 
   # max over ranks of every rank's own K-step time; per-rank figures kept
-  mine = torch.tensor([ms_dev, ms_e2e, ms_fp64], dtype=torch.float64, device=dev)
+  mine = torch.tensor([ms_dev, ms_e2e, ms_fp64, local_ms], dtype=torch.float64, device=dev)
   per_rank = [mine.clone() for _ in range(world)]
   if world > 1:
     dist.all_gather(per_rank, mine)
   per_rank = torch.stack(per_rank).cpu().numpy()
-  ms_dev, ms_e2e, ms_fp64 = [float(v) for v in per_rank.max(axis=0)]
+  ms_dev, ms_e2e, ms_fp64 = [float(v) for v in per_rank.max(axis=0)[:3]]
   value = wl.global_m * args.steps / (ms_dev * 1e-3)
   e2e_value = wl.global_m * args.steps / (ms_e2e * 1e-3)
 
@@ -614,7 +619,8 @@ def run_ours(args):
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': int(n_launch),
       'per_rank_ms_per_step': {'device': [float(v) / args.steps for v in per_rank[:, 0]],
-                               'e2e': [float(v) / args.steps for v in per_rank[:, 1]]},
+                               'e2e': [float(v) / args.steps for v in per_rank[:, 1]],
+                               'device_before_the_collective': [float(v) for v in per_rank[:, 3]]},
       'step_ms_each': {'device': t_dev, 'e2e': t_e2e},
       'collectives_per_step': {'headline': 1, 'c2': 1, 'c3': 7, 'c4': 1, 'c5': 1}[args.config] if world > 1 else 0,
     }
