@@ -96,24 +96,69 @@ CANDIDATE_RNG = 'numpy'
 STREAM_SLAB_ROWS = 1 << 17
 
 
-def _maximise_streamed(score, bounds, max_evals, slab):
+_PINNED_SLABS = {}
+
+
+def _pinned_slab_buffers(rows, dim, count=4):
+  """ `count` page-locked (rows, dim) staging arrays (NumPy views of pinned torch tensors), cached: the slabs of the
+      streamed draw are mapped to bounds straight into them, so the device call's host->device copies are real DMA
+      instead of the driver's pageable staging.  None without CUDA (the CPU tests). """
+  try:
+    import torch
+    if not torch.cuda.is_available():
+      return None
+  except Exception:  # pylint: disable=broad-except
+    return None
+  key = (int(rows), int(dim))
+  if key not in _PINNED_SLABS:
+    if len(_PINNED_SLABS) > 8:
+      _PINNED_SLABS.clear()
+    bufs = [torch.empty((key[0], key[1]), dtype=torch.float64, pin_memory=True) for _ in range(count)]
+    _PINNED_SLABS[key] = (bufs, [b.numpy() for b in bufs])
+  return _PINNED_SLABS[key][1]
+
+
+def _slab_schedule(max_evals, slab, unit):
+  """ Row ranges of the streamed draw: two short slabs first (2 and 6 scoring chunks) so that the device starts after
+      ~0.5 ms of drawing instead of after a full slab, then full slabs. """
+  starts, r0 = [], 0
+  for rows in (2 * unit, 6 * unit):
+    if unit > 0 and rows < slab and r0 + rows < max_evals:
+      starts.append((r0, rows)); r0 += rows
+  while r0 < max_evals:
+    rows = min(slab, max_evals - r0)
+    starts.append((r0, rows)); r0 += rows
+  return starts
+
+
+def _maximise_streamed(score, bounds, max_evals, slab, unit=0):
   """ random_maximise (oper_utils.py:70-80) with the candidate draw pipelined against the scoring.
       score(pts) -> (best_score, best_index_within_pts, ...).  np.random.random((M, d)) and consecutive
       np.random.random((m_k, d)) slabs consume the MT19937 stream identically (row-major fill), so the candidates
-      -- and the state the global RNG is left in -- are the reference's. """
+      -- and the state the global RNG is left in -- are the reference's.  `unit` = rows of one scoring chunk. """
   import queue
   import threading
   from . import dist as dfb_dist
   M, dim = int(max_evals), len(bounds)
   rank, world, dev = _shard_info()
   lo_r, hi_r = dfb_dist.shard_bounds(M, rank, world) if world > 1 else (0, M)
-  starts = list(range(0, M, slab)) if M > 0 else []
+  starts = _slab_schedule(M, slab, unit) if M > 0 else []
   q = queue.Queue(maxsize=2)
+  bnds = np.asarray(bounds, dtype=np.float64)
+  width, low = bnds[:, 1] - bnds[:, 0], bnds[:, 0]
+  pinned = _pinned_slab_buffers(slab, dim) if len(starts) > 1 else None
 
   def _producer():
     try:
-      for r0 in starts:
-        q.put((r0, draw_candidates(bounds, min(slab, M - r0))))
+      for k, (r0, rows) in enumerate(starts):
+        raw = np.random.random((rows, dim))
+        if pinned is not None and (min(hi_r, r0 + rows) > max(lo_r, r0)):
+          pts = pinned[k % len(pinned)][:rows]
+          np.multiply(raw, width, out=pts)             # map_to_bounds: pts * (hi - lo) + lo, written in place
+          np.add(pts, low, out=pts)
+        else:
+          pts = raw * width + low
+        q.put((r0, pts))
     except BaseException as exc:  # pylint: disable=broad-except
       q.put(exc)
 
@@ -192,7 +237,8 @@ def _fused_maximise(scorer, anc_data, bounds=None, session=None):
       return _maximise_device_candidates(sess, bounds, anc_data.max_evals)
     if mode != 'numpy':
       raise ValueError("candidate_rng should be 'numpy' or 'device'.")
-    return _maximise_streamed(sess.score, bounds, anc_data.max_evals, sess.slab_rows(STREAM_SLAB_ROWS))
+    return _maximise_streamed(sess.score, bounds, anc_data.max_evals, sess.slab_rows(STREAM_SLAB_ROWS),
+                              unit=sess.slab_rows(1))
 
 
 def _reference_fortran_direct_available():

@@ -747,3 +747,32 @@ def test_mf_hp_layout_unpacks_like_the_reference_mf_fitter():
   assert kern.kernel_list[0].hyperparams['nu'] == 2.5
   with pytest.raises(NotImplementedError):
     hp_grid.EuclideanMFHPLayout(1, 2, 'expdecay', 'se')
+
+
+def test_streamed_draw_schedule_covers_every_row_once_and_matches_the_single_draw():
+  """ gpb_acquisitions._slab_schedule / _maximise_streamed: short slabs first, whole slabs after; the concatenation of
+      the slab draws IS np.random.random((M, d)) (same global MT19937 consumption as oper_utils.py:59-67). """
+  from dragonfly_b200 import gpb_acquisitions as A
+  for M, slab, unit in [(1000000, 130560, 6528), (50000, 130560, 6528), (13056, 13056, 6528), (7, 100, 0), (1001, 300, 0)]:
+    sch = A._slab_schedule(M, slab, unit)
+    assert sch[0][0] == 0 and sum(r for _, r in sch) == M
+    assert all(sch[i][0] + sch[i][1] == sch[i + 1][0] for i in range(len(sch) - 1))
+    assert all(r <= slab for _, r in sch)
+  assert [r for _, r in A._slab_schedule(1000000, 130560, 6528)[:3]] == [13056, 39168, 130560]
+  bounds = np.array([[-1.0, 2.0], [0.0, 5.0], [3.0, 4.0]])
+  seen = []
+
+  def scorer(pts):
+    seen.append(np.array(pts))
+    vals = pts[:, 0] - pts[:, 1] * pts[:, 2]
+    i = int(np.argmax(vals))
+    return vals[i], i, None
+  np.random.seed(11)
+  pt = A._maximise_streamed(scorer, bounds, 2500, 600, unit=100)
+  after = np.random.random()
+  np.random.seed(11)
+  ref = A.draw_candidates(bounds, 2500)
+  assert np.random.random() == after
+  assert (np.concatenate(seen) == ref).all() and [len(x) for x in seen] == [200, 600, 600, 600, 500]
+  vals = ref[:, 0] - ref[:, 1] * ref[:, 2]
+  assert (pt == ref[int(np.argmax(vals))]).all()
