@@ -508,7 +508,7 @@ static ChunkMode chunk_mode(bool want_std, bool do_argmax, bool use_i8, const in
   md.want_std = want_std; md.do_argmax = do_argmax; md.use_i8 = use_i8; md.idx_map = idx_map;
   return md;
 }
-constexpr int64_t SMALL_EVAL_M = 16;
+constexpr int64_t SMALL_EVAL_M = 32;      // up to four 8-wide passes over W's rows (105 MB each at N = 5000): still ~10x cheaper than one 128-wide tile pass
 
 static int ensure_ks_stream(dfb_handle* h) {
   if (h->ks_stream != nullptr) return 0;

@@ -251,7 +251,7 @@ def _reference_fortran_direct_available():
   return getattr(ref_oper, 'direct_ft_wrap', None) is not None
 
 
-def _delegate_to_reference_maximiser(acq_fn, anc_data):
+def _delegate_to_reference_maximiser(acq_fn, anc_data, deterministic=True):
   """ The non-vectorised maximisers of maximise_acquisition (:29-37).  `acq_fn` takes a (k, d) array.
       'pdoo' -- and 'direct' wherever the reference itself would fall back to PDOO because its Fortran DIRECT is
       not built (oper_utils.py:121-137) -- run the batched PDOO of dragonfly_b200/doo.py: the same search as
@@ -260,8 +260,12 @@ def _delegate_to_reference_maximiser(acq_fn, anc_data):
   method = str(anc_data.acq_opt_method).lower()
   if method.startswith('pdoo') or (method.startswith('direct') and not _reference_fortran_direct_available()):
     from .doo import pdoo_maximise
-    _, opt_pt, _ = pdoo_maximise(lambda X: acq_fn(np.asarray(X, dtype=np.float64)), anc_data.domain.bounds,
-                                 anc_data.max_evals)
+    if deterministic:
+      _, opt_pt, _ = pdoo_maximise(lambda X: acq_fn(np.asarray(X, dtype=np.float64)), anc_data.domain.bounds,
+                                   anc_data.max_evals)
+    else:       # a random objective (asy_rand): one call per evaluation, like the reference, nothing cached
+      _, opt_pt, _ = pdoo_maximise(lambda x: acq_fn(np.asarray(x, dtype=np.float64).reshape((1, -1))),
+                                   anc_data.domain.bounds, anc_data.max_evals, vectorised=False, deterministic=False)
     return opt_pt
   try:
     from dragonfly.exd.exd_utils import maximise_with_method  # pylint: disable=import-error
@@ -553,7 +557,7 @@ def asy_rand(_, anc_data):
       the sequential maximisers call it point by point (one uniform per evaluation), so they run as in the
       reference and consume the global RNG like it. """
   if not _check_rand_euclidean(anc_data):
-    return _delegate_to_reference_maximiser(lambda x: np.random.random((1,)), anc_data)
+    return _delegate_to_reference_maximiser(lambda x: np.random.random((1,)), anc_data, deterministic=False)
   rand_pts = draw_candidates(anc_data.domain.bounds, anc_data.max_evals)
   np.random.random((1,))
   return rand_pts[0]

@@ -314,7 +314,7 @@ int dfb_debug_trace(void* buf_dev, int64_t cap_records);
  *  "lookahead"  : 1 (default) = look-ahead schedule of the blocked factorisation (next panel's column updated first,
  *                 chol_diag + panel solve of step k+1 overlap the bulk trailing update of step k on a second stream;
  *                 bit-identical results), 0 = one stream, step after step.
- *  "small_eval" : 1 (default) = dfb_eval of <= 16 points computes |L^-1 k_*|^2 by streaming the rows of W once (one
+ *  "small_eval" : 1 (default) = dfb_eval of <= 32 points computes |L^-1 k_*|^2 by streaming the rows of W once (one
  *                 warp per row, HBM-bound) instead of spending 128-wide DMMA tiles on them; 0 = tile kernels always.
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);

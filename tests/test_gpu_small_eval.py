@@ -1,5 +1,5 @@
 """
-GP.eval of a handful of points (-m gpu): the row-streaming kernel behind dfb_eval for m <= 16 (the one-point
+GP.eval of a handful of points (-m gpu): the row-streaming kernel behind dfb_eval for m <= 32 (the one-point
 objective of the sequential maximisers, TTEI's reference arm, BOCA's fidelity scan; gp_core.py:165-190) against
 the tile kernels on the same points and against the oracle / reference golden.
 """
@@ -32,16 +32,19 @@ def test_small_batches_match_tile_kernels_and_oracle(B, n):
                 lambda x: np.array([w['mean_const']] * len(x)), w['noise_var'])
   C = w['candidates']
   mu_big, sd_big = gp.eval(C, 'std')                       # 400 points: tile kernels
-  mu_o, var_o = B.O.eval_std_diag(ogp, C[:16])
-  for m in [1, 2, 3, 4, 5, 7, 8, 9, 12, 16]:
+  mu_o, var_o = B.O.eval_std_diag(ogp, C[:32])
+  for m in [1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 28, 32]:
     mu, sd = gp.eval(C[:m], 'std')
     np.testing.assert_array_equal(mu, mu_big[:m])          # the mean comes from the same K_* kernel
     np.testing.assert_allclose(sd ** 2, sd_big[:m] ** 2, rtol=0, atol=1e-12)
     np.testing.assert_allclose(sd ** 2, var_o[:m], rtol=0, atol=1e-8)
     np.testing.assert_allclose(mu, mu_o[:m], rtol=0, atol=1e-10)
-  # 17 points are back on the tile path: bit-identical to the big batch
-  mu17, sd17 = gp.eval(C[:17], 'std')
-  assert (sd17 == sd_big[:17]).all()
+  # 33 points are back on the tile path: bit-identical to the big batch
+  mu33, sd33 = gp.eval(C[:33], 'std')
+  assert (sd33 == sd_big[:33]).all()
+  # a point's result does not depend on what else is in a small batch (the level-wide PDOO batches rely on it)
+  mu_a, sd_a = gp.eval(C[5:6], 'std'); mu_b, sd_b = gp.eval(C[:29], 'std')
+  assert sd_a[0] == sd_b[5] and mu_a[0] == mu_b[5]
   # the switch
   gp._post.set_option('small_eval', 0)
   mu1, sd1 = gp.eval(C[:1], 'std')
@@ -90,7 +93,7 @@ def test_one_point_latency_at_n5000(B):
 @pytest.mark.parametrize('acq', ['ei', 'ucb'])
 def test_pdoo_maximiser_end_to_end(B, acq):
   """ acq_opt_method='pdoo' (what 'direct' falls back to without the Fortran extension): the batched PDOO of
-      dragonfly_b200/doo.py driving the device-backed acquisition two children per call, against the reference's
+      dragonfly_b200/doo.py driving the device-backed acquisition a whole round of all its passes per call, against the reference's
       asy_ei / asy_ucb recommendation (tests/golden/pdoo.npz; its doo.py evaluates one point per call). """
   from dragonfly_b200 import gpb_acquisitions as A, domains, doo
   g = load_golden('pdoo')
@@ -103,7 +106,7 @@ def test_pdoo_maximiser_end_to_end(B, acq):
                   handle_parallel='halluc', mf_strategy=None, is_mf=False)
   pt = getattr(A.asy, acq)(gp, anc)
   s = doo.pdoo_maximise.last_search
-  assert s.num_device_calls < 0.6 * len(s.query_vals) + 20
+  assert s.num_device_calls < 0.25 * len(s.query_vals) + 10 and s.num_prefetched > 0
   want = g['e2e_%s_pdoo_point' % acq]
   if not (np.asarray(pt) == want).all():
     # a tree search may legitimately branch differently on a 1e-12 difference of two near-equal bounds: then
