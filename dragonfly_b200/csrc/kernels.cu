@@ -898,8 +898,23 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* T, int64_t ld, i
       if (tid == 0) atomicCAS(info, 0, step * TILE + j + 1);
       return;
     }
-    const double dj = sqrt(piv);
-    const double rj = 1.0 / dj;
+    // d_j = sqrt(pivot) and 1 / d_j from ONE reciprocal-square-root seed: the two software sequences of sqrt() and of the
+    // division (~19 dependent fp64 operations, paid 128 times in a row by a single CTA) share their refinement -- 9
+    // dependent operations.  d_j is the correctly rounded root (the Markstein step of CUDA's own sqrt); 1 / d_j is one
+    // Newton step of y ~ pivot^-1/2 against the ROUNDED d_j, i.e. the reciprocal dpotf2 scales by, to well below an ulp.
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
+    double dj, rj;
+    if (piv >= 0x1p-900 && piv <= 0x1p900) {
+      const double e0 = fma(piv, -(y * y), 1.0);
+      y = fma(fma(e0, 0.375, 0.5), y * e0, y);                    // pivot^-1/2 to ~2^-58
+      const double g0 = piv * y;
+      dj = fma(fma(-g0, g0, piv), 0.5 * y, g0);
+      rj = fma(y, fma(-dj, y, 1.0), y);
+    } else {                                                      // out of the seed's comfortable range: the library pair
+      dj = sqrt(piv);
+      rj = 1.0 / dj;
+    }
     if (tx == jt) {                     // owners of column j scale it and publish it
 #pragma unroll
       for (int b = 0; b < 8; b++) {
