@@ -140,3 +140,31 @@ def test_device_candidate_source(B, gp1500):
   nxt = np.random.random()
   np.random.seed(3); np.random.randint(0, 2 ** 31 - 1); np.random.randint(0, 2 ** 31 - 1)
   assert (pt2 == pt).all() and np.random.random() == nxt
+
+
+def test_cartesian_product_gp_against_the_reference(B):
+  """ dragonfly_b200.cartesian_product_gp.CPGP (points as lists of per-domain parts) against the unmodified reference's
+      CPGP (tests/golden/cpgp.npz): K, LML, alpha, eval, hallucinated eval; and through an acquisition operator. """
+  from conftest import load_golden
+  from dragonfly_b200 import cartesian_product_gp as cp
+  g = load_golden('cpgp')
+  scale, nv, mc = [float(v) for v in g['meta']]
+  parts = lambda M: [[row[0:2], row[2:5], row[5:6]] for row in M]
+  kern = cp.CartesianProductKernel(scale, [B.kernel.SEKernel(2, 1.0, [0.4, 0.6]), B.kernel.MaternKernel(3, 2.5, 1.0, [0.5, 0.7, 0.9]),
+                                           B.kernel.MaternKernel(1, 1.5, 1.0, [0.3])])
+  gp = cp.CPGP(parts(g['X']), list(g['Y']), kern, lambda x: np.array([mc] * len(x)), nv)
+  np.testing.assert_allclose(gp.K_trtr_wo_noise[:16], g['K'], rtol=0, atol=1e-12)
+  np.testing.assert_allclose(gp.compute_log_marginal_likelihood(), float(g['lml']), rtol=1e-10)
+  np.testing.assert_allclose(gp.alpha, g['alpha'], rtol=1e-7, atol=1e-9)
+  mu, sd = gp.eval(parts(g['C']), 'std')
+  np.testing.assert_allclose(mu, g['mu'], rtol=0, atol=1e-10)
+  np.testing.assert_allclose(sd ** 2, g['sd'] ** 2, rtol=0, atol=1e-8)
+  mu_h, sd_h = gp.eval_with_hallucinated_observations(parts(g['C'][:100]), parts(g['H']), 'std')
+  np.testing.assert_allclose(mu_h, g['mu_h'], rtol=0, atol=1e-10)
+  np.testing.assert_allclose(sd_h ** 2, g['sd_h'] ** 2, rtol=0, atol=1e-8)
+  with pytest.raises(NotImplementedError):
+    cp.CPGP(parts(g['X']), list(g['Y']), kern, lambda x: np.array([mc] * len(x)), nv, domain_lists_of_dists=[None, [1], None])
+  # the fused scorer on flat candidate rows: arg-max = the golden's UCB arg-max
+  acq = B.device.make_acq_desc('ucb', beta=2.0)
+  best, idx, _ = gp._fused_score(acq, g['C'], mean_const=mc)
+  assert idx == int(np.argmax(g['mu'] + 2.0 * g['sd']))

@@ -365,3 +365,19 @@ def test_lml_gradients_match_reference(name):
   np.testing.assert_allclose(got, g[name + '_grads'], rtol=1e-10)
   np.testing.assert_allclose(kern.gradient('same_dim_bandwidths', X[:8], X), g[name + '_G_same'], rtol=1e-12, atol=1e-14)
   np.testing.assert_allclose(kern.gradient('dim_bandwidths', X, X, 1)[:8], g[name + '_G_dim1'], rtol=1e-12, atol=1e-14)
+
+
+def test_cartesian_product_gp_matches_reference():
+  """ The reference's CPGP + CartesianProductKernel (kernel.py:504-538, cartesian_product_gp.py:207-248, default
+      'project_first') on Euclidean factors is the coordinate-product kernel on the parts laid side by side: the
+      eigen-projection of a PSD matrix moves nothing beyond rounding.  Golden: tests/golden/make_golden_cpgp.py. """
+  g = load_golden('cpgp')
+  scale, nv, mc = [float(v) for v in g['meta']]
+  kern = O.OCoordinateProductKernel(6, scale, [O.OSEKernel(2, 1.0, [0.4, 0.6]), O.OMaternKernel(3, 2.5, 1.0, [0.5, 0.7, 0.9]),
+                                               O.OMaternKernel(1, 1.5, 1.0, [0.3])], [[0, 1], [2, 3, 4], [5]])
+  gp = O.OGP(g['X'], g['Y'], kern, lambda x: np.array([mc] * len(x)), nv)
+  np.testing.assert_allclose(gp.K_trtr_wo_noise[:16], g['K'], rtol=0, atol=1e-12)
+  np.testing.assert_allclose(gp.compute_log_marginal_likelihood(), float(g['lml']), rtol=1e-10)
+  mu, var = O.eval_std_diag(gp, g['C'])
+  np.testing.assert_allclose(mu, g['mu'], rtol=0, atol=1e-10)
+  np.testing.assert_allclose(var, g['sd'] ** 2, rtol=0, atol=1e-8)
