@@ -146,7 +146,10 @@ def _maximise_streamed(score, bounds, max_evals, slab, unit=0):
   q = queue.Queue(maxsize=2)
   bnds = np.asarray(bounds, dtype=np.float64)
   width, low = bnds[:, 1] - bnds[:, 0], bnds[:, 0]
-  pinned = _pinned_slab_buffers(slab, dim) if len(starts) > 1 else None
+  # staging buffers sized by the largest slab actually scheduled (never by the nominal slab size), and only while they
+  # stay modest: 4 x 256 MB at most
+  rows_max = max([r for _, r in starts] or [0])
+  pinned = _pinned_slab_buffers(rows_max, dim) if (len(starts) > 1 and rows_max * dim * 8 <= (256 << 20)) else None
 
   def _producer():
     try:

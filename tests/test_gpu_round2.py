@@ -93,7 +93,7 @@ def test_streamed_host_draw_returns_the_point_of_the_single_draw(B, gp1500):
   A = B.acq
   old = A.STREAM_SLAB_ROWS
   try:
-    A.STREAM_SLAB_ROWS = 1 << 30                  # one slab = the reference's single draw
+    A.STREAM_SLAB_ROWS = 1 << 22                  # >> max_evals: the reference's single draw (after the two short slabs)
     np.random.seed(9)
     want = A.asy.ucb(gp, _anc(B, 'ucb', 100000))
     after_want = np.random.random()
