@@ -93,7 +93,7 @@ def _sharded_argmax(scorer, n_rows, align=1):
 #            NumPy stream, so seeded runs are reproducible and every rank agrees.  Different candidates than the
 #            reference's, same distribution.  Select per call with anc_data.candidate_rng or module-wide here.
 CANDIDATE_RNG = 'numpy'
-STREAM_SLAB_ROWS = 1 << 17
+STREAM_SLAB_ROWS = 1 << 18
 
 
 _PINNED_SLABS = {}
