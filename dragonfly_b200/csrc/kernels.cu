@@ -634,11 +634,10 @@ __device__ __forceinline__ double ks_exp(double x) {
   return (x < -707.0) ? 0.0 : out;
 }
 
-// Four of them, stage by stage (see the staging note in kstar_seg_kernel).  The kernel is bound by the LATENCY of
-// dependent fp64 operations (a few warps per SM sub-partition when co-resident), so the degree-13 polynomial is
-// evaluated by Estrin's scheme -- depth 4 instead of Horner's 13, three more multiplications:
-//   p = (a0 + a1 r2) + (a2 + a3 r2) r4 + ((a4 + a5 r2) + a6 r4) r8,   a_k = c_2k + c_2k+1 r
-// (c_i = 1/i! lives in dfb_exp_cd[13 - i]).  Rounding differs from Horner's by an ulp or two.
+// Four of them, stage by stage (see the staging note in kstar_seg_kernel).  Degree-13 polynomial by Horner's rule: with
+// 16 warps per SM stand-alone the kernel is bound by instruction count, not by the depth of the dependency chain, and
+// Horner is three multiplications shorter (0.171 ms per chunk against 0.189 for the Estrin form, which -DDFB_KS_ESTRIN
+// keeps for the co-resident, latency-bound setting of kstar_overlap: depth 4 instead of 13).
 __device__ __forceinline__ void ks_exp4(const double (&x)[4], double (&out)[4]) {
   double t[4], r[4], p[4];
   int n[4];
@@ -646,6 +645,15 @@ __device__ __forceinline__ void ks_exp4(const double (&x)[4], double (&out)[4]) 
   for (int e = 0; e < 4; e++) { t[e] = fma(x[e], ks_cd[0], ks_cd[3]); n[e] = __double2loint(t[e]); t[e] -= ks_cd[3]; }
 #pragma unroll
   for (int e = 0; e < 4; e++) r[e] = fma(t[e], ks_cd[2], fma(t[e], ks_cd[1], x[e]));
+#ifndef DFB_KS_ESTRIN
+#pragma unroll
+  for (int e = 0; e < 4; e++) p[e] = dfb_exp_cd[0];
+#pragma unroll
+  for (int i = 1; i < 14; i++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) p[e] = fma(p[e], r[e], dfb_exp_cd[i]);
+  }
+#else
   double r2[4], r4[4], a[4][7];
 #pragma unroll
   for (int e = 0; e < 4; e++) r2[e] = r[e] * r[e];
@@ -665,6 +673,7 @@ __device__ __forceinline__ void ks_exp4(const double (&x)[4], double (&out)[4]) 
     const double e1 = fma(a[e][6], r4[e], b2);
     p[e] = fma(e1, r4[e] * r4[e], e0);
   }
+#endif
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const double o = __hiloint2double(__double2hiint(p[e]) + (n[e] << 20), __double2loint(p[e]));
@@ -681,7 +690,6 @@ struct KsegArgs {
   double s8, ms2, c0, c1, c2;         // ms2 = -sqrt(2 nu)
   double* mu_part; int64_t ld_mu;
   const int* abort_count; int abort_cap;
-  int debug;         // diagnostics (env DFB200_KSEG_DEBUG): 1 = no digit stores, 2 = candidate rows not re-loaded
 };
 
 template <int KIND, int P, int D>
@@ -724,20 +732,13 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
     for (int rr = 0; rr < 2; rr++) {
       double xc[D];
       const double2* cp = reinterpret_cast<const double2*>(g.cprep + (r + rr) * CP);
-      double nc;
-      if (g.debug & 2) {       // diagnostics: no loads at all in the loop
-#pragma unroll
-        for (int q = 0; q < D; q++) xc[q] = xt[q][0] + 1e-3 * (double)(r + rr);
-        nc = nt2[0];
-      } else {
 #pragma unroll
       for (int q = 0; q < D; q += 2) {
         const double2 w2 = cp[q >> 1];
         xc[q] = w2.x;
         if (q + 1 < D) xc[q + 1] = w2.y;
       }
-      nc = g.cprep[(r + rr) * CP + D];
-      }
+      const double nc = g.cprep[(r + rr) * CP + D];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         if (KIND == DFB_BASE_MATERN && P == 0) {
@@ -806,14 +807,12 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
       const double m1 = fma(v[3], aj[1], v[2] * aj[0]);
       double keep = up ? m1 : m0;
       const double send = up ? m0 : m1;
-      if (!(g.debug & 4)) {
       keep += __shfl_xor_sync(0xffffffffu, send, 16);
       keep += __shfl_xor_sync(0xffffffffu, keep, 8);
       keep += __shfl_xor_sync(0xffffffffu, keep, 4);
       keep += __shfl_xor_sync(0xffffffffu, keep, 2);
       keep += __shfl_xor_sync(0xffffffffu, keep, 1);
-      }
-      if ((lane & 15) == 0 && (!(g.debug & 4) || keep == 0.12345)) g.mu_part[(int64_t)blk * g.ld_mu + r + (lane >> 4)] = keep;
+      if ((lane & 15) == 0) g.mu_part[(int64_t)blk * g.ld_mu + r + (lane >> 4)] = keep;
     }
     // digits: word of chain c = bytes (a4, a3, a2, a1), a0 in the low byte of the high word; two points per 16-bit store
 #pragma unroll
@@ -827,7 +826,6 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
       const unsigned short d4 = (unsigned short)__byte_perm(w0, w1, 0x0040);
       // pair-interleaved planes: digits (2p, 2p+1) side by side in 32-byte k segments (gemm_i8c2.cuh)
       uint8_t* dst = g.planes + (r + rr) * g.row_bytes + doff;
-      if ((g.debug & 1) && d0 != 0x7777) continue;
       *reinterpret_cast<unsigned short*>(dst) = d0;
       *reinterpret_cast<unsigned short*>(dst + 32) = d1;
       *reinterpret_cast<unsigned short*>(dst + g.plane_bytes) = d2w;
@@ -2056,8 +2054,6 @@ int launch_kstar_seg(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_ker
   a.cval = desc.post_scale * desc.term_pre_scale[0] * f.scale * (f.kind == DFB_BASE_MATERN ? f.gamma_ratio : 1.0);
   a.s8 = f.s8; a.ms2 = -f.s2; a.c0 = f.coeffs[0]; a.c1 = f.coeffs[1]; a.c2 = f.coeffs[2];
   a.mu_part = mu_part; a.ld_mu = ld_mu; a.abort_count = abort_count; a.abort_cap = SHORTLIST_CAP;
-  static const int kseg_debug = getenv("DFB200_KSEG_DEBUG") ? atoi(getenv("DFB200_KSEG_DEBUG")) : 0;
-  a.debug = kseg_debug;
   const int n_seg = (int)(n_write / KS_BLK);             // 64-point blocks, one per warp
   bool ok = false;
 #define DFB_KS_ARGS h, f.n_dims, d_desc, Xc, m, dc, m_rows, cprep, kss_out, a, n_seg
