@@ -758,7 +758,7 @@ def test_streamed_draw_schedule_covers_every_row_once_and_matches_the_single_dra
     assert sch[0][0] == 0 and sum(r for _, r in sch) == M
     assert all(sch[i][0] + sch[i][1] == sch[i + 1][0] for i in range(len(sch) - 1))
     assert all(r <= slab for _, r in sch)
-  assert [r for _, r in A._slab_schedule(1000000, 130560, 6528)[:3]] == [13056, 39168, 130560]
+  assert [r for _, r in A._slab_schedule(1000000, 261120, 6528)[:4]] == [13056, 52224, 208896, 261120]
   bounds = np.array([[-1.0, 2.0], [0.0, 5.0], [3.0, 4.0]])
   seen = []
 
@@ -773,6 +773,6 @@ def test_streamed_draw_schedule_covers_every_row_once_and_matches_the_single_dra
   np.random.seed(11)
   ref = A.draw_candidates(bounds, 2500)
   assert np.random.random() == after
-  assert (np.concatenate(seen) == ref).all() and [len(x) for x in seen] == [200, 600, 600, 600, 500]
+  assert (np.concatenate(seen) == ref).all() and [len(x) for x in seen] == [200, 600, 600, 600, 500]          # 2 units, then the x4 slab would reach the slab size
   vals = ref[:, 0] - ref[:, 1] * ref[:, 2]
   assert (pt == ref[int(np.argmax(vals))]).all()
