@@ -723,22 +723,30 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
   // byte offset of this lane's two digits inside a pair-interleaved row: ((j >> 5) << 6) + (j & 31)
   const unsigned doff = (unsigned)(((j >> 5) << 6) + (j & 31));
   const bool up = (lane & 16) != 0;
-  for (int64_t r = r_lo; r < r_hi; r += 2) {
-    // Rows r and r + 1 against the lane's two points: four independent dependency chains c = 2 * row + point, advanced
-    // STAGE BY STAGE (every stage an unrolled loop over c) so that all four stay in flight -- a co-resident CTA has one
-    // warp per SM sub-partition, so the parallelism that hides the fp64 latency has to come from inside the warp.
-    double d2[4], v[4];
+  // candidate rows r, r + 1 (warp-uniform, 64 bytes each): loaded one iteration ahead -- the coordinates are dead after the
+  // dot-product stage, so the next pair is fetched into the same registers right there and has the rest of the iteration
+  // (~250 instructions) to arrive (ncu: long-scoreboard was the kernel's top stall with the loads at the top of the loop)
+  double xc[2][D], nc[2];
+  auto load_rows = [&](int64_t r) {
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
-      double xc[D];
       const double2* cp = reinterpret_cast<const double2*>(g.cprep + (r + rr) * CP);
 #pragma unroll
       for (int q = 0; q < D; q += 2) {
         const double2 w2 = cp[q >> 1];
-        xc[q] = w2.x;
-        if (q + 1 < D) xc[q + 1] = w2.y;
+        xc[rr][q] = w2.x;
+        if (q + 1 < D) xc[rr][q + 1] = w2.y;
       }
-      const double nc = g.cprep[(r + rr) * CP + D];
+      nc[rr] = g.cprep[(r + rr) * CP + D];
+    }
+  };
+  if (r_lo < r_hi) load_rows(r_lo);
+  for (int64_t r = r_lo; r < r_hi; r += 2) {
+    // Rows r and r + 1 against the lane's two points: four independent dependency chains c = 2 * row + point, advanced
+    // STAGE BY STAGE (every stage an unrolled loop over c) so that all four stay in flight.
+    double d2[4], v[4];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         if (KIND == DFB_BASE_MATERN && P == 0) {
@@ -747,21 +755,22 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
           // reference-order kernels form it: sequential FMA chain, (|y|^2 + |x|^2) - 2 x.y (general_utils.py:66-69)
           double dot = 0.0;
 #pragma unroll
-          for (int q = 0; q < D; q++) dot = fma(xc[q], xt[q][e], dot);
-          d2[2 * rr + e] = __dadd_rn(__dadd_rn(nt2[e], nc), -2.0 * dot);
+          for (int q = 0; q < D; q++) dot = fma(xc[rr][q], xt[q][e], dot);
+          d2[2 * rr + e] = __dadd_rn(__dadd_rn(nt2[e], nc[rr]), -2.0 * dot);
         } else {
           // smooth at 0 (SE, Matern-3/2, -5/2: value = 1 - O(d2)): the residue is harmless, so the dot product runs
           // as two half-length chains and d2 by one fused multiply-add (shorter dependency chain)
-          double p0 = xc[0] * xt[0][e], p1 = (D > 1) ? xc[1] * xt[1][e] : 0.0;
+          double p0 = xc[rr][0] * xt[0][e], p1 = (D > 1) ? xc[rr][1] * xt[1][e] : 0.0;
 #pragma unroll
           for (int q = 2; q < D; q += 2) {
-            p0 = fma(xc[q], xt[q][e], p0);
-            if (q + 1 < D) p1 = fma(xc[q + 1], xt[q + 1][e], p1);
+            p0 = fma(xc[rr][q], xt[q][e], p0);
+            if (q + 1 < D) p1 = fma(xc[rr][q + 1], xt[q + 1][e], p1);
           }
-          d2[2 * rr + e] = fma(-2.0, p0 + p1, nt2[e] + nc);
+          d2[2 * rr + e] = fma(-2.0, p0 + p1, nt2[e] + nc[rr]);
         }
       }
     }
+    if (r + 2 < r_hi) load_rows(r + 2);
     if (KIND == DFB_BASE_SE) {
       // d2 < 0 (rounding residue of coincident points) -> exp(+1e-16) = 1: no clip needed
       double x[4];
