@@ -415,6 +415,17 @@ class Workload(object):
       self.operator(gp, 'numpy')
     return gp
 
+  def step_e2e_device_rng(self):
+    """ The same operator in its throughput mode (anc_data.candidate_rng = 'device'): candidates generated on the GPU by
+        global row index, so a rank neither draws nor uploads anything proportional to max_evals. """
+    gp = self.make_gp()
+    np.random.seed(7)
+    if self.cfg == 'headline':
+      self.A.asy.ei(gp, self.anc('device'))
+    else:
+      self.operator(gp, 'device')
+    return gp
+
   def operator(self, gp, rng):
     A = self.A
     if self.cfg == 'c2':
@@ -502,8 +513,15 @@ def run_ours(args):
   barrier()
   t_e2e = timed(wl.step_e2e, args.steps)
   barrier()
+  t_e2e_dev = []
+  if headline:
+    wl.step_e2e_device_rng()
+    barrier()
+    t_e2e_dev = timed(wl.step_e2e_device_rng, max(2, args.steps // 2))
+    barrier()
   clocks = sampler.stop() if rank == 0 else None
   ms_dev, ms_e2e = float(np.sum(t_dev)), float(np.sum(t_e2e))
+  ms_e2e_dev = float(np.mean(t_e2e_dev)) if t_e2e_dev else 0.0
 
   extras = {}
   prof, used_i8, shortlist, i8_bound, i8_impl, i8_r256 = {}, False, 0, 0.0, 2, 1
@@ -588,7 +606,7 @@ def run_ours(args):
       del gp
 
   # max over ranks of every rank's own K-step time; per-rank figures kept
-  mine = torch.tensor([ms_dev, ms_e2e, ms_fp64, local_ms], dtype=torch.float64, device=dev)
+  mine = torch.tensor([ms_dev, ms_e2e, ms_fp64, local_ms, ms_e2e_dev], dtype=torch.float64, device=dev)
   per_rank = [mine.clone() for _ in range(world)]
   if world > 1:
     dist.all_gather(per_rank, mine)
@@ -618,6 +636,11 @@ def run_ours(args):
                       'the configuration\'s public operator with the reference\'s host-side NumPy candidate draw',
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': int(n_launch),
+      'e2e_device_candidates': ({'value': wl.global_m / (float(per_rank[:, 4].max()) * 1e-3), 'unit': UNIT,
+                                 'ms_per_step': float(per_rank[:, 4].max()),
+                                 'call': 'the same asy.ei(gp, anc_data) with anc_data.candidate_rng = \'device\': candidates generated on the '
+                                         'GPU by global row index (Philox), host inputs = the training data only'}
+                                if float(per_rank[:, 4].max()) > 0 else None),
       'per_rank_ms_per_step': {'device': [float(v) / args.steps for v in per_rank[:, 0]],
                                'e2e': [float(v) / args.steps for v in per_rank[:, 1]],
                                'device_before_the_collective': [float(v) for v in per_rank[:, 3]]},
