@@ -1367,6 +1367,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "tma_cb_group") == 0 && value >= 1) { h->tma_cb_group = (int)value; return 0; }
   if (strcmp(name, "i8_cb_group") == 0 && value >= 1) { h->i8_cb_group = (int)value; return 0; }
   if (strcmp(name, "i8_c2_group") == 0 && value >= 0) { h->i8_c2_group = (int)value; return 0; }
+  if (strcmp(name, "i8_l2_hint") == 0 && value >= 0 && value <= 2) { h->i8_l2_hint = (int)value; return 0; }
   if (strcmp(name, "score_impl") == 0) {
     if (value < 0 || value > 2) { set_error("score_impl must be 0 (fp64 DMMA), 1 (int8-slice tcgen05) or 2 (auto)"); return -1; }
     h->score_impl = (int)value;

@@ -115,6 +115,7 @@ struct dfb_handle {
   int i8_cb_group = 12;        // int8 kernel: 12 candidate tiles per group keeps W's digits L2-resident (time-neutral, 9x less DRAM traffic)
   int i8_c2_group = 0;        // pair kernel: candidate tiles per group of its tile order; 0 = chosen by simulation (kernels.cu)
   int last_c2_group = 0;
+  int i8_l2_hint = 0;         // pair kernel: L2 eviction priorities of its TMA loads (kernels.cu: launch_score_i8c2_args)
   int kstar_fast = 1;         // specialised K_* kernel for plain SE / Matern on <= 8 dims
   bool tma_ready = false;
   CUtensorMap tmW;            // W  (npad x npad)

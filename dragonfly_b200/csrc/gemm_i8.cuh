@@ -59,6 +59,7 @@ struct ScoreI8Args {
   unsigned long long* timing;   // diagnostics (DFB200_I8_TIMING): per-CTA clocks the MMA thread spent waiting; else NULL
   const int* abort_count;       // CTA-pair kernel: the launch is a no-op once *abort_count > abort_cap (the arg-max
   int abort_cap;                // shortlist overflowed, so this int8 pass will be discarded for an fp64 one); may be NULL
+  unsigned long long l2_a, l2_b;   // CTA-pair kernel: L2 eviction-priority descriptors of the W-digit / K_*-digit TMA loads
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,

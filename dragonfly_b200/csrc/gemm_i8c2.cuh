@@ -109,13 +109,17 @@ __device__ __forceinline__ void c2_arrive_leader(void* bar) {
       "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
-// TMA load into this CTA's shared memory, transaction bytes credited to the leader CTA's barrier
+// TMA load into this CTA's shared memory, transaction bytes credited to the leader CTA's barrier; `policy` is an L2
+// eviction-priority descriptor (the fixed encodings CUTLASS uses: normal / evict-first / evict-last)
+constexpr uint64_t C2_L2_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t C2_L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t C2_L2_EVICT_LAST = 0x14F0000000000000ull;
 __device__ __forceinline__ void c2_tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
-                                               void* bar) {
+                                               void* bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(
           smem_u32(smem_dst)),
-      "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void c2_umma(unsigned tmem_d, uint64_t da, uint64_t db, unsigned accumulate) {
@@ -230,20 +234,20 @@ score_i8c2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           if (R256 && it >= nk) {
             // pass B, radix 256: 128 k-values of the compact leading-digit planes (A 16 KB, B half 8 KB)
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)C2_PB_BYTES);
-            c2_tma_load_3d(dst, &tmA1c, (it - nk) * 128, rb * X2_BM, 0, &full_bar[s]);
-            c2_tma_load_3d(dst + C2_PB_A_BYTES, &tmB1c, (it - nk) * 128, brow, 0, &full_bar[s]);
+            c2_tma_load_3d(dst, &tmA1c, (it - nk) * 128, rb * X2_BM, 0, &full_bar[s], g.l2_a);
+            c2_tma_load_3d(dst + C2_PB_A_BYTES, &tmB1c, (it - nk) * 128, brow, 0, &full_bar[s], g.l2_b);
             continue;
           }
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (unsigned)C2_STAGE_BYTES);   // both CTAs' bytes
           if (it < nk) {
-            c2_tma_load_3d(dst, &tmA3, it * 2 * X2_BK, rb * X2_BM, 0, &full_bar[s]);
-            c2_tma_load_3d(dst + 3 * C2_A_SUB, &tmB3, it * 2 * X2_BK, brow, 0, &full_bar[s]);
+            c2_tma_load_3d(dst, &tmA3, it * 2 * X2_BK, rb * X2_BM, 0, &full_bar[s], g.l2_a);
+            c2_tma_load_3d(dst + 3 * C2_A_SUB, &tmB3, it * 2 * X2_BK, brow, 0, &full_bar[s], g.l2_b);
           } else {
             const int kb0 = (it - nk) * 3;
 #pragma unroll
             for (int u = 0; u < 3; u++) {
-              c2_tma_load_3d(dst + u * C2_A_SUB, &tmA1, (kb0 + u) * 2 * X2_BK, rb * X2_BM, 0, &full_bar[s]);
-              c2_tma_load_3d(dst + 3 * C2_A_SUB + u * C2_B_SUB, &tmB1, (kb0 + u) * 2 * X2_BK, brow, 0, &full_bar[s]);
+              c2_tma_load_3d(dst + u * C2_A_SUB, &tmA1, (kb0 + u) * 2 * X2_BK, rb * X2_BM, 0, &full_bar[s], g.l2_a);
+              c2_tma_load_3d(dst + 3 * C2_A_SUB + u * C2_B_SUB, &tmB1, (kb0 + u) * 2 * X2_BK, brow, 0, &full_bar[s], g.l2_b);
             }
           }
         }

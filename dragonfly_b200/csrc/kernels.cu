@@ -1865,6 +1865,10 @@ int launch_score_i8c2_args(dfb_handle* h, const CUtensorMap& tmA1, const CUtenso
     }
     h->last_c2_group = g.cb_group;
   }
+  // L2 priorities (option i8_l2_hint): 0 = normal / normal, 1 = K_* digits evict-last (they are re-read by every row-block
+  // pair of the group), 2 = additionally W digits evict-first (streamed once per group)
+  g.l2_a = (h->i8_l2_hint == 2) ? C2_L2_EVICT_FIRST : C2_L2_NORMAL;
+  g.l2_b = (h->i8_l2_hint >= 1) ? C2_L2_EVICT_LAST : C2_L2_NORMAL;
   if (!g_i8c2_attr) {
     DFB_CUDA_OK(cudaFuncSetAttribute(score_i8c2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C2_SMEM_BYTES));
