@@ -332,7 +332,7 @@ def kstar_build_line(prof, n_train, peaks):
     return None
   gbs = cands * n_train * 8.0 / (ms * 1e-3) * 1e-9
   hbm = float(peaks.get('hbm_gbs', 6564.2))
-  return {'kernel': 'kstar_fast_kernel<Matern, p=2, d=6> writing fp64 K_* rows', 'achieved_gbs': gbs,
+  return {'kernel': 'kstar_seg_kernel<Matern, p=2, d=6, ROWS64> (+ cand_prep, mu_reduce) writing fp64 K_* rows', 'achieved_gbs': gbs,
           'achieved_gbs_incl_padding': gbs * npad / n_train,
           'hbm_peak_gbs': hbm, 'frac_of_hbm': gbs / hbm, 'candidates_per_s': cands / (ms * 1e-3),
           'entries_per_s': cands * n_train / (ms * 1e-3), 'launch_ms_avg': ms / max(launches, 1),

@@ -1350,6 +1350,7 @@ int dfb_set_option(dfb_handle* h, const char* name, int64_t value) {
   if (strcmp(name, "i8_ts") == 0) { h->i8_ts = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_fuse") == 0) { h->i8_fuse = value ? 1 : 0; return 0; }
   if (strcmp(name, "kstar_seg") == 0) { h->kstar_seg = value ? 1 : 0; return 0; }
+  if (strcmp(name, "kstar_rows64") == 0) { h->kstar_rows64 = value ? 1 : 0; return 0; }
   if (strcmp(name, "kstar_overlap") == 0) { h->kstar_overlap = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_unguarded") == 0) { h->i8_unguarded = value ? 1 : 0; return 0; }
   if (strcmp(name, "i8_impl") == 0) {

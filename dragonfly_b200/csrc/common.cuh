@@ -140,6 +140,7 @@ struct dfb_handle {
   int i8_unguarded = 0;       // diagnostics: use the int8 path even when its a-priori bound exceeds the limit (the error sweep)
   int i8_fuse = 1;            // K_* kernel emits the digit planes itself (no fp64 K_* round trip)
   int kstar_seg = 1;          // second-generation digit kernel (kstar_seg_kernel) where it applies
+  int kstar_rows64 = 1;       // ... and its fp64-row form for the materialising K_* build of the fp64 scoring paths
   int kstar_overlap = 0;      // option: chunk c+1's K_* on a second stream while chunk c is contracted (api.cu: run_chunks)
   int i8_ts = 0;              // 1 = A digits staged in tensor memory (tcgen05.cp + TS-form MMA)
   int8_t* Wi8 = nullptr;      // [6][npad][npad]

@@ -42,6 +42,8 @@ int debug_set_trace(void* buf, long long cap_records) {
 
 namespace dfb {
 
+#define DFB_TRY_RET(expr) do { int _r = (expr); if (_r != 0) return _r; } while (0)
+
 // ================================================================================================
 // Kernel evaluation in the reference's operation order (include/dfb200.h, "kernel descriptor").
 // ================================================================================================
@@ -688,11 +690,14 @@ struct KsegArgs {
   double cdig;       // 2^-F 2^39: kernel value -> q
   double cval;       // post * pre * scale (* Gamma(p+1)/Gamma(2p+1)): the constant factors of the kernel, fused
   double s8, ms2, c0, c1, c2;         // ms2 = -sqrt(2 nu)
-  double* mu_part; int64_t ld_mu;
+  double* mu_part; int64_t ld_mu;       // mu_part may be NULL (no mu wanted)
   const int* abort_count; int abort_cap;
+  double* rows64; int64_t ld64;         // ROWS64 variant
 };
 
-template <int KIND, int P, int D>
+// ROWS64 = true: the same kernel writing the fp64 K_* rows (g.rows64, leading dimension g.ld64) instead of the digit
+// planes -- the materialising build of the fp64 scoring path, dfb_eval and the Thompson-sampling blocks.
+template <int KIND, int P, int D, bool ROWS64>
 __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
   if (g.abort_count != nullptr && *g.abort_count > g.abort_cap) return;
   constexpr int CP = (D + 2) & ~1;
@@ -821,7 +826,16 @@ __global__ void __maxnreg__(KS_MAXREG) kstar_seg_kernel(const KsegArgs g) {
       keep += __shfl_xor_sync(0xffffffffu, keep, 4);
       keep += __shfl_xor_sync(0xffffffffu, keep, 2);
       keep += __shfl_xor_sync(0xffffffffu, keep, 1);
-      if ((lane & 15) == 0) g.mu_part[(int64_t)blk * g.ld_mu + r + (lane >> 4)] = keep;
+      if ((lane & 15) == 0 && g.mu_part != nullptr) g.mu_part[(int64_t)blk * g.ld_mu + r + (lane >> 4)] = keep;
+    }
+    if (ROWS64) {
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        double2 o;
+        o.x = v[2 * rr]; o.y = v[2 * rr + 1];
+        *reinterpret_cast<double2*>(g.rows64 + (r + rr) * g.ld64 + j) = o;
+      }
+      continue;
     }
     // digits: word of chain c = bytes (a4, a3, a2, a1), a0 in the low byte of the high word; two points per 16-bit store
 #pragma unroll
@@ -2019,7 +2033,7 @@ int launch_kstar_i8(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kern
 }
 
 // Second-generation K_* digit path (kstar_seg_kernel): cand_prep -> segments -> mu.  Returns 1 in *emitted when it ran.
-template <int KIND, int P>
+template <int KIND, int P, bool ROWS64>
 static bool launch_kseg_d(dfb_handle* h, int d, const dfb_kernel_desc* d_desc, const double* Xc, int64_t m, int dc,
                           int64_t m_rows, double* cprep, double* kss_out, const KsegArgs& a, int n_seg) {
   const dim3 grid((unsigned)((n_seg + KS_WARPS - 1) / KS_WARPS), (unsigned)((m_rows + KS_ROWS - 1) / KS_ROWS));
@@ -2031,12 +2045,12 @@ static bool launch_kseg_d(dfb_handle* h, int d, const dfb_kernel_desc* d_desc, c
     static bool attr_set = false;                                                                                    \
     if (!attr_set) {                                                                                                 \
       cudaFuncSetAttribute(cand_prep_kernel<KIND, P, DD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      \
-      cudaFuncSetAttribute(kstar_seg_kernel<KIND, P, DD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      \
+      cudaFuncSetAttribute(kstar_seg_kernel<KIND, P, DD, ROWS64>, cudaFuncAttributePreferredSharedMemoryCarveout, ROWS64 ? -1 : 100); \
       cudaFuncSetAttribute(mu_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);                   \
       attr_set = true;                                                                                               \
     }                                                                                                                \
     cand_prep_kernel<KIND, P, DD><<<pblocks, 128, 0, h->stream>>>(d_desc, Xc, m, dc, m_rows, cprep, kss_out);        \
-    kstar_seg_kernel<KIND, P, DD><<<grid, KS_WARPS * 32, 0, h->stream>>>(a);                                         \
+    kstar_seg_kernel<KIND, P, DD, ROWS64><<<grid, KS_WARPS * 32, 0, h->stream>>>(a);                                 \
     return true;                                                                                                     \
   }
   switch (d) {
@@ -2070,10 +2084,10 @@ int launch_kstar_seg(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_ker
   const int n_seg = (int)(n_write / KS_BLK);             // 64-point blocks, one per warp
   bool ok = false;
 #define DFB_KS_ARGS h, f.n_dims, d_desc, Xc, m, dc, m_rows, cprep, kss_out, a, n_seg
-  if (f.kind == DFB_BASE_SE) ok = launch_kseg_d<DFB_BASE_SE, 0>(DFB_KS_ARGS);
-  else if (f.p == 0) ok = launch_kseg_d<DFB_BASE_MATERN, 0>(DFB_KS_ARGS);
-  else if (f.p == 1) ok = launch_kseg_d<DFB_BASE_MATERN, 1>(DFB_KS_ARGS);
-  else ok = launch_kseg_d<DFB_BASE_MATERN, 2>(DFB_KS_ARGS);
+  if (f.kind == DFB_BASE_SE) ok = launch_kseg_d<DFB_BASE_SE, 0, false>(DFB_KS_ARGS);
+  else if (f.p == 0) ok = launch_kseg_d<DFB_BASE_MATERN, 0, false>(DFB_KS_ARGS);
+  else if (f.p == 1) ok = launch_kseg_d<DFB_BASE_MATERN, 1, false>(DFB_KS_ARGS);
+  else ok = launch_kseg_d<DFB_BASE_MATERN, 2, false>(DFB_KS_ARGS);
 #undef DFB_KS_ARGS
   if (!ok) return 0;
   h->launches += 2;
@@ -2087,12 +2101,62 @@ int launch_kstar_seg(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_ker
   return 0;
 }
 
+// fp64-row form of the segment kernel: K_* rows of m candidates (rows m .. m_rows-1 zero) + mu + k(x*,x*).  Served when the
+// candidate side uses candidate coordinates and the shapes are the padded ones of the scoring paths; returns 0 in *done
+// otherwise (the caller falls back to kstar_fast_kernel / kstar_kernel).
+int launch_kstar_rows64(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc, const double* xsT,
+                        const double* nrm, int64_t npad_tr, const double* alpha, const double* Xc, int64_t m, int dc,
+                        int64_t m_rows, double* Ks, int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const,
+                        double* mu, double* kss_out, int* done) {
+  *done = 0;
+  const dfb_factor_desc& f = desc.factors[0];
+  if (!(h->kstar_fast && h->kstar_seg && desc.n_terms == 1 && desc.n_factors == 1 && f.n_dims <= 8 && f.slot_off == 0 &&
+        (f.kind == DFB_BASE_SE || f.p <= 2) && n_write % KS_BLK == 0 && npad_tr % 2 == 0 && m_rows % 2 == 0 && ldk % 2 == 0 &&
+        m_rows <= h->chunk && (reinterpret_cast<uintptr_t>(Ks) & 15) == 0 && h->cprep != nullptr &&
+        (alpha == nullptr || (reinterpret_cast<uintptr_t>(alpha) & 15) == 0)))
+    return 0;
+  const int n_seg = (int)(n_write / KS_BLK);
+  const bool want_mu = (mu != nullptr) && n_seg <= (int)(h->npad_max / KS_BLK) + 2;
+  if (mu != nullptr && !want_mu) return 0;
+  KsegArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xsT = xsT; a.nrm = nrm; a.alpha = alpha; a.npad_tr = npad_tr; a.n_valid = n_valid; a.cprep = h->cprep; a.m_rows = m_rows;
+  a.n_write = n_write;
+  a.cval = desc.post_scale * desc.term_pre_scale[0] * f.scale * (f.kind == DFB_BASE_MATERN ? f.gamma_ratio : 1.0);
+  a.s8 = f.s8; a.ms2 = -f.s2; a.c0 = f.coeffs[0]; a.c1 = f.coeffs[1]; a.c2 = f.coeffs[2];
+  a.mu_part = want_mu ? h->mu_part : nullptr; a.ld_mu = h->chunk;
+  a.rows64 = Ks; a.ld64 = ldk;
+  bool ok = false;
+#define DFB_KS_ARGS h, f.n_dims, d_desc, Xc, m, dc, m_rows, h->cprep, kss_out, a, n_seg
+  if (f.kind == DFB_BASE_SE) ok = launch_kseg_d<DFB_BASE_SE, 0, true>(DFB_KS_ARGS);
+  else if (f.p == 0) ok = launch_kseg_d<DFB_BASE_MATERN, 0, true>(DFB_KS_ARGS);
+  else if (f.p == 1) ok = launch_kseg_d<DFB_BASE_MATERN, 1, true>(DFB_KS_ARGS);
+  else ok = launch_kseg_d<DFB_BASE_MATERN, 2, true>(DFB_KS_ARGS);
+#undef DFB_KS_ARGS
+  if (!ok) return 0;
+  h->launches += 2;
+  DFB_CUDA_OK(cudaGetLastError());
+  if (want_mu) {
+    mu_reduce_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(h->mu_part, n_seg, h->chunk, m, mean_const, mu);
+    h->launches++;
+    DFB_CUDA_OK(cudaGetLastError());
+  }
+  *done = 1;
+  return 0;
+}
+
 int launch_kstar(dfb_handle* h, const dfb_kernel_desc* d_desc, const dfb_kernel_desc& desc,
                  int cand_uses_train_coords, const double* xsT, const double* nrmT, int64_t npad_tr,
                  const double* alpha, const double* Xc, int64_t m, int dc, int64_t m_rows, double* Ks,
                  int64_t ldk, int64_t n_valid, int64_t n_write, double mean_const, double* mu,
                  double* kss_out) {
   if (m_rows <= 0) return 0;
+  if (!cand_uses_train_coords && h->kstar_rows64) {
+    int done = 0;
+    DFB_TRY_RET(launch_kstar_rows64(h, d_desc, desc, xsT, nrmT, npad_tr, alpha, Xc, m, dc, m_rows, Ks, ldk, n_valid, n_write,
+                                    mean_const, mu, kss_out, &done));
+    if (done) return 0;
+  }
   // fast path: plain SE / Matern(p <= 2) on <= 8 coordinates
   if (h->kstar_fast && desc.n_terms == 1 && desc.n_factors == 1 && desc.factors[0].n_dims <= 8 &&
       desc.factors[0].slot_off == 0 && (desc.factors[0].kind == DFB_BASE_SE || desc.factors[0].p <= 2) &&

@@ -52,7 +52,11 @@ def test_pipeline_and_tile_order_options_do_not_change_results(B, gp1500):
     results[name] = gp._fused_score(acq, C)
     post.set_option('kstar_overlap', 0); post.set_option('i8_c2_group', 0); post.set_option('kstar_seg', 1)
   for name, r in results.items():
-    assert r[1] == base[1] and r[0] == base[0], (name, r[:2], base[:2])
+    assert r[1] == base[1], (name, r[:2], base[:2])
+    if name.startswith('old_kstar'):     # kstar_seg = 0 also re-scores through the reference-order fp64 K_* kernel: ulps apart
+      assert abs(r[0] - base[0]) <= 1e-13 * abs(base[0]), (name, r[:2], base[:2])
+    else:
+      assert r[0] == base[0], (name, r[:2], base[:2])
   # against pure fp64
   post.set_option('score_impl', 0)
   exact = gp._fused_score(acq, C)
