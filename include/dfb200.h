@@ -294,8 +294,8 @@ int dfb_debug_trace(void* buf_dev, int64_t cap_records);
  *                     and finally checks the int8 scores of that shortlist against the fp64 ones: a candidate
  *                     outside its allowance voids the screen and the call is redone in fp64 (queries
  *                     "last_selfcheck_violations", "last_selfcheck_ratio").  The bound (api.cu: i8_sigma2_bound) is
- *                     a sqrt(n) rounding-error model with a 9x margin over every measured maximum
- *                     (profiles/r02_i8_bound_sweep.json), not a worst-case bound.  The screen is skipped when the
+ *                     a sqrt(n) rounding-error model validated by a committed sweep (profiles/r02_i8_bound_sweep.json:
+ *                     480 configurations, worst measured / bound 0.28), not a worst-case bound.  The screen is skipped when the
  *                     bound exceeds 5e-9 ABSOLUTE (half the 1e-8 sigma^2 contract, whatever the kernel scale;
  *                     query "i8_bound_limit") or n < 1024.
  *  "i8_impl"    : which tcgen05 kernel the int8 path uses (switching re-slices W: layouts differ):
@@ -316,12 +316,21 @@ int dfb_debug_trace(void* buf_dev, int64_t cap_records);
  *                 bit-identical results), 0 = one stream, step after step.
  *  "small_eval" : 1 (default) = dfb_eval of <= 32 points computes |L^-1 k_*|^2 by streaming the rows of W once (one
  *                 warp per row, HBM-bound) instead of spending 128-wide DMMA tiles on them; 0 = tile kernels always.
+ *  "kstar_seg"  : 1 (default) = second-generation K_* kernels (kstar_seg_kernel: training-stationary, digits from one FMA) for
+ *                 plain SE / Matern on <= 8 dims; 0 = the round-1 kernels in the reference's operation order.
+ *  "kstar_rows64": 1 (default) = the fp64 K_* rows of the fp64 scoring paths come from kstar_seg_kernel's row form too.
+ *  "kstar_overlap": 1 = K_* of chunk c+1 on a second stream beside the contraction of chunk c (two-stream pipeline with
+ *                 double-buffered digit planes); default 0 -- no net gain on B200.
+ *  "i8_c2_group": candidate tiles per group of the CTA-pair kernel's tile order; 0 (default) = chosen per geometry by
+ *                 simulating the static deal (balance first, then the least HBM traffic); query "last_c2_group".
+ *  "i8_l2_hint" : L2 eviction priorities of that kernel's TMA loads: 0 (default) none, 1 = K_* digits evict-last,
+ *                 2 = also W digits evict-first (measured neutral / slower).
  *  "kstar_fast", "tma_cb_group", "i8_cb_group": kernel-selection / scheduling knobs used by tools/. */
 int dfb_set_option(dfb_handle* h, const char* name, int64_t value);
 /* Diagnostics: "i8_sigma2_bound", "i8_bound_limit", "i8_ready", "i8_impl", "i8_radix256", "score_impl",
  * "last_used_i8", "last_shortlist" (-1 = overflow -> fp64 pass), "last_selfcheck_violations" (> 0: the int8 screen
  * was voided and the call redone in fp64), "last_selfcheck_ratio" (max |s_int8 - s_fp64| / allowance over the last
- * shortlist; the model's margin is its inverse). */
+ * shortlist; the model's margin is its inverse), "chunk", "last_c2_group", "last_overlapped". */
 int dfb_query(dfb_handle* h, const char* name, double* out);
 
 /* Per-kernel-class device timing with CUDA events on the handle's stream (bench.py's roofline):
