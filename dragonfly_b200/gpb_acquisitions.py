@@ -158,7 +158,10 @@ def _maximise_streamed(score, bounds, max_evals, slab, unit=0):
     try:
       for k, (r0, rows) in enumerate(starts):
         raw = np.random.random((rows, dim))
-        if pinned is not None and (min(hi_r, r0 + rows) > max(lo_r, r0)):
+        if not min(hi_r, r0 + rows) > max(lo_r, r0):
+          q.put((r0, None))                            # another rank's rows: drawn (the stream must advance), not mapped
+          continue
+        if pinned is not None:
           pts = pinned[k % len(pinned)][:rows]
           np.multiply(raw, width, out=pts)             # map_to_bounds: pts * (hi - lo) + lo, written in place
           np.add(pts, low, out=pts)
@@ -183,6 +186,8 @@ def _maximise_streamed(score, bounds, max_evals, slab, unit=0):
     if err is not None:
       continue            # keep draining: the global RNG must end where the reference leaves it
     r0, pts = item
+    if pts is None:
+      continue
     a, b = max(lo_r, r0), min(hi_r, r0 + len(pts))
     if b <= a:
       continue
