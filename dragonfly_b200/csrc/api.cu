@@ -570,6 +570,38 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
   // (chunk x DFB_MAX_SLOTS doubles), so a 6-column candidate matrix needs 1 copy per ~21 chunks
   const int64_t stage_rows = (Mc * DFB_MAX_SLOTS / dc) / Mc * Mc;
   int64_t staged_lo = 0, staged_hi = 0;
+  // Page-locked host candidates (what the streamed `rand` maximiser hands over): the staging buffer is used as two halves
+  // and the copy of batch b+1 runs on a copy stream while batch b is scored (ev_cp: copy done, ev_free: every stage
+  // that reads the half is done).  Pageable memory keeps the single-buffer copy on the compute stream: its
+  // cudaMemcpyAsync would block the host on the half's ev_free and stall the launches of the batch in flight.
+  const int64_t half_rows = (stage_rows / Mc / 2) * Mc;
+  bool dbuf = false;
+  if (space == DFB_HOST && half_rows >= Mc && m > half_rows) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, Xc) == cudaSuccess && pa.type == cudaMemoryTypeHost) dbuf = true;
+    cudaGetLastError();                                   // an unregistered pointer may leave a sticky-free error behind
+  }
+  if (dbuf) {
+    if (h->cp_stream == nullptr) {
+      DFB_CUDA_OK(cudaStreamCreateWithFlags(&h->cp_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        DFB_CUDA_OK(cudaEventCreateWithFlags(&h->cp_done[i], cudaEventDisableTiming));
+        DFB_CUDA_OK(cudaEventCreateWithFlags(&h->cp_free[i], cudaEventDisableTiming));
+      }
+      DFB_CUDA_OK(cudaEventCreateWithFlags(&h->cp_fork, cudaEventDisableTiming));
+    }
+    DFB_CUDA_OK(cudaEventRecord(h->cp_fork, s_user));     // the copy stream starts after everything already on the caller's stream
+    DFB_CUDA_OK(cudaStreamWaitEvent(h->cp_stream, h->cp_fork, 0));
+  }
+  auto issue_copy = [&](int64_t bi) -> int {               // batch bi -> half bi % 2, on the copy stream
+    const int64_t lo = bi * half_rows;
+    const int64_t hi = (m - lo < half_rows) ? m : lo + half_rows;
+    if (bi >= 2) DFB_CUDA_OK(cudaStreamWaitEvent(h->cp_stream, h->cp_free[bi & 1], 0));
+    DFB_CUDA_OK(cudaMemcpyAsync(h->stage + (bi & 1) * half_rows * dc, Xc + lo * dc, sizeof(double) * (hi - lo) * dc,
+                                cudaMemcpyHostToDevice, h->cp_stream));
+    DFB_CUDA_OK(cudaEventRecord(h->cp_done[bi & 1], h->cp_stream));
+    return 0;
+  };
   const int64_t n_chunks = (m + Mc - 1) / Mc;
   const double* xc_of[2] = {nullptr, nullptr};
 
@@ -581,7 +613,15 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
     h->stream = s_k;
     if (pipelined && ci >= 2) DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->ks_g[b], 0));     // G(ci-2) is done with buffer b
     const double* xc_dev;
-    if (space == DFB_HOST) {
+    if (space == DFB_HOST && dbuf) {
+      const int64_t bi = c0 / half_rows;
+      if (c0 % half_rows == 0) {                           // first chunk of a batch
+        if (bi == 0) DFB_TRY(issue_copy(0));
+        if ((bi + 1) * half_rows < m) DFB_TRY(issue_copy(bi + 1));
+        DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->cp_done[bi & 1], 0));
+      }
+      xc_dev = h->stage + (bi & 1) * half_rows * dc + (c0 - bi * half_rows) * dc;
+    } else if (space == DFB_HOST) {
       if (c0 >= staged_hi) {
         // the shortlist collection of earlier chunks reads the staged rows: wait for the latest G stage
         if (pipelined && ci >= 1) DFB_CUDA_OK(cudaStreamWaitEvent(s_k, h->ks_g[(ci - 1) & 1], 0));
@@ -690,6 +730,11 @@ static int run_chunks(dfb_handle* h, const dfb_acq_desc& acq, const double* Xc, 
         DFB_CUDA_OK(cudaMemcpyAsync(out.score + c0, sc_dev, sizeof(double) * mc, cudaMemcpyDeviceToHost, s_g));
     }
     if (pipelined) DFB_CUDA_OK(cudaEventRecord(h->ks_g[b], s_g));
+    if (dbuf) {                                            // last chunk of its batch: the half may be overwritten
+      const int64_t bi = c0 / half_rows;
+      const int64_t b_hi = (m - bi * half_rows < half_rows) ? m : (bi + 1) * half_rows;
+      if (c0 + Mc >= b_hi) DFB_CUDA_OK(cudaEventRecord(h->cp_free[bi & 1], s_g));
+    }
     return 0;
   };
 
@@ -760,6 +805,10 @@ void dfb_destroy(dfb_handle* h) {
     cudaStreamDestroy(h->fs_hi); cudaStreamDestroy(h->fs_lo);
     cudaEventDestroy(h->fe_fork); cudaEventDestroy(h->fe_panel); cudaEventDestroy(h->fe_rest);
     cudaEventDestroy(h->fe_join_hi); cudaEventDestroy(h->fe_join_lo);
+  }
+  if (h->cp_stream != nullptr) {
+    cudaStreamDestroy(h->cp_stream); cudaEventDestroy(h->cp_fork);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(h->cp_done[i]); cudaEventDestroy(h->cp_free[i]); }
   }
   if (h->ks_stream != nullptr) {
     cudaStreamDestroy(h->ks_stream); cudaStreamDestroy(h->gs_stream); cudaEventDestroy(h->ks_fork); cudaEventDestroy(h->ks_join);

@@ -155,6 +155,8 @@ struct dfb_handle {
   cudaStream_t ks_stream = nullptr;   // K stage (least priority)
   cudaStream_t gs_stream = nullptr;   // G stage (greatest priority: the persistent kernel's CTAs are placed first)
   cudaEvent_t ks_join = nullptr;
+  cudaStream_t cp_stream = nullptr;   // H2D copies of page-locked host candidates, one batch ahead (api.cu: run_chunks)
+  cudaEvent_t cp_fork = nullptr, cp_done[2] = {nullptr, nullptr}, cp_free[2] = {nullptr, nullptr};
   cudaEvent_t ks_fork = nullptr, ks_k[2] = {nullptr, nullptr}, ks_g[2] = {nullptr, nullptr};
   CUtensorMap tmK2h_b, tmK3h_b, tmK1c_b;   // maps of the second digit buffer
   int64_t last_overlapped = 0;             // diagnostics: chunks of the last call that went through the two-stream pipeline

@@ -172,3 +172,29 @@ def test_cartesian_product_gp_against_the_reference(B):
   acq = B.device.make_acq_desc('ucb', beta=2.0)
   best, idx, _ = gp._fused_score(acq, g['C'], mean_const=mc)
   assert idx == int(np.argmax(g['mu'] + 2.0 * g['sd']))
+
+
+def test_page_locked_host_candidates_are_copied_one_batch_ahead(B, gp1500):
+  """ Host candidates in page-locked memory take the double-buffered staging path of run_chunks (copy of batch b+1 on a
+      copy stream while batch b is scored): same results as device-resident and as pageable candidates, bit for bit,
+      over several batches, for the fused arg-max and for eval. """
+  w, gp = gp1500
+  post = gp._post
+  chunk = int(post.query('chunk'))
+  M = 25 * chunk + 1234                       # > 2 batches of 10 chunks, ragged tail
+  pinned = B.torch.empty((M, 6), dtype=B.torch.float64, pin_memory=True)
+  Cp = pinned.numpy()
+  Cp[:] = np.random.RandomState(12).random_sample((M, 6))
+  Cpage = Cp.copy()
+  Cd = B.torch.from_numpy(Cpage).cuda()
+  acq = B.device.make_acq_desc('ucb', beta=2.0)
+  want = post.score_argmax(acq, Cd, mean_const=w['mean_const'])
+  for overlap in (0, 1):
+    post.set_option('kstar_overlap', overlap)
+    got_pinned = post.score_argmax(acq, Cp, mean_const=w['mean_const'])
+    got_page = post.score_argmax(acq, Cpage, mean_const=w['mean_const'])
+    assert got_pinned[:2] == want[:2] and got_page[:2] == want[:2], (overlap, got_pinned[:2], got_page[:2], want[:2])
+  post.set_option('kstar_overlap', 0)
+  mu_d, sd_d = post.eval(Cd, mean_const=w['mean_const'])
+  mu_p, sd_p = post.eval(Cp, mean_const=w['mean_const'])
+  assert (mu_p == mu_d.cpu().numpy()).all() and (sd_p == sd_d.cpu().numpy()).all()
