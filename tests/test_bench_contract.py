@@ -50,3 +50,21 @@ def test_reference_arm_other_ranks_print_nothing():
                         '--steps', '1', '--warmup', '1'], capture_output=True, text=True, env=env, timeout=300,
                        cwd=ROOT)
   assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_reference_arm_of_every_config():
+  """ `bench.py --impl reference --config c2..c5`: one JSON line each, strong-scaling label, a port-kind cpu_baseline. """
+  import pytest
+  for cfg in ('c2', 'c3', 'c4', 'c5'):
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', cfg, '--steps', '1',
+                          '--warmup', '0', '--n-train', '200', '--cpu-sample', '700', '--gpus', '1'],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (cfg, out.stderr[-2000:])
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, (cfg, out.stdout)
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['scaling'] == 'strong' and line['value'] > 0, cfg
+    assert line['config']['n_train'] == 200 and 'workload' in line['config'] and 'model' not in line['config']
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
